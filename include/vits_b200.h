@@ -1,0 +1,147 @@
+/*
+ * vits_b200.h -- C ABI of the B200-native VITS synthesis engine (libvits_b200.so).
+ *
+ * Drop-in boundary: this library replaces the third-party
+ * onnxruntime.InferenceSession that phoonnx's TTSVoice holds
+ * (reference: phoonnx/voice.py:105-107 field, :167-171 construction, :347 get_inputs(),
+ * :374-377 run()).  ORT's own C API is NOT re-implemented; these entry points are what a
+ * ctypes / cffi binding on the reference side calls instead, and what
+ * phoonnx_b200/engine.py binds.  Plain pointers and sizes only -- no torch / C++ types.
+ *
+ * All functions return 0 on success, a negative VITS_E_* code on failure; the message is
+ * available from vits_last_error().  There is NO CPU fallback: every entry point that
+ * computes fails with VITS_E_CUDA when no sm_100 device is usable.
+ *
+ * Threading: one handle == one GPU + one stream.  Calls on one handle are serialised by
+ * an internal mutex; different handles are fully concurrent (ORT's run() is re-entrant,
+ * voice.py:374 is called serially by TTSVoice.synthesize).
+ */
+#ifndef VITS_B200_H
+#define VITS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITS_B200_ABI_VERSION 1
+
+enum {
+    VITS_OK = 0,
+    VITS_E_INVALID = -1,  /* bad argument (shape, id >= n_vocab, sid >= n_speakers, ...) -> ValueError  */
+    VITS_E_CUDA = -2,     /* CUDA runtime failure / no device                              -> RuntimeError */
+    VITS_E_STATE = -3,    /* call order violated (decode before prepare, missing tensor)   -> RuntimeError */
+    VITS_E_NOMEM = -4
+};
+
+typedef struct vits_handle vits_handle;
+
+/* Architecture of the voice.  The exported file carries no hyper-parameters
+ * (export_onnx.py:335-345 stores only n_speakers/n_vocab/sample_rate), so the host-side
+ * loader infers them from initializer shapes and passes them here.
+ * Field meaning follows phoonnx_train/vits/models.py:527-615. */
+#define VITS_MAX_UPS 8
+#define VITS_MAX_RBK 8
+#define VITS_MAX_DIL 4
+#define VITS_MAX_FLOWS 8
+typedef struct vits_arch {
+    int32_t n_vocab, hidden, inter, filter, n_heads, n_layers, enc_kernel, window;
+    int32_t n_speakers, gin;
+    int32_t use_sdp, dp_filter, dp_kernel, dds_layers, n_cflows, cflows[VITS_MAX_FLOWS], num_bins;
+    int32_t n_flow, flow_layers[VITS_MAX_FLOWS], wn_layers, wn_kernel, wn_dilation_rate;
+    int32_t resblock_type;                 /* 1 = ResBlock1 (high), 2 = ResBlock2          */
+    int32_t n_ups, up_rates[VITS_MAX_UPS], up_kernels[VITS_MAX_UPS], up_init;
+    int32_t n_rbk, rb_kernels[VITS_MAX_RBK], rb_ndil[VITS_MAX_RBK], rb_dilations[VITS_MAX_RBK][VITS_MAX_DIL];
+    int32_t sample_rate;
+} vits_arch;
+
+/* ABI / build information: returns VITS_B200_ABI_VERSION. */
+int vits_abi_version(void);
+
+/* Replaces InferenceSession(...) construction (voice.py:167-171): binds device `device_id`,
+ * creates the stream and an empty weight table. */
+int vits_create(const vits_arch* arch, int device_id, vits_handle** out);
+
+/* Upload one packed weight blob (already in kernel layout; packing is done by the
+ * host-side loader phoonnx_b200/packing.py from the exported initializers).
+ * dtype: 0 = float32, 1 = bfloat16 (raw uint16), 2 = int32. */
+int vits_upload(vits_handle* h, const char* name, const void* data, size_t nbytes, int dtype);
+
+/* Resolve every tensor the architecture needs; fails with VITS_E_STATE naming the first
+ * missing blob. */
+int vits_finalize(vits_handle* h);
+
+/* Options.  "precision": 0 = fp32 CUDA cores everywhere (parity mode),
+ *                        1 = bf16 tcgen05 tensor cores for the decoder / flow contractions
+ *                            (fp32 accumulate, fp32 everywhere else).
+ *           "max_chunk_frames": frame budget of one decoder pass (workspace sizing). */
+int vits_set_option(vits_handle* h, const char* key, double value);
+
+/* ---- the hot path: replaces session.run(None, feed) (voice.py:374-377) --------------
+ *
+ * Phase 1 (text side): embedding, text encoder, duration predictor, length regulation.
+ *   ids          packed phoneme ids, sum(lengths) values      ("input", voice.py:350)
+ *   lengths      [B]                                          ("input_lengths", voice.py:351)
+ *   scales       {noise_scale, length_scale, noise_w}         ("scales", voice.py:364-367)
+ *   sid          [B] or NULL (single-speaker)                 ("sid", voice.py:370)
+ *   noise_dp     test-only: [B][2][dp_stride] N(0,1) samples replacing the
+ *                RandomNormalLike of models.py:111, or NULL -> Philox(seed)
+ *   logw_override test-only: packed [sum(lengths)] log-durations replacing the duration
+ *                predictor output (bit-exactness tests of the integer path), or NULL
+ * Outputs: total_frames and, per utterance, y_lengths[B] (frames).  Audio length of
+ * utterance b is y_lengths[b] * hop samples.
+ */
+int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int32_t B,
+                 const float scales[3], const int64_t* sid, const float* noise_dp,
+                 int64_t dp_stride, const float* logw_override, uint64_t seed,
+                 int64_t* y_lengths, int64_t* total_frames);
+
+/* Phase 2 (frame side): prior expansion + sampling, coupling flow (reverse), HiFi-GAN.
+ *   noise_z      test-only: [B][inter][z_stride] N(0,1) samples replacing randn_like of
+ *                models.py:718, or NULL -> Philox(seed)
+ *   out_kind     0: keep audio on the device only (throughput timing)
+ *                1: float32 to host buffer `out` (packed, utterance b at sample offset
+ *                   hop * sum(y_lengths[:b]))
+ *                2: int16 to host buffer after the caller-side post-processing of
+ *                   voice.py:271-282 + AudioChunk.audio_int16_array voice.py:88-91
+ *                   (peak-normalise per utterance, volume, clip, x32767) done on device
+ *   out_capacity number of samples `out` can hold (>= hop * total_frames)
+ */
+int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t out_kind,
+                void* out, int64_t out_capacity, float volume, int32_t normalize);
+
+/* Test / debugging: copy a stage tensor of the last prepare/decode to the host.
+ * names: "x" [sumT,H], "m_p" [sumT,C], "logs_p" [sumT,C], "logw" [sumT], "durations" (int32
+ * bits, [sumT]), "frame_index" (int32 bits, [frames of last chunk]), "z_p" / "z"
+ * [frames of last chunk, C].  Returns the element count written (<= capacity) or <0. */
+int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity_elems);
+
+/* Device-side timing of everything enqueued between start and stop on the handle's
+ * stream (CUDA events on the launching stream). */
+int vits_timer_start(vits_handle* h);
+int vits_timer_stop(vits_handle* h, float* elapsed_ms);
+
+/* Counters since creation: number of kernels of THIS library launched. */
+int64_t vits_launch_count(vits_handle* h);
+
+/* Device time (ms, CUDA events) of the decoder (HiFi-GAN) part of the last vits_decode
+ * calls since the last vits_timer_start, for the roofline of the dominant kernel family. */
+int vits_stage_ms(vits_handle* h, float* text_ms, float* flow_ms, float* dec_ms);
+
+/* Test hook: one convolution (single utterance of L rows, channel-last) through the production
+ * launch path -- use_tc = 0: fp32 CUDA-core kernel, 1: tcgen05 kernel.  `out` is [L, out_cols]
+ * and is read first when `accumulate` is set.  epi: 0 store, 1 gate (out_cols = n/2),
+ * 2 split (first n/2 columns accumulate into out[:, :n/2], the rest into out[:, n/2:]), 3 res - v. */
+int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, const int* taps, int ntaps,
+                   const float* w32, const uint16_t* wtc, const float* bias, int n, int in_act, float in_slope,
+                   int epi, const float* res, int accumulate, float out_div, int out_act, float* out, int out_cols);
+
+const char* vits_last_error(vits_handle* h);
+void vits_destroy(vits_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITS_B200_H */

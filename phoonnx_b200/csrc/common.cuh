@@ -1,0 +1,56 @@
+// Shared declarations for the B200 VITS engine kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define CONV_MAX_TAPS 16
+
+enum ConvEpi { EPI_STORE = 0, EPI_GATE = 1, EPI_SPLIT = 2, EPI_SUBFROM = 3 };
+enum OutAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+// One 1-D convolution over a packed, channel-last varlen batch, expressed as an implicit
+// GEMM:  out[t, n] = epi( sum_tap sum_ci act(x[t + toff[tap], ci]) * W[tap][ci][n] + bias[n] ).
+// Rows of utterance b are [cu[b]*rate, cu[b+1]*rate); samples outside the utterance read 0
+// (the zero padding of every Conv1d on the path; the decoder is unmasked, models.py:720,
+// so B=1 semantics == zero padding at utterance edges).
+struct ConvArgs {
+    const float* x;  int ldx;  int xcol;  int cin;
+    int ntaps;  int toff[CONV_MAX_TAPS];
+    const float* w;            // fp32 [ntaps][cin][npad]
+    const __nv_bfloat16* wtc;  // bf16 tcgen05 layout [ntaps][cin/8][npad16][8] (may be null)
+    int n;  int npad;          // npad: n rounded up to a multiple of 4 (fp32) ; npad16 to 16 (tc)
+    int npad16;
+    const float* bias;         // [npad] or null
+    const float* utab;  const int* uidx;  int utab_ld;   // per-utterance bias row utab[uidx[b]*utab_ld + n] or null
+    int in_act;  float in_slope;      // 1: leaky-relu(slope) applied to x on load
+    int epi;
+    const float* res;  int ldres;  int rescol;           // residual (added; SUBFROM: res - v)
+    int out_act;  float out_div;  int accumulate;
+    float* out;  int ldo;  int ocol;
+    float* out2;  int ldo2;  int ocol2;  int split;  int accumulate2;   // EPI_SPLIT: n >= split -> out2[n - split]
+    const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
+};
+
+__device__ __forceinline__ int find_segment(const int* __restrict__ offs, int B, int v) {
+    // largest b in [0, B) with offs[b] <= v   (offs is non-decreasing, offs[0] == 0)
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(offs + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v >= 0.f ? v : v * slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

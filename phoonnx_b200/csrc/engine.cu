@@ -1,0 +1,936 @@
+// libvits_b200: host-side orchestration of the VITS phoneme-ids -> audio hot path and its C ABI
+// (include/vits_b200.h).  What it replaces: the onnxruntime InferenceSession.run() call at
+// phoonnx/voice.py:374-377, whose arithmetic is SynthesizerTrn.infer
+// (phoonnx_train/vits/models.py:681-722).
+//
+// Execution model: one handle = one GPU = one stream.  All activations are packed varlen,
+// channel-last fp32 ([rows, C]); utterances never see each other's samples (B=1 semantics per
+// utterance, zero padding at utterance edges).  Phase 1 (vits_prepare) runs the text side and
+// ends with the only host sync of the path: the per-utterance frame counts.  Phase 2
+// (vits_decode) runs the frame side in chunks bounded by a frame budget.
+#include "../../include/vits_b200.h"
+#include "common.cuh"
+#include "kernels_f32.cuh"
+#include "conv_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBlob { void* p = nullptr; size_t bytes = 0; int dtype = 0; };
+
+struct ConvP {
+    const float* w = nullptr; const __nv_bfloat16* wtc = nullptr; const float* b = nullptr;
+    int cin = 0, n = 0, npad = 0, npad16 = 0, ntaps = 0; int toff[CONV_MAX_TAPS] = {0};
+};
+
+struct LnP { const float* g = nullptr; const float* b = nullptr; };
+struct DdsP { const float* dw_w; const float* dw_b; LnP ln1; ConvP pw; LnP ln2; int dil; };
+
+struct Buf {   // grow-only device buffer
+    void* p = nullptr; size_t cap = 0;
+};
+
+struct StagePair { cudaEvent_t a, b; int stage; };
+
+}  // namespace
+
+struct vits_handle {
+    vits_arch A;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::map<std::string, DevBlob> blobs;
+    std::map<std::string, double> opts;
+    bool finalized = false;
+    int precision = 0;
+    int64_t max_chunk_frames = 8192;
+    int64_t launches = 0;
+    int num_sms = 148;
+
+    // resolved weights
+    const float* emb = nullptr;
+    struct EncL { ConvP qkv, o, ffn1, ffn2; const float* rel_k; const float* rel_v; LnP ln1, ln2; };
+    std::vector<EncL> enc;
+    ConvP enc_proj;
+    ConvP dp_pre, dp_proj; std::vector<DdsP> dp_dds; const float* dp_cond_tab = nullptr;
+    struct CFlow { const float* pre_w; const float* pre_b; std::vector<DdsP> dds; ConvP proj; };
+    std::vector<CFlow> cflows;
+    float ea_m = 0.f, ea_logs = 0.f;
+    ConvP dpd_c1, dpd_c2, dpd_proj; LnP dpd_n1, dpd_n2;
+    struct FlowS { ConvP pre, post; std::vector<ConvP> in, rs; std::vector<const float*> cond_tab; int xcol, ocol; };
+    std::vector<FlowS> flows;
+    ConvP dec_pre; const float* dec_cond_tab = nullptr;
+    struct UpS { ConvP A, B; int rate, cout; };
+    std::vector<UpS> ups;
+    std::vector<std::vector<ConvP>> rb_c1, rb_c2;   // [resblock][conv]
+    const float* post_w = nullptr; int post_c = 0;
+
+    // text-side state of the last prepare
+    int B = 0; int R = 0;            // utterances, total ids
+    std::vector<int> h_cu_t, h_ylen, h_cu_y; std::vector<int> h_sid;
+    float scales[3] = {0.667f, 1.f, 0.8f};
+    uint64_t seed = 0, utt_counter = 0, utt_base = 0;
+    bool prepared = false;
+    int64_t total_frames = 0;
+    int last_chunk_frames = 0;
+
+    Buf ids, cu_t, tile_t, sid, x, y, qkv, att, ffn, stats, d0, d1, gdp, hp, z0, z1, logw, dur, cum, ylen;
+    Buf inj_dp, inj_z;
+    Buf chunk_meta, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp;
+
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    std::vector<StagePair> stage_events;
+    std::vector<cudaEvent_t> event_pool;
+    float stage_ms[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(vits_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return fail(h, VITS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+int ensure(vits_handle* h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~size_t(255);
+    if (b.p) { CK(h, cudaStreamSynchronize(h->stream)); CK(h, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    CK(h, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+template <class T> T* ptr(Buf& b) { return reinterpret_cast<T*>(b.p); }
+
+const DevBlob* find_blob(vits_handle* h, const std::string& name) {
+    auto it = h->blobs.find(name);
+    return it == h->blobs.end() ? nullptr : &it->second;
+}
+
+int need_f32(vits_handle* h, const std::string& name, const float** out, size_t min_elems) {
+    const DevBlob* b = find_blob(h, name);
+    if (!b) return fail(h, VITS_E_STATE, "missing weight blob '%s'", name.c_str());
+    if (b->dtype != 0 || b->bytes < min_elems * sizeof(float))
+        return fail(h, VITS_E_STATE, "weight blob '%s': wrong dtype/size (%zu bytes, need %zu)", name.c_str(), b->bytes,
+                    min_elems * sizeof(float));
+    *out = reinterpret_cast<const float*>(b->p);
+    return 0;
+}
+
+int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+// Resolve a conv: blobs "<name>.w" [ntaps][cin][npad] fp32, optional "<name>.b" [npad],
+// optional "<name>.wtc" bf16 [ntaps][cin/8][npad16][8].
+int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, const std::vector<int>& toff, bool bias) {
+    c.cin = cin; c.n = n; c.npad = rup(n, 4); c.npad16 = rup(n, 16); c.ntaps = (int)toff.size();
+    if (c.ntaps > CONV_MAX_TAPS) return fail(h, VITS_E_INVALID, "conv '%s': %d taps > %d", name.c_str(), c.ntaps, CONV_MAX_TAPS);
+    if (cin % 4) return fail(h, VITS_E_INVALID, "conv '%s': cin %d not a multiple of 4", name.c_str(), cin);
+    for (int i = 0; i < c.ntaps; i++) c.toff[i] = toff[i];
+    int rc = need_f32(h, name + ".w", &c.w, (size_t)c.ntaps * cin * c.npad);
+    if (rc) return rc;
+    c.b = nullptr;
+    if (bias) { rc = need_f32(h, name + ".b", &c.b, c.npad); if (rc) return rc; }
+    const DevBlob* t = find_blob(h, name + ".wtc");
+    c.wtc = nullptr;
+    if (t && t->dtype == 1 && cin % 16 == 0 && t->bytes >= (size_t)c.ntaps * cin * c.npad16 * 2)
+        c.wtc = reinterpret_cast<const __nv_bfloat16*>(t->p);
+    return 0;
+}
+
+std::vector<int> sym_taps(int k, int d) {   // Conv1d with "same" padding (k*d - d)/2, commons.py:17-18
+    std::vector<int> t(k);
+    for (int i = 0; i < k; i++) t[i] = (i - (k - 1) / 2) * d;
+    return t;
+}
+
+int mkln(vits_handle* h, LnP& l, const std::string& name, int C) {
+    int rc = need_f32(h, name + ".g", &l.g, C); if (rc) return rc;
+    return need_f32(h, name + ".b", &l.b, C);
+}
+
+int mkdds(vits_handle* h, std::vector<DdsP>& v, const std::string& name, int C) {
+    const vits_arch& A = h->A;
+    v.resize(A.dds_layers);
+    int dil = 1;
+    for (int i = 0; i < A.dds_layers; i++) {
+        DdsP& d = v[i];
+        std::string p = name + "." + std::to_string(i);
+        int rc;
+        if ((rc = need_f32(h, p + ".dw_w", &d.dw_w, (size_t)A.dp_kernel * C))) return rc;
+        if ((rc = need_f32(h, p + ".dw_b", &d.dw_b, C))) return rc;
+        if ((rc = mkln(h, d.ln1, p + ".ln1", C))) return rc;
+        if ((rc = mkconv(h, d.pw, p + ".pw", C, C, {0}, true))) return rc;
+        if ((rc = mkln(h, d.ln2, p + ".ln2", C))) return rc;
+        d.dil = dil;
+        dil *= A.dp_kernel;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------
+struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; int n64, n128, n256; int B; int rate; };
+
+ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out, int ldo, int ocol) {
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.ldx = ldx; a.xcol = xcol; a.cin = c.cin;
+    a.ntaps = c.ntaps; for (int i = 0; i < c.ntaps; i++) a.toff[i] = c.toff[i];
+    a.w = c.w; a.wtc = c.wtc; a.n = c.n; a.npad = c.npad; a.npad16 = c.npad16; a.bias = c.b;
+    a.in_act = 0; a.in_slope = 1.f; a.epi = EPI_STORE; a.out_act = ACT_NONE; a.out_div = 1.f;
+    a.out = out; a.ldo = ldo; a.ocol = ocol;
+    return a;
+}
+
+int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
+    a.cu = T.cu; a.B = T.B; a.rate = T.rate;
+    if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
+        a.tile_cu = T.t128; a.ntiles = T.n128;
+        if (T.n128 == 0) return 0;
+        cudaError_t e = conv_tc_launch(a, h->num_sms, h->stream);
+        if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc launch: %s", cudaGetErrorString(e));
+        h->launches++;
+        return 0;
+    }
+    a.tile_cu = T.t64; a.ntiles = T.n64;
+    if (T.n64 == 0) return 0;
+    dim3 grid(T.n64, (a.n + CF_TN - 1) / CF_TN);
+    k_conv_f32<<<grid, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_ln(vits_handle* h, const float* in, float* out, const LnP& ln, int rows, int C, int mode,
+              const DdsP* dw, const Tiles& T) {
+    if (C % 32 || C > 32 * LN_MAXV) return fail(h, VITS_E_INVALID, "LayerNorm width %d unsupported (multiple of 32, <= %d)", C, 32 * LN_MAXV);
+    if (rows == 0) return 0;
+    k_layernorm<<<(rows + 3) / 4, 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, C, mode,
+                                                         dw ? dw->dw_w : nullptr, dw ? dw->dw_b : nullptr,
+                                                         h->A.dp_kernel, dw ? dw->dil : 1, T.cu, T.B);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// DDSConv (modules.py:117-129): x updated in place; tmp1/tmp2 scratch [rows, C]
+int run_dds(vits_handle* h, std::vector<DdsP>& L, float* x, float* tmp1, float* tmp2, int rows, int C, const Tiles& T) {
+    for (auto& d : L) {
+        int rc;
+        if ((rc = launch_ln(h, x, tmp1, d.ln1, rows, C, 1, &d, T))) return rc;
+        ConvArgs a = base_args(d.pw, tmp1, C, 0, tmp2, C, 0);
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_ln(h, tmp2, x, d.ln2, rows, C, 2, nullptr, T))) return rc;
+    }
+    return 0;
+}
+
+cudaEvent_t get_event(vits_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void stage_begin(vits_handle* h, int stage) {
+    StagePair sp; sp.a = get_event(h); sp.b = get_event(h); sp.stage = stage;
+    cudaEventRecord(sp.a, h->stream);
+    h->stage_events.push_back(sp);
+}
+void stage_end(vits_handle* h) { cudaEventRecord(h->stage_events.back().b, h->stream); }
+void resolve_stage_events(vits_handle* h) {
+    for (auto& sp : h->stage_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess)
+            h->stage_ms[sp.stage] += ms;
+        h->event_pool.push_back(sp.a); h->event_pool.push_back(sp.b);
+    }
+    h->stage_events.clear();
+}
+
+// build per-rate tile tables on the host and upload them in one copy
+struct TileBuilder {
+    std::vector<int> host;
+    struct Ent { int rate; size_t o64, o128, o256; int n64, n128, n256; };
+    std::vector<Ent> ents;
+    size_t cu_off = 0; int B = 0;
+    void begin(const int* cu_local, int B_) {
+        B = B_; host.assign(cu_local, cu_local + B + 1); cu_off = 0; ents.clear();
+    }
+    void add(int rate) {
+        Ent e; e.rate = rate;
+        auto build = [&](int tm, int& n) {
+            size_t off = host.size();
+            int acc = 0;
+            for (int b = 0; b < B; b++) {
+                host.push_back(acc);
+                long rows = (long)(host[cu_off + b + 1] - host[cu_off + b]) * rate;
+                acc += (int)((rows + tm - 1) / tm);
+            }
+            host.push_back(acc); n = acc;
+            return off;
+        };
+        e.o64 = build(64, e.n64); e.o128 = build(128, e.n128); e.o256 = build(256, e.n256);
+        ents.push_back(e);
+    }
+    Tiles get(const int* dev, int rate) const {
+        for (auto& e : ents) if (e.rate == rate) {
+            Tiles t; t.cu = dev + cu_off; t.t64 = dev + e.o64; t.t128 = dev + e.o128; t.t256 = dev + e.o256;
+            t.n64 = e.n64; t.n128 = e.n128; t.n256 = e.n256; t.B = B; t.rate = rate; return t;
+        }
+        Tiles t; memset(&t, 0, sizeof t); return t;
+    }
+};
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int vits_abi_version(void) { return VITS_B200_ABI_VERSION; }
+
+int vits_create(const vits_arch* arch, int device_id, vits_handle** out) {
+    if (!arch || !out) return VITS_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_id < 0 || device_id >= ndev) return VITS_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return VITS_E_CUDA;
+    if (prop.major != 10) return VITS_E_CUDA;   // sm_100a only: no other code path exists
+    vits_handle* h = new vits_handle();
+    h->A = *arch; h->device = device_id; h->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h; return VITS_E_CUDA;
+    }
+    cudaEventCreate(&h->ev_t0); cudaEventCreate(&h->ev_t1);
+    *out = h;
+    return VITS_OK;
+}
+
+int vits_upload(vits_handle* h, const char* name, const void* data, size_t nbytes, int dtype) {
+    if (!h || !name || !data) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    DevBlob b; b.bytes = nbytes; b.dtype = dtype;
+    CK(h, cudaMalloc(&b.p, std::max<size_t>(nbytes, 16)));
+    CK(h, cudaMemcpy(b.p, data, nbytes, cudaMemcpyHostToDevice));
+    auto it = h->blobs.find(name);
+    if (it != h->blobs.end()) { cudaFree(it->second.p); it->second = b; } else h->blobs[name] = b;
+    h->finalized = false;
+    return VITS_OK;
+}
+
+int vits_set_option(vits_handle* h, const char* key, double value) {
+    if (!h || !key) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    std::string k(key);
+    if (k == "precision") {
+        if (value != 0 && value != 1) return fail(h, VITS_E_INVALID, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+        h->precision = (int)value;
+    } else if (k == "max_chunk_frames") {
+        if (value < 1) return fail(h, VITS_E_INVALID, "max_chunk_frames must be >= 1");
+        h->max_chunk_frames = (int64_t)value;
+    } else {
+        h->opts[k] = value;
+    }
+    return VITS_OK;
+}
+
+int vits_finalize(vits_handle* h) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const vits_arch& A = h->A;
+    const int H = A.hidden, C = A.inter, F = A.filter, Fd = A.dp_filter;
+    if (H % 32 || H > 256 || H % A.n_heads || (H / A.n_heads) % 4 || (H / A.n_heads) > 32 * ATT_MAX_DKM)
+        return fail(h, VITS_E_INVALID, "hidden=%d / heads=%d unsupported", H, A.n_heads);
+    if (C % 8) return fail(h, VITS_E_INVALID, "inter_channels=%d must be a multiple of 8", C);
+    if (A.num_bins != SPL_K && A.use_sdp) return fail(h, VITS_E_INVALID, "num_bins=%d unsupported (kernel is specialised for %d)", A.num_bins, SPL_K);
+    int rc;
+    if ((rc = need_f32(h, "enc.emb", &h->emb, (size_t)A.n_vocab * H))) return rc;
+    h->enc.resize(A.n_layers);
+    std::vector<int> ffn_taps(A.enc_kernel);
+    for (int i = 0; i < A.enc_kernel; i++) ffn_taps[i] = i - (A.enc_kernel - 1) / 2;   // attentions.py:419-427
+    const int nrel = 2 * A.window + 1, dk = H / A.n_heads;
+    for (int i = 0; i < A.n_layers; i++) {
+        auto& L = h->enc[i];
+        std::string p = "enc." + std::to_string(i);
+        if ((rc = mkconv(h, L.qkv, p + ".qkv", H, 3 * H, {0}, true))) return rc;
+        if ((rc = need_f32(h, p + ".rel_k", &L.rel_k, (size_t)nrel * dk))) return rc;
+        if ((rc = need_f32(h, p + ".rel_v", &L.rel_v, (size_t)nrel * dk))) return rc;
+        if ((rc = mkconv(h, L.o, p + ".o", H, H, {0}, true))) return rc;
+        if ((rc = mkln(h, L.ln1, p + ".ln1", H))) return rc;
+        if ((rc = mkconv(h, L.ffn1, p + ".ffn1", H, F, ffn_taps, true))) return rc;
+        if ((rc = mkconv(h, L.ffn2, p + ".ffn2", F, H, ffn_taps, true))) return rc;
+        if ((rc = mkln(h, L.ln2, p + ".ln2", H))) return rc;
+    }
+    if ((rc = mkconv(h, h->enc_proj, "enc.proj", H, 2 * C, {0}, true))) return rc;
+    if (A.n_speakers > 1) {
+        if ((rc = need_f32(h, "dp.cond_tab", &h->dp_cond_tab, (size_t)A.n_speakers * (A.use_sdp ? Fd : H)))) return rc;
+        if ((rc = need_f32(h, "dec.cond_tab", &h->dec_cond_tab, (size_t)A.n_speakers * A.up_init))) return rc;
+    }
+    if (A.use_sdp) {
+        if ((rc = mkconv(h, h->dp_pre, "dp.pre", H, Fd, {0}, true))) return rc;
+        if ((rc = mkconv(h, h->dp_proj, "dp.proj", Fd, Fd, {0}, true))) return rc;
+        if ((rc = mkdds(h, h->dp_dds, "dp.convs", Fd))) return rc;
+        h->cflows.resize(A.n_cflows);
+        for (int k = 0; k < A.n_cflows; k++) {
+            auto& cf = h->cflows[k];
+            std::string p = "dp.flows." + std::to_string(A.cflows[k]);
+            if ((rc = need_f32(h, p + ".pre_w", &cf.pre_w, Fd))) return rc;
+            if ((rc = need_f32(h, p + ".pre_b", &cf.pre_b, Fd))) return rc;
+            if ((rc = mkdds(h, cf.dds, p + ".convs", Fd))) return rc;
+            if ((rc = mkconv(h, cf.proj, p + ".proj", Fd, 3 * A.num_bins - 1, {0}, true))) return rc;
+        }
+        if (!h->opts.count("dp.ea_m") || !h->opts.count("dp.ea_logs"))
+            return fail(h, VITS_E_STATE, "missing options dp.ea_m / dp.ea_logs (ElementwiseAffine of the duration flow)");
+        h->ea_m = (float)h->opts["dp.ea_m"]; h->ea_logs = (float)h->opts["dp.ea_logs"];
+    } else {
+        if ((rc = mkconv(h, h->dpd_c1, "dp.conv_1", H, Fd, sym_taps(A.dp_kernel, 1), true))) return rc;
+        if ((rc = mkln(h, h->dpd_n1, "dp.norm_1", Fd))) return rc;
+        if ((rc = mkconv(h, h->dpd_c2, "dp.conv_2", Fd, Fd, sym_taps(A.dp_kernel, 1), true))) return rc;
+        if ((rc = mkln(h, h->dpd_n2, "dp.norm_2", Fd))) return rc;
+        if ((rc = mkconv(h, h->dpd_proj, "dp.proj", Fd, 1, {0}, true))) return rc;
+    }
+    // coupling flow, execution order; Flip folded into column offsets + permuted weights
+    h->flows.resize(A.n_flow);
+    const int half = C / 2;
+    if (half % 4) return fail(h, VITS_E_INVALID, "inter_channels/2 = %d must be a multiple of 4", half);
+    for (int s = 0; s < A.n_flow; s++) {
+        auto& f = h->flows[s];
+        const bool flipped = (s % 2 == 0);
+        f.xcol = flipped ? half : 0; f.ocol = flipped ? 0 : half;
+        std::string p = "flow." + std::to_string(s);
+        if ((rc = mkconv(h, f.pre, p + ".pre", half, H, {0}, true))) return rc;
+        f.in.resize(A.wn_layers); f.rs.resize(A.wn_layers); f.cond_tab.assign(A.wn_layers, nullptr);
+        int dil = 1;
+        for (int i = 0; i < A.wn_layers; i++) {
+            if ((rc = mkconv(h, f.in[i], p + ".in." + std::to_string(i), H, 2 * H, sym_taps(A.wn_kernel, dil), true))) return rc;
+            if ((rc = mkconv(h, f.rs[i], p + ".rs." + std::to_string(i), H, (i < A.wn_layers - 1) ? 2 * H : H, {0}, true))) return rc;
+            if (A.n_speakers > 1)
+                if ((rc = need_f32(h, p + ".cond_tab." + std::to_string(i), &f.cond_tab[i], (size_t)A.n_speakers * 2 * H))) return rc;
+            dil *= A.wn_dilation_rate;
+        }
+        if ((rc = mkconv(h, f.post, p + ".post", H, half, {0}, true))) return rc;
+    }
+    // decoder
+    if ((rc = mkconv(h, h->dec_pre, "dec.pre", C, A.up_init, sym_taps(7, 1), true))) return rc;
+    h->ups.resize(A.n_ups);
+    int ch = A.up_init;
+    h->rb_c1.clear(); h->rb_c2.clear();
+    for (int i = 0; i < A.n_ups; i++) {
+        const int u = A.up_rates[i];
+        if (u % 2 || A.up_kernels[i] != 2 * u) return fail(h, VITS_E_INVALID, "upsample %d: rate %d kernel %d unsupported (need even rate, kernel = 2*rate)", i, u, A.up_kernels[i]);
+        auto& U = h->ups[i];
+        U.rate = u; U.cout = ch / 2;
+        std::string p = "dec.ups." + std::to_string(i);
+        if ((rc = mkconv(h, U.A, p + ".A", ch, (u / 2) * (ch / 2), {-1, 0}, true))) return rc;
+        if ((rc = mkconv(h, U.B, p + ".B", ch, (u / 2) * (ch / 2), {0, 1}, true))) return rc;
+        ch /= 2;
+        for (int j = 0; j < A.n_rbk; j++) {
+            const int n = i * A.n_rbk + j;
+            std::vector<ConvP> c1(A.rb_ndil[j]), c2;
+            if (A.resblock_type == 1) c2.resize(A.rb_ndil[j]);
+            for (int c = 0; c < A.rb_ndil[j]; c++) {
+                std::string q = "dec.rb." + std::to_string(n);
+                if (A.resblock_type == 1) {
+                    if ((rc = mkconv(h, c1[c], q + ".c1." + std::to_string(c), ch, ch, sym_taps(A.rb_kernels[j], A.rb_dilations[j][c]), true))) return rc;
+                    if ((rc = mkconv(h, c2[c], q + ".c2." + std::to_string(c), ch, ch, sym_taps(A.rb_kernels[j], 1), true))) return rc;
+                } else {
+                    if ((rc = mkconv(h, c1[c], q + ".c." + std::to_string(c), ch, ch, sym_taps(A.rb_kernels[j], A.rb_dilations[j][c]), true))) return rc;
+                }
+            }
+            h->rb_c1.push_back(c1); h->rb_c2.push_back(c2);
+        }
+    }
+    h->post_c = ch;
+    if (ch > 64) return fail(h, VITS_E_INVALID, "conv_post input width %d > 64 unsupported", ch);
+    if ((rc = need_f32(h, "dec.post_w", &h->post_w, (size_t)7 * ch))) return rc;
+    h->finalized = true;
+    return VITS_OK;
+}
+
+int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int32_t B, const float scales[3],
+                 const int64_t* sid, const float* noise_dp, int64_t dp_stride, const float* logw_override,
+                 uint64_t seed, int64_t* y_lengths, int64_t* total_frames) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->finalized) return fail(h, VITS_E_STATE, "vits_finalize() has not succeeded");
+    if (!ids || !lengths || !scales || B <= 0 || !y_lengths) return fail(h, VITS_E_INVALID, "null argument or B <= 0");
+    const vits_arch& A = h->A;
+    h->prepared = false;
+    // ---- validation (what ORT's Gather would raise on)
+    long R = 0;
+    h->h_cu_t.assign(B + 1, 0);
+    for (int b = 0; b < B; b++) {
+        if (lengths[b] < 1 || lengths[b] > (1 << 20)) return fail(h, VITS_E_INVALID, "input_lengths[%d] = %lld out of range", b, (long long)lengths[b]);
+        R += lengths[b]; h->h_cu_t[b + 1] = (int)R;
+        if (R > (1l << 30)) return fail(h, VITS_E_INVALID, "batch too large");
+    }
+    std::vector<int> h_ids(R);
+    for (long i = 0; i < R; i++) {
+        if (ids[i] < 0 || ids[i] >= A.n_vocab) return fail(h, VITS_E_INVALID, "phoneme id %lld at position %ld outside [0, %d)", (long long)ids[i], i, A.n_vocab);
+        h_ids[i] = (int)ids[i];
+    }
+    h->h_sid.assign(B, 0);
+    if (A.n_speakers > 1) {
+        if (!sid) return fail(h, VITS_E_INVALID, "multi-speaker voice: 'sid' is required");
+        for (int b = 0; b < B; b++) {
+            if (sid[b] < 0 || sid[b] >= A.n_speakers) return fail(h, VITS_E_INVALID, "sid[%d] = %lld outside [0, %d)", b, (long long)sid[b], A.n_speakers);
+            h->h_sid[b] = (int)sid[b];
+        }
+    }
+    if (!(scales[1] > 0.f) || scales[0] < 0.f || scales[2] < 0.f) return fail(h, VITS_E_INVALID, "scales must be >= 0 (length_scale > 0)");
+    if (noise_dp) for (int b = 0; b < B; b++) if (dp_stride < lengths[b]) return fail(h, VITS_E_INVALID, "noise_dp stride %lld < length %lld", (long long)dp_stride, (long long)lengths[b]);
+    h->scales[0] = scales[0]; h->scales[1] = scales[1]; h->scales[2] = scales[2];
+    h->seed = seed; h->B = B; h->R = (int)R;
+    h->utt_base = h->utt_counter; h->utt_counter += (uint64_t)B;
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int H = A.hidden, C = A.inter, F = A.filter, Fd = A.dp_filter;
+    int rc;
+    // ---- buffers
+    TileBuilder tb; tb.begin(h->h_cu_t.data(), B); tb.add(1);
+    if ((rc = ensure(h, h->ids, R * 4)) || (rc = ensure(h, h->tile_t, tb.host.size() * 4)) || (rc = ensure(h, h->sid, B * 4)) ||
+        (rc = ensure(h, h->x, R * H * 4)) || (rc = ensure(h, h->y, R * H * 4)) || (rc = ensure(h, h->qkv, R * 3 * H * 4)) ||
+        (rc = ensure(h, h->att, R * H * 4)) || (rc = ensure(h, h->ffn, R * F * 4)) || (rc = ensure(h, h->stats, R * 2 * C * 4)) ||
+        (rc = ensure(h, h->d0, R * Fd * 4)) || (rc = ensure(h, h->d1, R * Fd * 4)) || (rc = ensure(h, h->y, R * std::max(H, Fd) * 4)) ||
+        (rc = ensure(h, h->gdp, R * Fd * 4)) || (rc = ensure(h, h->hp, R * 32 * 4)) || (rc = ensure(h, h->z0, R * 4)) ||
+        (rc = ensure(h, h->z1, R * 4)) || (rc = ensure(h, h->logw, R * 4)) || (rc = ensure(h, h->dur, R * 4)) ||
+        (rc = ensure(h, h->cum, R * 4)) || (rc = ensure(h, h->ylen, B * 4)))
+        return rc;
+    CK(h, cudaMemcpyAsync(h->ids.p, h_ids.data(), R * 4, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->tile_t.p, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->sid.p, h->h_sid.data(), B * 4, cudaMemcpyHostToDevice, st));
+    const float* d_inj = nullptr;
+    if (noise_dp && A.use_sdp && !logw_override) {
+        size_t nb = (size_t)B * 2 * dp_stride * 4;
+        if ((rc = ensure(h, h->inj_dp, nb))) return rc;
+        CK(h, cudaMemcpyAsync(h->inj_dp.p, noise_dp, nb, cudaMemcpyHostToDevice, st));
+        d_inj = ptr<float>(h->inj_dp);
+    }
+    const Tiles T = tb.get(ptr<int>(h->tile_t), 1);
+    const int* d_sid = ptr<int>(h->sid);
+    float *x = ptr<float>(h->x), *y = ptr<float>(h->y), *qkv = ptr<float>(h->qkv), *att = ptr<float>(h->att),
+          *ffn = ptr<float>(h->ffn), *stats = ptr<float>(h->stats);
+    stage_begin(h, 0);
+    // ---- text encoder (models.py:198-209, attentions.py:60-74)
+    {
+        long n4 = R * (H / 4);
+        k_embed<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ptr<int>(h->ids), h->emb, x, (int)R, H, sqrtf((float)H));
+        h->launches++;
+        const int dk = H / A.n_heads, nrel = 2 * A.window + 1;
+        for (int i = 0; i < A.n_layers; i++) {
+            auto& L = h->enc[i];
+            ConvArgs a = base_args(L.qkv, x, H, 0, qkv, 3 * H, 0);
+            if ((rc = launch_conv(h, a, T, false))) return rc;
+            k_rel_attention<<<dim3((R + 3) / 4, A.n_heads), 128, 4 * (dk + nrel) * sizeof(float), st>>>(
+                qkv, L.rel_k, L.rel_v, att, T.cu, B, (int)R, H, A.n_heads, dk, A.window);
+            h->launches++;
+            a = base_args(L.o, att, H, 0, y, H, 0); a.res = x; a.ldres = H;
+            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_ln(h, y, x, L.ln1, (int)R, H, 0, nullptr, T))) return rc;
+            a = base_args(L.ffn1, x, H, 0, ffn, F, 0); a.out_act = ACT_RELU;
+            if ((rc = launch_conv(h, a, T, false))) return rc;
+            a = base_args(L.ffn2, ffn, F, 0, y, H, 0); a.res = x; a.ldres = H;
+            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_ln(h, y, x, L.ln2, (int)R, H, 0, nullptr, T))) return rc;
+        }
+        ConvArgs a = base_args(h->enc_proj, x, H, 0, stats, 2 * C, 0);
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+    }
+    // ---- duration predictor
+    float* logw = ptr<float>(h->logw);
+    if (logw_override) {
+        CK(h, cudaMemcpyAsync(logw, logw_override, R * 4, cudaMemcpyHostToDevice, st));
+    } else if (A.use_sdp) {
+        float *d0 = ptr<float>(h->d0), *d1 = ptr<float>(h->d1), *gdp = ptr<float>(h->gdp), *hp = ptr<float>(h->hp);
+        float *z0 = ptr<float>(h->z0), *z1 = ptr<float>(h->z1);
+        ConvArgs a = base_args(h->dp_pre, x, H, 0, d0, Fd, 0);
+        if (A.n_speakers > 1) { a.utab = h->dp_cond_tab; a.uidx = d_sid; a.utab_ld = Fd; }
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = run_dds(h, h->dp_dds, d0, d1, y, (int)R, Fd, T))) return rc;
+        a = base_args(h->dp_proj, d0, Fd, 0, gdp, Fd, 0);
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+        k_noise_dp<<<(R + 255) / 256, 256, 0, st>>>(z0, z1, d_inj, dp_stride, T.cu, B, (int)R, h->scales[2], seed, h->utt_base);
+        h->launches++;
+        for (int k = 0; k < A.n_cflows; k++) {
+            std::swap(z0, z1);                                   // Flip (modules.py:386)
+            auto& cf = h->cflows[k];
+            long n = R * Fd;
+            k_cf_pre<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z0, cf.pre_w, cf.pre_b, gdp, d0, (int)R, Fd);
+            h->launches++;
+            if ((rc = run_dds(h, cf.dds, d0, d1, y, (int)R, Fd, T))) return rc;
+            a = base_args(cf.proj, d0, Fd, 0, hp, 32, 0);
+            if ((rc = launch_conv(h, a, T, false))) return rc;
+            k_spline_inverse<<<(R + 127) / 128, 128, 0, st>>>(hp, 32, z1, (int)R, 1.f / sqrtf((float)Fd));
+            h->launches++;
+        }
+        std::swap(z0, z1);                                       // final Flip, then EA on channel 0
+        k_ea_logw<<<(R + 255) / 256, 256, 0, st>>>(z0, h->ea_m, expf(-h->ea_logs), logw, (int)R);
+        h->launches++;
+    } else {
+        float *d0 = ptr<float>(h->d0), *d1 = ptr<float>(h->d1);
+        const float* xin = x;
+        if (A.n_speakers > 1) {
+            CK(h, cudaMemcpyAsync(y, x, R * H * 4, cudaMemcpyDeviceToDevice, st));
+            long n = R * H;
+            k_add_rowbias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, h->dp_cond_tab, d_sid, T.cu, B, (int)R, H);
+            h->launches++;
+            xin = y;
+        }
+        ConvArgs a = base_args(h->dpd_c1, xin, H, 0, d0, Fd, 0); a.out_act = ACT_RELU;
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_ln(h, d0, d0, h->dpd_n1, (int)R, Fd, 0, nullptr, T))) return rc;
+        a = base_args(h->dpd_c2, d0, Fd, 0, d1, Fd, 0); a.out_act = ACT_RELU;
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_ln(h, d1, d1, h->dpd_n2, (int)R, Fd, 0, nullptr, T))) return rc;
+        a = base_args(h->dpd_proj, d1, Fd, 0, logw, 1, 0);
+        if ((rc = launch_conv(h, a, T, false))) return rc;
+    }
+    // ---- length regulation (integer path)
+    k_durations<<<B, 256, 0, st>>>(logw, h->scales[1], T.cu, ptr<int>(h->dur), ptr<int>(h->cum), ptr<int>(h->ylen));
+    h->launches++;
+    CK(h, cudaGetLastError());
+    stage_end(h);
+    h->h_ylen.assign(B, 0);
+    CK(h, cudaMemcpyAsync(h->h_ylen.data(), h->ylen.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));          // the one host sync of the path: frame counts
+    h->h_cu_y.assign(B + 1, 0);
+    int64_t tot = 0;
+    for (int b = 0; b < B; b++) {
+        tot += h->h_ylen[b];
+        if (tot > (1ll << 30)) return fail(h, VITS_E_INVALID, "durations overflow: more than 2^30 frames");
+        h->h_cu_y[b + 1] = (int)tot;
+        y_lengths[b] = h->h_ylen[b];
+    }
+    h->total_frames = tot;
+    if (total_frames) *total_frames = tot;
+    h->prepared = true;
+    return VITS_OK;
+}
+
+int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t out_kind, void* out,
+                int64_t out_capacity, float volume, int32_t normalize) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->prepared) return fail(h, VITS_E_STATE, "vits_decode() before a successful vits_prepare()");
+    const vits_arch& A = h->A;
+    const int B = h->B, H = A.hidden, C = A.inter;
+    int hop = 1; for (int i = 0; i < A.n_ups; i++) hop *= A.up_rates[i];
+    const int64_t total_samples = h->total_frames * hop;
+    if (out_kind < 0 || out_kind > 2) return fail(h, VITS_E_INVALID, "out_kind %d", out_kind);
+    if (out_kind != 0 && (!out || out_capacity < total_samples)) return fail(h, VITS_E_INVALID, "output buffer too small: %lld < %lld samples", (long long)out_capacity, (long long)total_samples);
+    if (noise_z) for (int b = 0; b < B; b++) if (z_stride < h->h_ylen[b]) return fail(h, VITS_E_INVALID, "noise_z stride %lld < frames %d of utterance %d", (long long)z_stride, h->h_ylen[b], b);
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int rc;
+    const float* d_injz = nullptr;
+    if (noise_z) {
+        size_t nb = (size_t)B * C * z_stride * 4;
+        if ((rc = ensure(h, h->inj_z, nb))) return rc;
+        CK(h, cudaMemcpyAsync(h->inj_z.p, noise_z, nb, cudaMemcpyHostToDevice, st));
+        d_injz = ptr<float>(h->inj_z);
+    }
+    if ((rc = ensure(h, h->audio, std::max<int64_t>(total_samples, 1) * 4))) return rc;
+    float* audio = ptr<float>(h->audio);
+    // per-stage geometry
+    std::vector<int> rates(A.n_ups + 1), chans(A.n_ups + 1);
+    rates[0] = 1; chans[0] = A.up_init;
+    for (int i = 0; i < A.n_ups; i++) { rates[i + 1] = rates[i] * A.up_rates[i]; chans[i + 1] = chans[i] / 2; }
+    size_t stage_elems_per_frame = 0;
+    for (int i = 1; i <= A.n_ups; i++) stage_elems_per_frame = std::max(stage_elems_per_frame, (size_t)rates[i] * chans[i]);
+
+    int b_lo = 0;
+    while (b_lo < B) {
+        int b_hi = b_lo + 1;
+        int64_t fr = h->h_ylen[b_lo];
+        while (b_hi < B && fr + h->h_ylen[b_hi] <= h->max_chunk_frames) { fr += h->h_ylen[b_hi]; b_hi++; }
+        const int nB = b_hi - b_lo;
+        const int Fr = (int)fr;
+        const int f_lo = h->h_cu_y[b_lo];
+        std::vector<int> cu_local(nB + 1);
+        for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
+        TileBuilder tb; tb.begin(cu_local.data(), nB);
+        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i]);
+        if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
+            (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
+            (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) ||
+            (rc = ensure(h, h->dpre, (size_t)Fr * A.up_init * 4)) ||
+            (rc = ensure(h, h->sX, Fr * stage_elems_per_frame * 4)) || (rc = ensure(h, h->sT1, Fr * stage_elems_per_frame * 4)) ||
+            (rc = ensure(h, h->sXSa, Fr * stage_elems_per_frame * 4)) || (rc = ensure(h, h->sXSb, Fr * stage_elems_per_frame * 4)) ||
+            (rc = ensure(h, h->sYa, Fr * stage_elems_per_frame * 4)))
+            return rc;
+        if (A.resblock_type == 1)
+            if ((rc = ensure(h, h->sYb, Fr * stage_elems_per_frame * 4))) return rc;
+        CK(h, cudaMemcpyAsync(h->chunk_meta.p, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice, st));
+        const int* meta = ptr<int>(h->chunk_meta);
+        const Tiles T1 = tb.get(meta, 1);
+        const int* d_sid = ptr<int>(h->sid) + b_lo;
+        float *P = ptr<float>(h->P), *fh = ptr<float>(h->fh), *facts = ptr<float>(h->facts), *fskip = ptr<float>(h->fskip);
+        // ---- prior expansion + sampling (models.py:705-718)
+        stage_begin(h, 1);
+        k_frame_index<<<(Fr + 255) / 256, 256, 0, st>>>(ptr<int>(h->cum), ptr<int>(h->tile_t), T1.cu, b_lo, nB, Fr, ptr<int>(h->fidx));
+        h->launches++;
+        {
+            long n = (long)Fr * C;
+            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ptr<float>(h->stats), ptr<int>(h->fidx), T1.cu, b_lo, nB,
+                                                                         d_injz, z_stride, h->scales[0], h->seed, h->utt_base, P, Fr, C);
+            h->launches++;
+        }
+        h->last_chunk_frames = Fr;
+        if (h->opts.count("debug_keep_zp") && h->opts["debug_keep_zp"] != 0) {
+            if ((rc = ensure(h, h->dbg_zp, (size_t)Fr * C * 4))) return rc;
+            CK(h, cudaMemcpyAsync(h->dbg_zp.p, P, (size_t)Fr * C * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        // ---- coupling flow, reverse (models.py:247-254, modules.py:447-466, 184-209)
+        const bool tc_flow = true;
+        for (int s = 0; s < A.n_flow; s++) {
+            auto& f = h->flows[s];
+            ConvArgs a = base_args(f.pre, P, C, f.xcol, fh, H, 0);
+            if ((rc = launch_conv(h, a, T1, false))) return rc;
+            for (int i = 0; i < A.wn_layers; i++) {
+                a = base_args(f.in[i], fh, H, 0, facts, H, 0); a.epi = EPI_GATE;
+                if (A.n_speakers > 1) { a.utab = f.cond_tab[i]; a.uidx = d_sid; a.utab_ld = 2 * H; }
+                if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
+                if (i < A.wn_layers - 1) {
+                    a = base_args(f.rs[i], facts, H, 0, fh, H, 0); a.epi = EPI_SPLIT; a.split = H; a.accumulate = 1;
+                    a.out2 = fskip; a.ldo2 = H; a.ocol2 = 0; a.accumulate2 = (i > 0);
+                } else {
+                    a = base_args(f.rs[i], facts, H, 0, fskip, H, 0); a.accumulate = (i > 0);
+                }
+                if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
+            }
+            a = base_args(f.post, fskip, H, 0, P, C, f.ocol); a.epi = EPI_SUBFROM; a.res = P; a.ldres = C; a.rescol = f.ocol;
+            if ((rc = launch_conv(h, a, T1, false))) return rc;
+        }
+        stage_end(h);
+        // ---- HiFi-GAN generator (models.py:348-368)
+        stage_begin(h, 2);
+        float *dpre = ptr<float>(h->dpre), *X = ptr<float>(h->sX), *T1b = ptr<float>(h->sT1);
+        float *XSab[2] = {ptr<float>(h->sXSa), ptr<float>(h->sXSb)};
+        float *Ya = ptr<float>(h->sYa), *Yb = ptr<float>(h->sYb);
+        {
+            ConvArgs a = base_args(h->dec_pre, P, C, 0, dpre, A.up_init, 0);
+            if (A.n_speakers > 1) { a.utab = h->dec_cond_tab; a.uidx = d_sid; a.utab_ld = A.up_init; }
+            if ((rc = launch_conv(h, a, T1, true))) return rc;
+        }
+        const float* cur = dpre; int cur_c = A.up_init;
+        for (int i = 0; i < A.n_ups; i++) {
+            auto& U = h->ups[i];
+            const Tiles Tin = tb.get(meta, rates[i]);
+            const Tiles Tout = tb.get(meta, rates[i + 1]);
+            const int co = U.cout, u = U.rate;
+            float* XS = XSab[i & 1];      // stage output; the next stage reads it while writing the other one
+            // polyphase ConvTranspose1d (models.py:320-332): output row-block q holds u*co contiguous floats
+            // == rows q*u .. q*u+u-1 of the [rows*u, co] result; phases [0,u/2) use taps {-1,0}, the rest {0,+1}
+            ConvArgs a = base_args(U.A, cur, cur_c, 0, X, u * co, 0); a.in_act = 1; a.in_slope = 0.1f;
+            if ((rc = launch_conv(h, a, Tin, true))) return rc;
+            a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
+            if ((rc = launch_conv(h, a, Tin, true))) return rc;
+            for (int j = 0; j < A.n_rbk; j++) {
+                const int n = i * A.n_rbk + j;
+                const bool first = (j == 0), last = (j == A.n_rbk - 1);
+                const int nd = A.rb_ndil[j];
+                const float* in = X;
+                for (int c = 0; c < nd; c++) {
+                    const bool fin = (c == nd - 1);
+                    if (A.resblock_type == 2) {
+                        // modules.py:355-364: x = conv_d(lrelu(x)) + x
+                        float* dst = fin ? XS : ((c & 1) ? Ya : T1b);
+                        a = base_args(h->rb_c1[n][c], in, co, 0, dst, co, 0); a.in_act = 1; a.in_slope = 0.1f;
+                        a.res = in; a.ldres = co;
+                        if (fin) { a.accumulate = !first; if (last) a.out_div = (float)A.n_rbk; }
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                        in = dst;
+                    } else {
+                        // modules.py:301-314: xt = c1(lrelu(x)); xt = c2(lrelu(xt)); x = xt + x
+                        a = base_args(h->rb_c1[n][c], in, co, 0, T1b, co, 0); a.in_act = 1; a.in_slope = 0.1f;
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                        float* dst = fin ? XS : ((c & 1) ? Yb : Ya);
+                        a = base_args(h->rb_c2[n][c], T1b, co, 0, dst, co, 0); a.in_act = 1; a.in_slope = 0.1f;
+                        a.res = in; a.ldres = co;
+                        if (fin) { a.accumulate = !first; if (last) a.out_div = (float)A.n_rbk; }
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                        in = dst;
+                    }
+                }
+            }
+            cur = XS; cur_c = co;
+        }
+        // ---- lrelu(0.01) -> conv_post -> tanh (models.py:364-366)
+        {
+            const Tiles Tl = tb.get(meta, rates[A.n_ups]);
+            if (Tl.n256 > 0) {
+                size_t smem = (size_t)(CP_TILE + 6) * (h->post_c + 1) * sizeof(float);
+                k_conv_post<<<Tl.n256, 256, smem, st>>>(cur, h->post_c, h->post_w, Tl.cu, Tl.t256, nB, Tl.rate, 0.01f,
+                                                        audio + (int64_t)f_lo * hop);
+                h->launches++;
+            }
+        }
+        CK(h, cudaGetLastError());
+        stage_end(h);
+        b_lo = b_hi;
+    }
+    // ---- output
+    if (out_kind == 1) {
+        CK(h, cudaMemcpyAsync(out, audio, total_samples * 4, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+    } else if (out_kind == 2) {
+        // caller-side post-processing on device (voice.py:271-282, 88-91)
+        if ((rc = ensure(h, h->peaks, B * 4)) || (rc = ensure(h, h->cu_y_dev, (B + 1) * 4)) ||
+            (rc = ensure(h, h->audio16, total_samples * 2 + 16)))
+            return rc;
+        CK(h, cudaMemcpyAsync(h->cu_y_dev.p, h->h_cu_y.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemsetAsync(h->peaks.p, 0, B * 4, st));
+        dim3 g(32, B);
+        k_absmax<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev), B, hop, ptr<unsigned int>(h->peaks));
+        k_to_int16<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev), B, hop, ptr<unsigned int>(h->peaks), normalize, volume,
+                                      ptr<int16_t>(h->audio16));
+        h->launches += 2;
+        CK(h, cudaGetLastError());
+        CK(h, cudaMemcpyAsync(out, h->audio16.p, total_samples * 2, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    return VITS_OK;
+}
+
+int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity_elems) {
+    if (!h || !name || !out) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->prepared) return fail(h, VITS_E_STATE, "nothing to fetch: no successful vits_prepare()");
+    const vits_arch& A = h->A;
+    const std::string k(name);
+    const void* src = nullptr; int64_t n = 0;
+    const int64_t R = h->R, Fr = h->last_chunk_frames;
+    if (k == "x") { src = h->x.p; n = R * A.hidden; }
+    else if (k == "stats") { src = h->stats.p; n = R * 2 * A.inter; }
+    else if (k == "logw") { src = h->logw.p; n = R; }
+    else if (k == "durations") { src = h->dur.p; n = R; }
+    else if (k == "cum") { src = h->cum.p; n = R; }
+    else if (k == "frame_index") { src = h->fidx.p; n = Fr; }
+    else if (k == "z_p") { src = h->dbg_zp.p; n = h->dbg_zp.p ? Fr * A.inter : 0; }
+    else if (k == "z") { src = h->P.p; n = Fr * A.inter; }
+    else return fail(h, VITS_E_INVALID, "unknown stage tensor '%s'", name);
+    if (!src || n == 0) return fail(h, VITS_E_STATE, "stage tensor '%s' is not available", name);
+    if (n > capacity_elems) return fail(h, VITS_E_INVALID, "fetch '%s': capacity %lld < %lld", name, (long long)capacity_elems, (long long)n);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int vits_timer_start(vits_handle* h) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    resolve_stage_events(h);
+    h->stage_ms[0] = h->stage_ms[1] = h->stage_ms[2] = 0.f;
+    CK(h, cudaEventRecord(h->ev_t0, h->stream));
+    return VITS_OK;
+}
+
+int vits_timer_stop(vits_handle* h, float* elapsed_ms) {
+    if (!h || !elapsed_ms) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaEventRecord(h->ev_t1, h->stream));
+    CK(h, cudaEventSynchronize(h->ev_t1));
+    CK(h, cudaEventElapsedTime(elapsed_ms, h->ev_t0, h->ev_t1));
+    resolve_stage_events(h);
+    return VITS_OK;
+}
+
+int vits_stage_ms(vits_handle* h, float* text_ms, float* flow_ms, float* dec_ms) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    resolve_stage_events(h);
+    if (text_ms) *text_ms = h->stage_ms[0];
+    if (flow_ms) *flow_ms = h->stage_ms[1];
+    if (dec_ms) *dec_ms = h->stage_ms[2];
+    return VITS_OK;
+}
+
+// Test hook: one convolution through the production launch path (fp32 or tcgen05 kernel) on
+// host data, single utterance of L rows.  Used by tests/ to pin both conv kernels against numpy.
+int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, const int* taps, int ntaps,
+                   const float* w32, const uint16_t* wtc, const float* bias, int n, int in_act, float in_slope,
+                   int epi, const float* res, int accumulate, float out_div, int out_act, float* out, int out_cols) {
+    if (!h || !x || !taps || !w32 || !out || ntaps < 1 || ntaps > CONV_MAX_TAPS) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int npad = rup(n, 4), npad16 = rup(n, 16);
+    float *dx = nullptr, *dw = nullptr, *db = nullptr, *dres = nullptr, *dout = nullptr; void* dwtc = nullptr; int* dmeta = nullptr;
+    const size_t out_elems = (size_t)L * out_cols;
+    CK(h, cudaMalloc(&dx, (size_t)L * cin * 4)); CK(h, cudaMalloc(&dw, (size_t)ntaps * cin * npad * 4));
+    CK(h, cudaMalloc(&dout, out_elems * 4)); CK(h, cudaMalloc(&dmeta, 64));
+    CK(h, cudaMemcpy(dx, x, (size_t)L * cin * 4, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(dw, w32, (size_t)ntaps * cin * npad * 4, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(dout, out, out_elems * 4, cudaMemcpyHostToDevice));
+    if (bias) { CK(h, cudaMalloc(&db, npad * 4)); CK(h, cudaMemcpy(db, bias, npad * 4, cudaMemcpyHostToDevice)); }
+    if (res) { CK(h, cudaMalloc(&dres, (size_t)L * n * 4)); CK(h, cudaMemcpy(dres, res, (size_t)L * n * 4, cudaMemcpyHostToDevice)); }
+    if (wtc) { CK(h, cudaMalloc(&dwtc, (size_t)ntaps * cin * npad16 * 2)); CK(h, cudaMemcpy(dwtc, wtc, (size_t)ntaps * cin * npad16 * 2, cudaMemcpyHostToDevice)); }
+    int cu[2] = {0, L};
+    TileBuilder tb; tb.begin(cu, 1); tb.add(1);
+    CK(h, cudaMemcpy(dmeta, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice));
+    const Tiles T = tb.get(dmeta, 1);
+    ConvP c; c.w = dw; c.wtc = (const __nv_bfloat16*)dwtc; c.b = db; c.cin = cin; c.n = n; c.npad = npad; c.npad16 = npad16; c.ntaps = ntaps;
+    for (int i = 0; i < ntaps; i++) c.toff[i] = taps[i];
+    ConvArgs a = base_args(c, dx, cin, 0, dout, out_cols, 0);
+    a.in_act = in_act; a.in_slope = in_slope; a.epi = epi; a.res = dres; a.ldres = n; a.accumulate = accumulate;
+    a.out_div = out_div; a.out_act = out_act;
+    if (epi == EPI_SPLIT) { a.split = n / 2; a.out2 = dout + n / 2; a.ldo2 = out_cols; a.ocol2 = 0; a.accumulate2 = accumulate; }
+    const int saved = h->precision;
+    h->precision = use_tc ? 1 : 0;
+    int rc = 0;
+    if (use_tc && !conv_tc_supported(a)) rc = fail(h, VITS_E_INVALID, "shape not supported by the tcgen05 conv kernel");
+    if (!rc) rc = launch_conv(h, a, T, use_tc != 0);
+    h->precision = saved;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail(h, VITS_E_CUDA, "test conv failed: %s", cudaGetErrorString(e));
+    if (!rc) cudaMemcpy(out, dout, out_elems * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dmeta); if (db) cudaFree(db); if (dres) cudaFree(dres); if (dwtc) cudaFree(dwtc);
+    return rc;
+}
+
+int64_t vits_launch_count(vits_handle* h) { return h ? h->launches : 0; }
+
+const char* vits_last_error(vits_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void vits_destroy(vits_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    resolve_stage_events(h);
+    for (auto& kv : h->blobs) cudaFree(kv.second.p);
+    Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
+                   &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
+                   &h->chunk_meta, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp};
+    for (Buf* b : bufs) if (b->p) cudaFree(b->p);
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""B200Session: the object that replaces ``onnxruntime.InferenceSession`` inside phoonnx's
+``TTSVoice`` (reference seam: phoonnx/voice.py:105-107; touched at :347 ``get_inputs()`` and
+:374-377 ``run(None, feed)``; constructed at :167-171).
+
+Same constructor shape ``(path, sess_options=None, providers=None)``, same feed names and
+dtypes (``input`` int64 [B,T], ``input_lengths`` int64 [B], ``scales`` float32 [3] =
+[noise_scale, length_scale, noise_w], ``sid`` int64 [B] for multi-speaker voices; unknown
+keys such as ``langid`` are rejected by the caller's own filter, voice.py:373), same output:
+a list whose first element is float32 ``[B, 1, 1, T_max * hop]`` (export_onnx.py:269-278).
+
+Semantics: every utterance is synthesised exactly as if it were alone in the batch (B=1,
+which is what TTSVoice always sends, voice.py:350-351); rows are zero beyond their own length.
+Errors: bad shapes / ids / sid -> ValueError, CUDA problems -> RuntimeError.  No CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine
+from .packing import pack_model
+from .weights import load_model
+
+
+class NodeArg:
+    """Mirror of onnxruntime.NodeArg as far as TTSVoice looks (``.name``; voice.py:347)."""
+
+    def __init__(self, name: str, type_: str, shape):
+        self.name, self.type, self.shape = name, type_, shape
+
+    def __repr__(self):
+        return f"NodeArg(name='{self.name}', type='{self.type}', shape={self.shape})"
+
+
+class B200Session:
+    TEST_FEEDS = ("noise_dp", "noise_z", "logw")
+
+    def __init__(self, path_or_bytes, sess_options=None, providers=None, provider_options=None, *,
+                 device: int = 0, precision: str = "fp32", sample_rate: Optional[int] = None,
+                 max_chunk_frames: Optional[int] = None, seed: int = 0):
+        self._path = str(path_or_bytes)
+        W, arch, hdr = load_model(self._path, sample_rate)
+        self.arch = arch
+        self.metadata = dict(hdr.metadata)
+        blobs, opts = pack_model(W, arch)
+        self.engine = Engine(arch, blobs, opts, device=device, precision=precision)
+        if max_chunk_frames:
+            self.engine.set_option("max_chunk_frames", max_chunk_frames)
+        self._inputs = [NodeArg("input", "tensor(int64)", ["batch_size", "phonemes"]),
+                        NodeArg("input_lengths", "tensor(int64)", ["batch_size"]),
+                        NodeArg("scales", "tensor(float)", [3])]
+        if arch.n_speakers > 1:
+            self._inputs.append(NodeArg("sid", "tensor(int64)", ["batch_size"]))
+        self._outputs = [NodeArg("output", "tensor(float)", ["batch_size", 1, 1, "time"])]
+        self._seed = int(seed)
+        self._calls = 0
+        self.last_lengths: Optional[np.ndarray] = None   # samples per utterance of the last run
+
+    # ---- the InferenceSession surface TTSVoice uses ---------------------------------
+    def get_inputs(self) -> List[NodeArg]:
+        return list(self._inputs)
+
+    def get_outputs(self) -> List[NodeArg]:
+        return list(self._outputs)
+
+    def get_providers(self) -> List[str]:
+        return ["B200ExecutionProvider"]
+
+    def run(self, output_names: Optional[Sequence[str]], input_feed: Dict[str, np.ndarray], run_options=None):
+        if output_names is not None and list(output_names) not in ([], ["output"]):
+            raise ValueError(f"unknown output names {output_names!r}; the graph has one output: 'output'")
+        audio, lens = self.synthesize_packed(input_feed)
+        B = lens.shape[0]
+        tmax = int(lens.max()) if B else 0
+        out = np.zeros((B, 1, 1, tmax), np.float32)
+        off = 0
+        for b in range(B):
+            n = int(lens[b])
+            out[b, 0, 0, :n] = audio[off:off + n]
+            off += n
+        return [out]
+
+    # ---- batched entry used by run() and by the throughput harness ------------------
+    def _unpack_feed(self, feed):
+        known = {a.name for a in self._inputs} | set(self.TEST_FEEDS)
+        for k in feed:
+            if k not in known:
+                raise ValueError(f"Invalid input name: {k}")
+        for a in self._inputs:
+            if a.name not in feed:
+                raise ValueError(f"Required input '{a.name}' is missing from the feed")
+        x = np.asarray(feed["input"])
+        lens = np.asarray(feed["input_lengths"])
+        if x.dtype != np.int64 or lens.dtype != np.int64:
+            raise ValueError("'input' and 'input_lengths' must be int64 (voice.py:350-351)")
+        if x.ndim != 2 or lens.ndim != 1 or lens.shape[0] != x.shape[0]:
+            raise ValueError(f"expected input [B,T] and input_lengths [B], got {x.shape} / {lens.shape}")
+        if x.shape[0] < 1 or x.shape[1] < 1:
+            raise ValueError("empty batch / empty phoneme sequence")
+        if lens.min() < 1 or lens.max() > x.shape[1]:
+            raise ValueError("input_lengths must lie in [1, T]")
+        scales = np.asarray(feed["scales"])
+        if scales.dtype != np.float32 or scales.shape != (3,):
+            raise ValueError("'scales' must be float32 [3] = [noise_scale, length_scale, noise_w] (voice.py:364-367)")
+        sid = None
+        if self.arch.n_speakers > 1:
+            sid = np.asarray(feed["sid"])
+            if sid.dtype != np.int64 or sid.shape != (x.shape[0],):
+                raise ValueError("'sid' must be int64 [B] (voice.py:370)")
+        return x, lens, scales, sid
+
+    def synthesize_packed(self, feed, out: str = "f32", volume: float = 1.0, normalize: bool = True):
+        """Returns (packed audio of all utterances, samples per utterance)."""
+        x, lens, scales, sid = self._unpack_feed(feed)
+        B, T = x.shape
+        mask = np.arange(T)[None, :] < lens[:, None]
+        ids = x[mask]                                    # packed, positions >= length ignored (commons.py:109-113)
+        self._calls += 1
+        ylen = self.engine.prepare(ids, lens, scales, sid, feed.get("noise_dp"), feed.get("logw"),
+                                   seed=self._seed + self._calls)
+        audio = self.engine.decode(feed.get("noise_z"), out=out, volume=volume, normalize=normalize)
+        self.last_lengths = ylen * self.engine.hop
+        return audio, self.last_lengths
+
+    def end_profiling(self):
+        return None

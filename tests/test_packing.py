@@ -1,0 +1,45 @@
+"""Kernel-layout packing (flip folding, interleaved gate, polyphase transposed conv, speaker tables)
+verified on CPU: a numpy emulation of the kernels' indexing over the PACKED blobs vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import emulate
+from oracle.vits_oracle import VitsOracle
+from phoonnx_b200 import modelgen, packing
+
+
+@pytest.mark.parametrize("preset,ns", [("tiny", 1), ("tiny", 3), ("tiny_rb1", 1), ("x_low", 1)])
+def test_flow_and_decoder_packing(preset, ns):
+    a = modelgen.make_arch(preset, ns)
+    W = modelgen.synth_weights(a, 7)
+    blobs, opts = packing.pack_model(W, a)
+    orc = VitsOracle(W, a)
+    rs = np.random.RandomState(0)
+    zp = rs.randn(29, a.inter).astype(np.float32)
+    sid = 1 if ns > 1 else None
+    g = None if sid is None else orc.W["emb_g.weight"][sid][None, :, None]
+    z_ref = orc.flow_reverse(torch.from_numpy(zp.T.copy())[None], g)[0].T.numpy()
+    assert np.abs(z_ref - emulate.flow_reverse(zp, blobs, a, sid)).max() < 5e-6
+    o_ref = orc.decoder(torch.from_numpy(z_ref.T.copy())[None], g)[0, 0].numpy()
+    assert np.abs(o_ref - emulate.decoder(z_ref, blobs, a, sid)).max() < 5e-6
+    assert opts["dp.ea_m"] == float(W["dp.flows.0.m"][0, 0])
+
+
+def test_tc_weight_layout_and_bf16_rounding():
+    rs = np.random.RandomState(0)
+    w = rs.randn(3, 32, 48).astype(np.float32)          # [taps, cin, n]
+    out = {}
+    packing.pack_conv(out, "c", w, rs.randn(48).astype(np.float32), tc=True)
+    wt = out["c.wtc"]
+    assert wt.dtype == np.uint16 and wt.shape == (3, 4, 48, 8)
+    back = (wt.astype(np.uint32) << 16).view(np.float32)
+    # [tap][ci/8][n][8] -> element (tap, ci, n)
+    assert np.array_equal(back[1, 2, 5, 3], packing.bf16_round(w)[1, 2 * 8 + 3, 5])
+    # round-to-nearest-even against torch
+    x = rs.randn(1000).astype(np.float32)
+    assert np.array_equal(packing.bf16_round(x), torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy())
+    # N not a multiple of 16 / cin not a multiple of 16 -> no tensor-core blob
+    out2 = {}
+    packing.pack_conv(out2, "d", rs.randn(1, 32, 29).astype(np.float32), None, tc=True)
+    assert "d.wtc" not in out2 and out2["d.w"].shape == (1, 32, 32)
