@@ -24,7 +24,9 @@
 #endif
 
 #define TC_M 128
-#define TC_THREADS 192
+#define TC_THREADS 320
+#define TC_LOAD_THREADS 128
+#define TC_EPI_PITCH 36            // floats per staged row: 16 B aligned, conflict-free for 8-lane phases
 #define TC_PIECE_CH 64
 #define TC_MAX_STAGES 24
 #define TC_SPIN_LIMIT (1u << 28)
@@ -43,6 +45,9 @@ struct TcCfg {
     int a_bytes;
     int smem_bytes;
     int vec;          // epilogue may use 128-bit accesses
+    int nabuf;        // activation tile buffers (1 or 2)
+    int naccbuf;      // TMEM accumulator buffers (1 or 2)
+    int epi_off;      // byte offset of the epilogue transpose buffers (4 warps x 32 x TC_EPI_PITCH floats)
 };
 
 namespace tc {
@@ -132,28 +137,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 }  // namespace tc
 
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Warp-specialised persistent kernel (TC_THREADS = 320):
+//   warps 0-3  epilogue  (TMEM -> registers -> global), one TMEM lane quadrant each
+//   warps 4-7  activation loaders (global fp32 -> lrelu -> bf16 -> smem operand tile)
+//   warp  8    weight producer (lane 0) + TMEM allocator
+//   warp  9    MMA issuer (lane 0)
+// Activation tiles and TMEM accumulators are double-buffered when they fit, so the load of tile
+// i+1, the MMAs of tile i and the epilogue of tile i-1 overlap inside one CTA.
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const TcCfg c) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sW = smem + c.a_bytes;
+    uint8_t* sW = smem + (size_t)c.nabuf * c.a_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)c.nstages * c.slot_bytes);
-    // bars: full[nstages], empty[nstages], a_full, acc_full ; then tmem ptr
+    // bars: w_full[nstages], w_empty[nstages], a_full[2], a_empty[2], acc_full[2], acc_empty[2]; then tmem ptr
     const uint32_t bar_full0 = tc::smem_u32(bars);
     const uint32_t bar_empty0 = bar_full0 + 8u * c.nstages;
-    const uint32_t bar_afull = bar_empty0 + 8u * c.nstages;
-    const uint32_t bar_acc = bar_afull + 8u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 2);
+    const uint32_t bar_afull0 = bar_empty0 + 8u * c.nstages;
+    const uint32_t bar_aempty0 = bar_afull0 + 16u;
+    const uint32_t bar_accfull0 = bar_aempty0 + 16u;
+    const uint32_t bar_accempty0 = bar_accfull0 + 16u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ny = blockIdx.y;
 
     if (tid == 0) {
         for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
-        tc::mbar_init(bar_afull, 128);
-        tc::mbar_init(bar_acc, 1);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(bar_afull0 + 8u * i, TC_LOAD_THREADS);
+            tc::mbar_init(bar_aempty0 + 8u * i, 1);
+            tc::mbar_init(bar_accfull0 + 8u * i, 1);
+            tc::mbar_init(bar_accempty0 + 8u * i, 128);
+        }
         tc::fence_mbar_init();
     }
-    if (warp == 4) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
+    if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -164,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
     const uint32_t lbo_b = (uint32_t)c.ntile * 16u;
 
     if (warp < 4) {
-        // ================= activation loader + epilogue (128 threads) =================
+        // ================= epilogue (128 threads) =================
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
             const int b = find_segment(a.tile_cu, a.B, tile);
@@ -172,87 +196,153 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
-            // previous tile's MMAs are complete (we waited on acc_full) -> sA may be overwritten
-            const int items = c.rows_a * kc_total;
-            for (int i = tid; i < items; i += 128) {
-                const int r = i / kc_total, kc = i - r * kc_total;
-                const int t = t0 + c.min_off + r;
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (t >= 0 && t < len) {
-                    const float4* src = reinterpret_cast<const float4*>(a.x + (row0 + t) * a.ldx + a.xcol + kc * 8);
-                    float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                    if (a.in_act) {
-                        v0.x = leaky(v0.x, a.in_slope); v0.y = leaky(v0.y, a.in_slope); v0.z = leaky(v0.z, a.in_slope); v0.w = leaky(v0.w, a.in_slope);
-                        v1.x = leaky(v1.x, a.in_slope); v1.y = leaky(v1.y, a.in_slope); v1.z = leaky(v1.z, a.in_slope); v1.w = leaky(v1.w, a.in_slope);
-                    }
-                    pk.x = tc::pack_bf16(v0.x, v0.y); pk.y = tc::pack_bf16(v0.z, v0.w);
-                    pk.z = tc::pack_bf16(v1.x, v1.y); pk.w = tc::pack_bf16(v1.z, v1.w);
-                }
-                *reinterpret_cast<uint4*>(sA + ((size_t)kc * c.rows_a + r) * 16) = pk;
-            }
-            tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            tc::mbar_arrive(bar_afull);
-            // ---- epilogue
-            tc::mbar_wait(bar_acc, it & 1);
+            const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
+            tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
             tc::tc_fence_after();
-            const int m = warp * 32 + lane;
-            const int t = t0 + m;
-            const bool rowok = (t < len);
-            const long row = row0 + t;
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int n0 = 0; n0 < c.ntile; n0 += 16) {
-                float v[16];
-                tc::tmem_ld16(trow + (uint32_t)n0, v);
-                const int ng = ny * c.ntile + n0;           // global output column of v[0]
-                if (!rowok || ng >= a.n) continue;
-                if (a.epi == EPI_GATE) {
-                    // interleaved (tanh-arg, sigmoid-arg) column pairs; commons.py:99-106
-                    const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
-                    float g[8];
+            // Two-phase epilogue.  Phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias /
+            // gate, then a warp-private smem transpose buffer.  Phase 2 (8 lanes = 128 contiguous bytes of one row,
+            // 4 rows per warp instruction): residual / accumulate / activation with fully coalesced 128-bit global
+            // accesses.  (A thread-per-row epilogue touches 32 different 128 B lines per instruction.)
+            float* sE = reinterpret_cast<float*>(smem + c.epi_off) + warp * (32 * TC_EPI_PITCH);
+            const int trow0 = t0 + warp * 32;                 // first time row of this warp
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + cbuf * (uint32_t)c.ntile;
+            const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
+            const bool gate = (a.epi == EPI_GATE);
+            for (int n0 = 0; n0 < c.ntile; n0 += 32) {
+                const int ng = ny * c.ntile + n0;             // global accumulator column of this 32-wide group
+                const int ncols = min(32, c.ntile - n0);      // 16 or 32
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float va = v[2 * j], vb = v[2 * j + 1];
-                        const int n = ng + 2 * j;
-                        if (n + 1 < a.n) {
-                            if (a.bias) { va += __ldg(a.bias + n); vb += __ldg(a.bias + n + 1); }
-                            if (ur) { va += __ldg(ur + n); vb += __ldg(ur + n + 1); }
-                        }
-                        g[j] = tanhf(va) * (1.f / (1.f + expf(-vb)));
-                    }
-                    float* dst = a.out + row * a.ldo + a.ocol + (ng >> 1);
-                    if (c.vec && ng + 16 <= a.n) {
-                        *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(g[4], g[5], g[6], g[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) if (ng + 2 * j + 1 < a.n) dst[j] = g[j];
-                    }
-                } else if (c.vec && a.epi == EPI_STORE && ng + 16 <= a.n) {
-                    // fast path: 128-bit bias / residual / accumulate / store
-                    const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld + ng) : nullptr;
-                    float* dst = a.out + row * a.ldo + a.ocol + ng;
-                    const float* rs = a.res ? (a.res + row * a.ldres + a.rescol + ng) : nullptr;
+                for (int hcol = 0; hcol < 32; hcol += 16) {
+                    if (hcol >= ncols) break;
+                    float v[16];
+                    tc::tmem_ld16(trow + (uint32_t)(n0 + hcol), v);
+                    const int nc = ng + hcol;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (a.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + ng) + q); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-                        if (ur) { const float4 uu = __ldg(reinterpret_cast<const float4*>(ur) + q); o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w; }
-                        if (rs) { const float4 rr = *(reinterpret_cast<const float4*>(rs) + q); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                        if (nc + 4 * q < a.npad) {
+                            if (a.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nc) + q); v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w; }
+                            if (ur) { const float4 uu = __ldg(reinterpret_cast<const float4*>(ur + nc) + q); v[4 * q] += uu.x; v[4 * q + 1] += uu.y; v[4 * q + 2] += uu.z; v[4 * q + 3] += uu.w; }
+                        }
+                    }
+                    float* srow = sE + lane * TC_EPI_PITCH;
+                    if (gate) {
+                        // interleaved (tanh-arg, sigmoid-arg) pairs (commons.py:99-106); MUFU tanh: the gate output is
+                        // rounded to bf16 by the next conv's loader, far coarser than tanh.approx's 2^-11
+                        float g[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) g[j] = tanh_fast(v[2 * j]) * fmaf(0.5f, tanh_fast(0.5f * v[2 * j + 1]), 0.5f);
+                        *reinterpret_cast<float4*>(srow + (hcol >> 1)) = make_float4(g[0], g[1], g[2], g[3]);
+                        *reinterpret_cast<float4*>(srow + (hcol >> 1) + 4) = make_float4(g[4], g[5], g[6], g[7]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<float4*>(srow + hcol + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2
+                const int ocols = gate ? (ncols >> 1) : ncols;          // staged output columns of this group
+                const int og = gate ? (ng >> 1) : ng;                   // first output column
+                const int olim = gate ? (a.n >> 1) : a.n;               // valid output columns
+                const int cq = (lane & 7) * 4;
+                if (c.vec) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; itr++) {
+                        const int rl = itr * 4 + (lane >> 3);
+                        const int t = trow0 + rl;
+                        if (t >= len || cq >= ocols || og + cq >= olim) continue;
+                        const long row = row0 + t;
+                        const int n = og + cq;
+                        float4 o = *reinterpret_cast<const float4*>(sE + rl * TC_EPI_PITCH + cq);
+                        if (a.epi == EPI_SUBFROM) {
+                            const float4 rr = *reinterpret_cast<const float4*>(a.res + row * a.ldres + a.rescol + n);
+                            *reinterpret_cast<float4*>(a.out + row * a.ldo + a.ocol + n) = make_float4(rr.x - o.x, rr.y - o.y, rr.z - o.z, rr.w - o.w);
+                            continue;
+                        }
+                        float* dst; int acc;
+                        if (a.epi == EPI_SPLIT && n >= a.split) { dst = a.out2 + row * a.ldo2 + a.ocol2 + (n - a.split); acc = a.accumulate2; }
+                        else { dst = a.out + row * a.ldo + a.ocol + n; acc = a.accumulate; }
+                        if (a.res) { const float4 rr = *reinterpret_cast<const float4*>(a.res + row * a.ldres + a.rescol + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
                         if (a.out_act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        if (a.accumulate) { const float4 pp = *(reinterpret_cast<const float4*>(dst) + q); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
+                        if (acc) { const float4 pp = *reinterpret_cast<const float4*>(dst); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
                         if (a.out_div != 1.f) { o.x = o.x / a.out_div; o.y = o.y / a.out_div; o.z = o.z / a.out_div; o.w = o.w / a.out_div; }
                         if (a.out_act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-                        *(reinterpret_cast<float4*>(dst) + q) = o;
+                        *reinterpret_cast<float4*>(dst) = o;
                     }
                 } else {
+                    // unaligned / ragged-N fallback: scalar, still row-contiguous per warp instruction
+                    for (int rl = 0; rl < 32; rl++) {
+                        const int t = trow0 + rl;
+                        if (t >= len) break;
+                        const long row = row0 + t;
+                        if (lane < ocols && og + lane < olim) {
+                            const float val = sE[rl * TC_EPI_PITCH + lane];
+                            if (gate) a.out[row * a.ldo + a.ocol + og + lane] = val;
+                            else {
+                                ConvArgs a2 = a; a2.bias = nullptr; a2.utab = nullptr;      // already applied in phase 1
+                                conv_epilogue_store(a2, b, row, og + lane, val);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
+            tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
+        }
+    } else if (warp < 8) {
+        // ================= activation loaders (128 threads) =================
+        const int lt = tid - 128;
+        uint32_t it = 0;
+        const int items = c.rows_a * kc_total;
+        const int dr = TC_LOAD_THREADS / kc_total, dk = TC_LOAD_THREADS - dr * kc_total;   // advance of (r, kc) per 128 items
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            const int b = find_segment(a.tile_cu, a.B, tile);
+            const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
+            const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
+            const long row0 = (long)cb0 * a.rate;
+            const int len = (cb1 - cb0) * a.rate;
+            const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
+            tc::mbar_wait(bar_aempty0 + 8u * abuf, (ause & 1u) ^ 1u);     // MMAs that read this buffer have retired
+            uint8_t* dstA = sA + (size_t)abuf * c.a_bytes;
+            // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
+            // flight per thread before any conversion so the load latency is paid once per batch
+            int r = lt / kc_total, kc = lt - r * kc_total;
+            for (int base = lt; base < items; base += 4 * TC_LOAD_THREADS) {
+                float4 v0[4], v1[4];
+                int rr[4], kk[4];
+                bool ok[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (ng + j < a.n) conv_epilogue_store(a, b, row, ng + j, v[j]);
+                for (int u = 0; u < 4; u++) {
+                    rr[u] = r; kk[u] = kc;
+                    const int t = t0 + c.min_off + r;
+                    ok[u] = (base + u * TC_LOAD_THREADS < items);
+                    v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
+                    if (ok[u] && t >= 0 && t < len) {
+                        const float4* src = reinterpret_cast<const float4*>(a.x + (row0 + t) * a.ldx + a.xcol + kc * 8);
+                        v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
+                    }
+                    r += dr; kc += dk;
+                    if (kc >= kc_total) { kc -= kc_total; r++; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (!ok[u]) continue;
+                    float4 a0 = v0[u], a1 = v1[u];
+                    if (a.in_act) {
+                        a0.x = leaky(a0.x, a.in_slope); a0.y = leaky(a0.y, a.in_slope); a0.z = leaky(a0.z, a.in_slope); a0.w = leaky(a0.w, a.in_slope);
+                        a1.x = leaky(a1.x, a.in_slope); a1.y = leaky(a1.y, a.in_slope); a1.z = leaky(a1.z, a.in_slope); a1.w = leaky(a1.w, a.in_slope);
+                    }
+                    uint4 pk;
+                    pk.x = tc::pack_bf16(a0.x, a0.y); pk.y = tc::pack_bf16(a0.z, a0.w);
+                    pk.z = tc::pack_bf16(a1.x, a1.y); pk.w = tc::pack_bf16(a1.z, a1.w);
+                    *reinterpret_cast<uint4*>(dstA + ((size_t)kk[u] * c.rows_a + rr[u]) * 16) = pk;
                 }
             }
-            tc::tc_fence_before();   // TMEM reads done before the next tile's a_full arrive releases the MMA warp
+            tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc::mbar_arrive(bar_afull0 + 8u * abuf);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= weight producer (one thread, cp.async.bulk ring) =================
         if (lane == 0) {
             uint32_t gp = 0;
@@ -279,10 +369,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc(TC_M, c.ntile);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
+            const uint64_t dhi_a = tc::make_desc(0, lbo_a, 128u), dhi_b = tc::make_desc(0, lbo_b, 128u);   // start-address field = 0
             uint32_t gp = 0, it = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-                tc::mbar_wait(bar_afull, it & 1);
+                const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
+                const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
+                tc::mbar_wait(bar_afull0 + 8u * abuf, ause & 1u);
+                tc::mbar_wait(bar_accempty0 + 8u * cbuf, (cuse & 1u) ^ 1u);
                 tc::tc_fence_after();
+                const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
+                const uint32_t abase = sA_u + abuf * (uint32_t)c.a_bytes;
                 uint32_t accum = 0;
                 for (int p = 0; p < c.npieces; p++, gp++) {
                     const int tap = p / c.cpt, cc = p - tap * c.cpt;
@@ -294,23 +390,25 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
                         tc::tc_fence_after();
                     }
                     const uint32_t arow = (uint32_t)(a.toff[tap] - c.min_off);
-                    const uint32_t a0 = sA_u + (uint32_t)(ch0 >> 3) * lbo_a + arow * 16u;
-                    const uint32_t b0 = sW_u + s * (uint32_t)c.slot_bytes;
+                    // descriptors differ only in the 14-bit start-address field (bytes >> 4); no carry can reach bit 14
+                    uint64_t ad = dhi_a | (uint64_t)(((abase + (uint32_t)(ch0 >> 3) * lbo_a + arow * 16u) >> 4) & 0x3FFF);
+                    uint64_t bd = dhi_b | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                    const uint64_t ad_step = (uint64_t)((2u * lbo_a) >> 4), bd_step = (uint64_t)((2u * lbo_b) >> 4);
                     for (int k = 0; k < nk16; k++) {
-                        const uint64_t ad = tc::make_desc(a0 + (uint32_t)(2 * k) * lbo_a, lbo_a, 128u);
-                        const uint64_t bd = tc::make_desc(b0 + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
-                        tc::umma_bf16(tmem_base, ad, bd, idesc, accum);
+                        tc::umma_bf16(dcol, ad, bd, idesc, accum);
                         accum = 1;
+                        ad += ad_step; bd += bd_step;
                     }
                     if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);   // frees the weight slot when these MMAs retire
                 }
-                tc::umma_commit(bar_acc);                                     // accumulator ready for the epilogue
+                tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
+                tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
+    if (warp == 8) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -339,14 +437,18 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     for (;;) {
         c.ntile = nt;
         c.slot_bytes = c.piece_ch * nt * 2;
-        const int bar_bytes = (2 * TC_MAX_STAGES + 2) * 8 + 16;
+        const int epi_bytes = 4 * 32 * TC_EPI_PITCH * 4;
+        const int bar_bytes = (2 * TC_MAX_STAGES + 8) * 8 + 16 + epi_bytes + 128;
         const long res_bytes = (long)c.npieces * c.slot_bytes;
-        if (c.npieces <= TC_MAX_STAGES && res_bytes <= 72 * 1024 && c.a_bytes + res_bytes + bar_bytes <= limit) {
+        c.nabuf = 2;
+        if (c.npieces <= TC_MAX_STAGES && res_bytes <= 72 * 1024 && 2 * c.a_bytes + res_bytes + bar_bytes <= limit) {
             c.resident = 1; c.nstages = c.npieces;
         } else {
             c.resident = 0; c.nstages = c.npieces < 4 ? c.npieces : 4;
+            if (2 * c.a_bytes + c.nstages * c.slot_bytes + bar_bytes > limit) c.nabuf = 1;
         }
-        c.smem_bytes = c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 2) * 8 + 16;
+        c.epi_off = (c.nabuf * c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 8) * 8 + 16 + 127) / 128 * 128;
+        c.smem_bytes = c.epi_off + epi_bytes;
         if (c.smem_bytes <= limit) break;
         // shrink the N tile (keeps divisibility of npad16)
         int next = 0;
@@ -354,7 +456,8 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
         if (!next) return false;
         nt = next;
     }
-    int tc_cols = 32; while (tc_cols < c.ntile) tc_cols <<= 1;
+    c.naccbuf = (2 * c.ntile <= 512) ? 2 : 1;
+    int tc_cols = 32; while (tc_cols < c.naccbuf * c.ntile) tc_cols <<= 1;
     c.tmem_cols = tc_cols;
     c.vec = (a.ldo % 4 == 0) && (a.ocol % 4 == 0) && (!a.res || (a.ldres % 4 == 0 && a.rescol % 4 == 0)) &&
             (!a.utab || a.utab_ld % 4 == 0);
@@ -365,15 +468,27 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
 static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStream_t st) {
     TcCfg c;
     if (!conv_tc_plan(a, c)) return cudaErrorInvalidConfiguration;
-    static int max_set = 0;
-    if (c.smem_bytes > max_set) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        max_set = 227 * 1024;
+        e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
     }
-    int occ = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_tc, TC_THREADS, c.smem_bytes);
-    if (e != cudaSuccess) return e;
+    // resident CTAs per SM: shared memory (228 KB/SM, 1 KB reserved per CTA), registers (64K / (regs * threads)),
+    // TMEM columns (512 / tmem_cols)
+    static int regs_per_thread = 0;
+    if (!regs_per_thread) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_conv_tc) == cudaSuccess && fa.numRegs > 0) regs_per_thread = fa.numRegs; else regs_per_thread = 96;
+    }
+    int occ = (228 * 1024) / (c.smem_bytes + 1024);
+    const int reg_occ = 65536 / (((regs_per_thread + 7) / 8 * 8) * TC_THREADS);
+    if (occ > reg_occ) occ = reg_occ;
+    if (occ > 8) occ = 8;
     if (occ < 1) occ = 1;
     const int tmem_occ = 512 / c.tmem_cols;
     if (occ > tmem_occ) occ = tmem_occ;

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "conv_tc.cuh"
+#include "mrf_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -185,7 +186,7 @@ int mkdds(vits_handle* h, std::vector<DdsP>& v, const std::string& name, int C) 
 // ------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------
-struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; int n64, n128, n256; int B; int rate; };
+struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; const int* tx; int n64, n128, n256, nx, tmx; int B; int rate; };
 
 ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out, int ldo, int ocol) {
     ConvArgs a;
@@ -264,14 +265,14 @@ void resolve_stage_events(vits_handle* h) {
 // build per-rate tile tables on the host and upload them in one copy
 struct TileBuilder {
     std::vector<int> host;
-    struct Ent { int rate; size_t o64, o128, o256; int n64, n128, n256; };
+    struct Ent { int rate; size_t o64, o128, o256, ox; int n64, n128, n256, nx, tmx; };
     std::vector<Ent> ents;
     size_t cu_off = 0; int B = 0;
     void begin(const int* cu_local, int B_) {
         B = B_; host.assign(cu_local, cu_local + B + 1); cu_off = 0; ents.clear();
     }
-    void add(int rate) {
-        Ent e; e.rate = rate;
+    void add(int rate, int tm_extra = 0) {
+        Ent e; e.rate = rate; e.ox = 0; e.nx = 0; e.tmx = tm_extra;
         auto build = [&](int tm, int& n) {
             size_t off = host.size();
             int acc = 0;
@@ -284,12 +285,14 @@ struct TileBuilder {
             return off;
         };
         e.o64 = build(64, e.n64); e.o128 = build(128, e.n128); e.o256 = build(256, e.n256);
+        if (tm_extra > 0) e.ox = build(tm_extra, e.nx);
         ents.push_back(e);
     }
     Tiles get(const int* dev, int rate) const {
         for (auto& e : ents) if (e.rate == rate) {
             Tiles t; t.cu = dev + cu_off; t.t64 = dev + e.o64; t.t128 = dev + e.o128; t.t256 = dev + e.o256;
-            t.n64 = e.n64; t.n128 = e.n128; t.n256 = e.n256; t.B = B; t.rate = rate; return t;
+            t.n64 = e.n64; t.n128 = e.n128; t.n256 = e.n256; t.B = B; t.rate = rate;
+            t.tx = dev + e.ox; t.nx = e.nx; t.tmx = e.tmx; return t;
         }
         Tiles t; memset(&t, 0, sizeof t); return t;
     }
@@ -665,8 +668,27 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         const int f_lo = h->h_cu_y[b_lo];
         std::vector<int> cu_local(nB + 1);
         for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
+        // fused MRF stage kernel (mrf_tc.cuh) where the stage qualifies: bf16 mode, ResBlock2, 32/64 channels
+        std::vector<MrfArgs> mrf_args(A.n_ups + 1);
+        std::vector<MrfCfg> mrf_cfg(A.n_ups + 1);
+        std::vector<int> mrf_on(A.n_ups + 1, 0);
+        for (int i = 0; i < A.n_ups; i++) {
+            const int co = chans[i + 1];
+            if (h->precision != 1 || A.resblock_type != 2 || A.n_rbk > MRF_MAX_RB || h->opts["no_fused_mrf"] != 0) continue;
+            MrfArgs& m = mrf_args[i + 1];
+            memset(&m, 0, sizeof m);
+            m.C = co; m.nrb = A.n_rbk; m.out_div = (float)A.n_rbk; m.slope = 0.1f;
+            bool ok = true;
+            for (int j = 0; j < A.n_rbk; j++) {
+                const auto& cv = h->rb_c1[i * A.n_rbk + j];
+                if (A.rb_ndil[j] != 2 || !cv[0].wtc || !cv[1].wtc) { ok = false; break; }
+                m.k[j] = A.rb_kernels[j]; m.d1[j] = A.rb_dilations[j][0]; m.d2[j] = A.rb_dilations[j][1];
+                m.w[j][0] = cv[0].wtc; m.w[j][1] = cv[1].wtc; m.b[j][0] = cv[0].b; m.b[j][1] = cv[1].b;
+            }
+            if (ok && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
+        }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
-        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i]);
+        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i], mrf_on[i] ? mrf_cfg[i].t_out : 0);
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
             (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) ||
@@ -742,6 +764,15 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             if ((rc = launch_conv(h, a, Tin, true))) return rc;
             a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
             if ((rc = launch_conv(h, a, Tin, true))) return rc;
+            if (mrf_on[i + 1]) {
+                MrfArgs& m = mrf_args[i + 1];
+                m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
+                if (m.ntiles > 0) {
+                    cudaError_t e = mrf_tc_launch(m, mrf_cfg[i + 1], h->num_sms, st);
+                    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf_tc launch: %s", cudaGetErrorString(e));
+                    h->launches++;
+                }
+            } else
             for (int j = 0; j < A.n_rbk; j++) {
                 const int n = i * A.n_rbk + j;
                 const bool first = (j == 0), last = (j == A.n_rbk - 1);
