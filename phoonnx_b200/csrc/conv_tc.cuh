@@ -29,7 +29,7 @@
 #define TC_EPI_PITCH 36            // floats per staged row: 16 B aligned, conflict-free for 8-lane phases
 #define TC_PIECE_CH 64
 #define TC_MAX_STAGES 24
-#define TC_SPIN_LIMIT (1u << 28)
+#define TC_SPIN_LIMIT (1u << 24)
 
 struct TcCfg {
     int ntile;        // N columns per CTA (multiple of 16, <= 256)
@@ -64,16 +64,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips (or the hint expires)
+    // instead of spinning -- a hot spin loop in 8 waiting warps starves the single MMA-issuing thread of issue slots
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 // bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if (++spins > TC_SPIN_LIMIT) __trap();
+        if (++spins > 64u) __nanosleep(spins > 4096u ? 256 : 32);
+        if (spins > TC_SPIN_LIMIT) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -345,22 +348,23 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
     } else if (warp == 8) {
         // ================= weight producer (one thread, cp.async.bulk ring) =================
         if (lane == 0) {
-            uint32_t gp = 0;
+            uint32_t s = 0, ph = 1;                       // ring slot and the parity to wait for on its "empty" barrier
             const uint32_t kc_bytes = (uint32_t)c.ntile * 16u;
+            const uint32_t sW_u = tc::smem_u32(sW);
+            const long kc_stride = (long)a.npad16 * 8;          // elements between consecutive 8-channel chunks
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 if (c.resident && tile != (int)blockIdx.x) break;
-                for (int p = 0; p < c.npieces; p++, gp++) {
-                    const int tap = p / c.cpt, cc = p - tap * c.cpt;
-                    const int ch0 = cc * c.piece_ch;
-                    const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
-                    const uint32_t s = gp % (uint32_t)c.nstages;
-                    if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ((gp / (uint32_t)c.nstages) & 1u) ^ 1u);
-                    const uint32_t fb = bar_full0 + 8u * s;
-                    tc::mbar_expect_tx(fb, kc_bytes * (uint32_t)nkc);
-                    const uint32_t dst = tc::smem_u32(sW + (size_t)s * c.slot_bytes);
-                    const __nv_bfloat16* src = a.wtc + (((long)tap * kc_total + (ch0 >> 3)) * a.npad16 + (long)ny * c.ntile) * 8;
-                    for (int kc = 0; kc < nkc; kc++)
-                        tc::bulk_g2s(dst + (uint32_t)kc * kc_bytes, src + (long)kc * a.npad16 * 8, kc_bytes, fb);
+                const __nv_bfloat16* src = a.wtc + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
+                for (int tap = 0; tap < a.ntaps; tap++) {
+                    for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
+                        const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
+                        if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
+                        const uint32_t fb = bar_full0 + 8u * s;
+                        tc::mbar_expect_tx(fb, kc_bytes * (uint32_t)nkc);
+                        uint32_t dst = sW_u + s * (uint32_t)c.slot_bytes;
+                        for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s(dst, src, kc_bytes, fb);
+                        if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
+                    }
                 }
             }
         }
@@ -370,39 +374,39 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             const uint32_t idesc = tc::make_idesc(TC_M, c.ntile);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_a = tc::make_desc(0, lbo_a, 128u), dhi_b = tc::make_desc(0, lbo_b, 128u);   // start-address field = 0
-            uint32_t gp = 0, it = 0;
+            const uint64_t ad_step = (uint64_t)((2u * lbo_a) >> 4), bd_step = (uint64_t)((2u * lbo_b) >> 4);
+            const uint32_t piece_a16 = ((uint32_t)(c.piece_ch >> 3) * lbo_a) >> 4;     // A advance per 64-channel piece (16 B units)
+            uint32_t s = 0, ph = 0, it = 0;                   // ring slot / parity of its "full" barrier
+            uint32_t abuf = 0, aph = 0, cbuf = 0, cph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-                const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
-                const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
-                tc::mbar_wait(bar_afull0 + 8u * abuf, ause & 1u);
-                tc::mbar_wait(bar_accempty0 + 8u * cbuf, (cuse & 1u) ^ 1u);
+                tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
+                tc::mbar_wait(bar_accempty0 + 8u * cbuf, cph ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
-                const uint32_t abase = sA_u + abuf * (uint32_t)c.a_bytes;
+                const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
                 uint32_t accum = 0;
-                for (int p = 0; p < c.npieces; p++, gp++) {
-                    const int tap = p / c.cpt, cc = p - tap * c.cpt;
-                    const int ch0 = cc * c.piece_ch;
-                    const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
-                    const uint32_t s = c.resident ? (uint32_t)p : (gp % (uint32_t)c.nstages);
-                    if (!c.resident || it == 0) {
-                        tc::mbar_wait(bar_full0 + 8u * s, c.resident ? 0u : ((gp / (uint32_t)c.nstages) & 1u));
-                        tc::tc_fence_after();
+                for (int tap = 0; tap < a.ntaps; tap++) {
+                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap];
+                    for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch, arow16 += piece_a16) {
+                        const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
+                        if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
+                        // descriptors differ only in the 14-bit start-address field (bytes >> 4)
+                        uint64_t ad = dhi_a | (uint64_t)(arow16 & 0x3FFF);
+                        uint64_t bd = dhi_b | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                        for (int k = 0; k < nk16; k++) {
+                            tc::umma_bf16(dcol, ad, bd, idesc, accum);
+                            accum = 1;
+                            ad += ad_step; bd += bd_step;
+                        }
+                        if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);   // frees the weight slot when these MMAs retire
+                        if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
-                    const uint32_t arow = (uint32_t)(a.toff[tap] - c.min_off);
-                    // descriptors differ only in the 14-bit start-address field (bytes >> 4); no carry can reach bit 14
-                    uint64_t ad = dhi_a | (uint64_t)(((abase + (uint32_t)(ch0 >> 3) * lbo_a + arow * 16u) >> 4) & 0x3FFF);
-                    uint64_t bd = dhi_b | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
-                    const uint64_t ad_step = (uint64_t)((2u * lbo_a) >> 4), bd_step = (uint64_t)((2u * lbo_b) >> 4);
-                    for (int k = 0; k < nk16; k++) {
-                        tc::umma_bf16(dcol, ad, bd, idesc, accum);
-                        accum = 1;
-                        ad += ad_step; bd += bd_step;
-                    }
-                    if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);   // frees the weight slot when these MMAs retire
                 }
+                if (c.resident) s = 0;
                 tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
                 tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
+                if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
+                if (++cbuf == (uint32_t)c.naccbuf) { cbuf = 0; cph ^= 1u; }
             }
         }
     }

@@ -38,17 +38,19 @@ struct MrfCfg {
     int h1max;       // max conv1 half receptive field
     int t_out;       // span - 2*hmax
     int rx, rx1;     // rows of the two operand tiles (odd)
-    int x_bytes, x1_bytes;
+    int xf_bytes, x_bytes, x1_bytes;
     int slot_bytes, nstages, resident, npieces;
     int tmem_cols;
+    int bias_off;
     int smem_bytes;
 };
 
 template <int C, int OWN>
-__global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const MrfCfg c) {
+__global__ void __launch_bounds__(MRF_THREADS, (C == 32 && OWN == 1) ? 2 : 1) k_mrf_tc(const MrfArgs a, const MrfCfg c) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sX = smem;
-    uint8_t* sX1 = smem + c.x_bytes;
+    float* sXf = reinterpret_cast<float*>(smem);             // raw fp32 rows of x (bulk-copied; also the conv1 residual)
+    uint8_t* sX = smem + c.xf_bytes;
+    uint8_t* sX1 = sX + c.x_bytes;
     uint8_t* sW = sX1 + c.x1_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)c.nstages * c.slot_bytes);
     const uint32_t bar_full0 = tc::smem_u32(bars);
@@ -57,7 +59,9 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
     const uint32_t bar_x1 = bar_x + 8u;                      // x1 operand tile staged   (256 arrivals / resblock)
     const uint32_t bar_c1 = bar_x1 + 8u;                     // conv1 accumulators ready (commit / resblock)
     const uint32_t bar_c2 = bar_c1 + 8u;                     // conv2 accumulators ready (commit / tile)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 4);
+    const uint32_t bar_xf = bar_c2 + 8u;                     // raw x rows landed (bulk copy tx / tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 5);
+    float* sB = reinterpret_cast<float*>(smem + c.bias_off);   // bias1 of every resblock, then sum_r bias2_r
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -66,7 +70,13 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
         tc::mbar_init(bar_x1, MRF_EPI_THREADS);
         tc::mbar_init(bar_c1, 1);
         tc::mbar_init(bar_c2, 1);
+        tc::mbar_init(bar_xf, 1);
         tc::fence_mbar_init();
+    }
+    for (int i = tid; i < C; i += MRF_THREADS) {
+        float sum = 0.f;
+        for (int r = 0; r < a.nrb; r++) { sB[r * C + i] = __ldg(a.b[r][0] + i); sum += __ldg(a.b[r][1] + i); }
+        sB[a.nrb * C + i] = sum;
     }
     if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
@@ -81,68 +91,82 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
     if (warp < 8) {
         // ===================== loader + epilogues (256 threads) =====================
         const int q = warp & 3, hb = warp >> 2;
-        uint32_t ph_c1 = 0, ph_c2 = 0;
+        uint32_t ph_c1 = 0, ph_c2 = 0, ph_xf = 0;
+        // raw rows [max(tbase,0), min(tbase+rx,len)) of the tile's utterance: one contiguous bulk copy
+        auto issue_x_copy = [&](int tile) {
+            const int b = find_segment(a.tile_cu, a.B, tile);
+            const int o0 = (tile - __ldg(a.tile_cu + b)) * c.t_out;
+            const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
+            const long row0 = (long)cb0 * a.rate;
+            const int len = (cb1 - cb0) * a.rate;
+            const int tbase = o0 - c.hmax - c.h1max;
+            const int ts = tbase > 0 ? tbase : 0;
+            const int te = (tbase + c.rx < len) ? (tbase + c.rx) : len;
+            const uint32_t bytes = (uint32_t)(te - ts) * (uint32_t)(C * 4);
+            tc::mbar_expect_tx(bar_xf, bytes);
+            tc::bulk_g2s(tc::smem_u32(sXf), a.x + (row0 + ts) * C, bytes, bar_xf);
+        };
+        if (tid == 0 && (int)blockIdx.x < a.ntiles) issue_x_copy(blockIdx.x);
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int b = find_segment(a.tile_cu, a.B, tile);
             const int o0 = (tile - __ldg(a.tile_cu + b)) * c.t_out;
             const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
-            // ---- stage lrelu(x) as bf16 K-major chunks; rows outside the utterance are zero padding
+            const int tbase = o0 - c.hmax - c.h1max;
+            const int tstart = tbase > 0 ? tbase : 0;          // time row held at sXf row 0
+            // ---- smem -> smem: lrelu(x) as bf16 K-major chunks; rows outside the utterance are zero padding
+            tc::mbar_wait(bar_xf, ph_xf & 1); ph_xf++;
             {
                 const int items = c.rx * KC;
-                const int tbase = o0 - c.hmax - c.h1max;
-                constexpr int DR = MRF_EPI_THREADS / KC, DK = MRF_EPI_THREADS - DR * KC;
-                int r = tid / KC, kc = tid - r * KC;
-                for (int base = tid; base < items; base += 4 * MRF_EPI_THREADS) {
-                    float4 v0[4], v1[4];
-                    int rr[4], kk[4];
-                    bool ok[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        rr[u] = r; kk[u] = kc;
-                        const int t = tbase + r;
-                        ok[u] = (base + u * MRF_EPI_THREADS < items);
-                        v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
-                        if (ok[u] && t >= 0 && t < len) {
-                            const float4* src = reinterpret_cast<const float4*>(a.x + (row0 + t) * C + kc * 8);
-                            v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
-                        }
-                        r += DR; kc += DK;
-                        if (kc >= KC) { kc -= KC; r++; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (!ok[u]) continue;
-                        const float4 a0 = v0[u], a1 = v1[u];
-                        uint4 pk;
+                for (int i = tid; i < items; i += MRF_EPI_THREADS) {
+                    const int r = i / KC, kc = i - r * KC;
+                    const int t = tbase + r;
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    if (t >= 0 && t < len) {
+                        const float4* src = reinterpret_cast<const float4*>(sXf + (size_t)(t - tstart) * C + kc * 8);
+                        const float4 a0 = src[0], a1 = src[1];
                         pk.x = tc::pack_bf16(leaky(a0.x, a.slope), leaky(a0.y, a.slope)); pk.y = tc::pack_bf16(leaky(a0.z, a.slope), leaky(a0.w, a.slope));
                         pk.z = tc::pack_bf16(leaky(a1.x, a.slope), leaky(a1.y, a.slope)); pk.w = tc::pack_bf16(leaky(a1.z, a.slope), leaky(a1.w, a.slope));
-                        *reinterpret_cast<uint4*>(sX + ((size_t)kk[u] * c.rx + rr[u]) * 16) = pk;
                     }
+                    *reinterpret_cast<uint4*>(sX + ((size_t)kc * c.rx + r) * 16) = pk;
                 }
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_x);
 
-            // this thread's rows: block bb (= hb, hb+2, ...), window row wr = 128*bb + 32*q + lane
+            // this thread's rows: block bb (= hb, hb+2, ...), window row wr = 128*bb + 32*q + lane.
+            // The fp32 residual row is pulled into registers once per tile (it is the same for every resblock),
+            // after which the raw staging buffer is free and the NEXT tile's rows are prefetched under this tile.
+            float xrow[OWN][C];
+            bool inr[OWN];
             float xacc[OWN][C];                     // sum_r (x1_r + bias2_r) for the OWN blocks this thread owns
 #pragma unroll
-            for (int o = 0; o < OWN; o++)
+            for (int o = 0; o < OWN; o++) {
+                const int bb = hb + 2 * o;
+                const int tm = o0 - c.hmax + 128 * bb + 32 * q + lane;
+                inr[o] = (bb < c.nb) && (tm >= 0 && tm < len);
+                const float4* xr = reinterpret_cast<const float4*>(sXf + (size_t)(inr[o] ? (tm - tstart) : 0) * C);
 #pragma unroll
-                for (int j = 0; j < C; j++) xacc[o][j] = 0.f;
+                for (int j = 0; j < C / 4; j++) {
+                    const float4 xv = inr[o] ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xrow[o][4 * j] = xv.x; xrow[o][4 * j + 1] = xv.y; xrow[o][4 * j + 2] = xv.z; xrow[o][4 * j + 3] = xv.w;
+                    const float4 bs = *reinterpret_cast<const float4*>(sB + a.nrb * C + 4 * j);      // sum_r bias2_r
+                    xacc[o][4 * j] = bs.x; xacc[o][4 * j + 1] = bs.y; xacc[o][4 * j + 2] = bs.z; xacc[o][4 * j + 3] = bs.w;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(MRF_EPI_THREADS) : "memory");
+            if (tid == 0 && tile + (int)gridDim.x < a.ntiles) { tc::fence_proxy_async(); issue_x_copy(tile + gridDim.x); }
 
             for (int r = 0; r < a.nrb; r++) {
                 tc::mbar_wait(bar_c1, ph_c1 & 1); ph_c1++;
                 tc::tc_fence_after();
+                const float* b1 = sB + r * C;
 #pragma unroll
                 for (int o = 0; o < OWN; o++) {
                     const int bb = hb + 2 * o;
                     if (bb >= c.nb) break;
                     const int wr = 128 * bb + 32 * q + lane;
-                    const int tm = o0 - c.hmax + wr;
-                    const bool inr = (tm >= 0 && tm < len);
-                    const float* xr = a.x + (row0 + tm) * C;
                     const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(bb * C);
 #pragma unroll
                     for (int n0 = 0; n0 < C; n0 += 16) {
@@ -151,16 +175,13 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
                         uint32_t pk[8];
 #pragma unroll
                         for (int qd = 0; qd < 4; qd++) {
-                            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (inr) xv = __ldg(reinterpret_cast<const float4*>(xr + n0) + qd);
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.b[r][0] + n0) + qd);
-                            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.b[r][1] + n0) + qd);
+                            const float4 bv = *reinterpret_cast<const float4*>(b1 + n0 + 4 * qd);      // smem broadcast
                             float x1[4];
-                            x1[0] = v[4 * qd + 0] + b1.x + xv.x; x1[1] = v[4 * qd + 1] + b1.y + xv.y;
-                            x1[2] = v[4 * qd + 2] + b1.z + xv.z; x1[3] = v[4 * qd + 3] + b1.w + xv.w;
-                            if (!inr) { x1[0] = x1[1] = x1[2] = x1[3] = 0.f; }   // conv2 zero-pads x1 beyond the utterance
-                            xacc[o][n0 + 4 * qd + 0] += x1[0] + b2.x; xacc[o][n0 + 4 * qd + 1] += x1[1] + b2.y;
-                            xacc[o][n0 + 4 * qd + 2] += x1[2] + b2.z; xacc[o][n0 + 4 * qd + 3] += x1[3] + b2.w;
+                            x1[0] = v[4 * qd + 0] + bv.x + xrow[o][n0 + 4 * qd + 0]; x1[1] = v[4 * qd + 1] + bv.y + xrow[o][n0 + 4 * qd + 1];
+                            x1[2] = v[4 * qd + 2] + bv.z + xrow[o][n0 + 4 * qd + 2]; x1[3] = v[4 * qd + 3] + bv.w + xrow[o][n0 + 4 * qd + 3];
+                            if (!inr[o]) { x1[0] = x1[1] = x1[2] = x1[3] = 0.f; }   // conv2 zero-pads x1 beyond the utterance
+                            xacc[o][n0 + 4 * qd + 0] += x1[0]; xacc[o][n0 + 4 * qd + 1] += x1[1];
+                            xacc[o][n0 + 4 * qd + 2] += x1[2]; xacc[o][n0 + 4 * qd + 3] += x1[3];
                             pk[2 * qd + 0] = tc::pack_bf16(leaky(x1[0], a.slope), leaky(x1[1], a.slope));
                             pk[2 * qd + 1] = tc::pack_bf16(leaky(x1[2], a.slope), leaky(x1[3], a.slope));
                         }
@@ -208,19 +229,21 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
     } else if (warp == 8) {
         // ===================== weight producer =====================
         if (lane == 0) {
-            uint32_t gp = 0;
+            uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 if (c.resident && tile != (int)blockIdx.x) break;
                 for (int r = 0; r < a.nrb; r++)
-                    for (int cv = 0; cv < 2; cv++)
-                        for (int tap = 0; tap < a.k[r]; tap++, gp++) {
-                            const uint32_t s = gp % (uint32_t)c.nstages;
-                            if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ((gp / (uint32_t)c.nstages) & 1u) ^ 1u);
+                    for (int cv = 0; cv < 2; cv++) {
+                        const __nv_bfloat16* wsrc = a.w[r][cv];
+                        for (int tap = 0; tap < a.k[r]; tap++) {
+                            if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
                             const uint32_t fb = bar_full0 + 8u * s;
                             tc::mbar_expect_tx(fb, (uint32_t)c.slot_bytes);
-                            tc::bulk_g2s(tc::smem_u32(sW + (size_t)s * c.slot_bytes), a.w[r][cv] + (long)tap * C * C,
-                                         (uint32_t)c.slot_bytes, fb);
+                            tc::bulk_g2s(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb);
+                            wsrc += C * C;
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
+                    }
             }
         }
     } else {
@@ -228,43 +251,46 @@ __global__ void __launch_bounds__(MRF_THREADS) k_mrf_tc(const MrfArgs a, const M
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc(128, C);
             const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
-            uint32_t gp = 0, it = 0, ph_x1 = 0;
+            const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
+            const uint64_t bd_step = (uint64_t)((2u * lbo_w) >> 4);
+            const uint64_t ad_step_x = (uint64_t)((2u * lbo_x) >> 4), ad_step_x1 = (uint64_t)((2u * lbo_x1) >> 4);
+            const uint32_t x16 = (sX_u >> 4) + (uint32_t)c.h1max, x116 = (sX1_u >> 4) + (uint32_t)c.hmax;   // 16-byte units == rows
+            uint32_t s = 0, ph = 0, it = 0, ph_x1 = 0;          // ring slot / parity of its "full" barrier
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
                 tc::mbar_wait(bar_x, it & 1);
                 tc::tc_fence_after();
-                uint32_t p = 0;                                  // piece index within the tile (resident slot)
                 for (int r = 0; r < a.nrb; r++) {
+                    const int kr = a.k[r];
+#pragma unroll
                     for (int cv = 0; cv < 2; cv++) {
                         if (cv == 1) { tc::mbar_wait(bar_x1, ph_x1 & 1); ph_x1++; tc::tc_fence_after(); }
                         const int dil = cv ? a.d2[r] : a.d1[r];
-                        const int half = (a.k[r] - 1) / 2;
-                        for (int tap = 0; tap < a.k[r]; tap++, gp++, p++) {
-                            const uint32_t s = c.resident ? p : (gp % (uint32_t)c.nstages);
-                            if (!c.resident || it == 0) {
-                                tc::mbar_wait(bar_full0 + 8u * s, c.resident ? 0u : ((gp / (uint32_t)c.nstages) & 1u));
-                                tc::tc_fence_after();
-                            }
-                            const int off = (tap - half) * dil;
-                            const uint32_t wb = sW_u + s * (uint32_t)c.slot_bytes;
+                        const uint64_t dhi = cv ? dhi_x1 : dhi_x;
+                        const uint64_t ad_step = cv ? ad_step_x1 : ad_step_x;
+                        const uint32_t dcol0 = tmem_base + (cv ? acc2_col : 0u);
+                        uint32_t arow16 = (cv ? x116 : x16) - (uint32_t)(((kr - 1) >> 1) * dil);     // tap 0
+                        for (int tap = 0; tap < kr; tap++, arow16 += (uint32_t)dil) {
+                            if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
+                            const uint64_t bd0 = dhi_w | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                            // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks (and taps)
+                            const uint32_t acc0 = (tap > 0 || (cv && r > 0)) ? 1u : 0u;
                             for (int bb = 0; bb < c.nb; bb++) {
-                                const uint32_t arow = cv ? (uint32_t)(128 * bb + c.hmax + off) : (uint32_t)(128 * bb + c.h1max + off);
-                                const uint32_t abase = (cv ? sX1_u : sX_u) + arow * 16u;
-                                const uint32_t lbo_a = cv ? lbo_x1 : lbo_x;
-                                const uint32_t dcol = tmem_base + (cv ? acc2_col : 0u) + (uint32_t)(bb * C);
+                                uint64_t ad = dhi | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
+                                uint64_t bd = bd0;
+                                const uint32_t dcol = dcol0 + (uint32_t)(bb * C);
 #pragma unroll
                                 for (int k16 = 0; k16 < C / 16; k16++) {
-                                    const uint64_t ad = tc::make_desc(abase + (uint32_t)(2 * k16) * lbo_a, lbo_a, 128u);
-                                    const uint64_t bd = tc::make_desc(wb + (uint32_t)(2 * k16) * lbo_w, lbo_w, 128u);
-                                    // conv1: fresh accumulator per resblock; conv2: accumulates across resblocks
-                                    const uint32_t accum = cv ? ((r > 0 || tap > 0 || k16 > 0) ? 1u : 0u) : ((tap > 0 || k16 > 0) ? 1u : 0u);
-                                    tc::umma_bf16(dcol, ad, bd, idesc, accum);
+                                    tc::umma_bf16(dcol, ad, bd, idesc, k16 ? 1u : acc0);
+                                    ad += ad_step; bd += bd_step;
                                 }
                             }
                             if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
                         if (cv == 0) tc::umma_commit(bar_c1);
                     }
                 }
+                if (c.resident) { s = 0; }
                 tc::umma_commit(bar_c2);
             }
         }
@@ -294,12 +320,16 @@ static inline bool mrf_tc_plan(const MrfArgs& a, MrfCfg& c, int nb_pref) {
         if (c.t_out < 32) continue;
         c.rx = ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
         c.rx1 = ((c.span + 2 * hmax + 7) / 8) * 8 + 1;
+        c.xf_bytes = (c.rx * a.C * 4 + 127) / 128 * 128;
         c.x_bytes = ((a.C / 8) * c.rx * 16 + 127) / 128 * 128;
         c.x1_bytes = ((a.C / 8) * c.rx1 * 16 + 127) / 128 * 128;
         const long res_bytes = (long)npieces * c.slot_bytes;
-        if (npieces <= MRF_MAX_STAGES && res_bytes <= 64 * 1024) { c.resident = 1; c.nstages = npieces; }
-        else { c.resident = 0; c.nstages = 6; }
-        c.smem_bytes = c.x_bytes + c.x1_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 4) * 8 + 16;
+        // weights stay resident only when that does not cost a second CTA per SM
+        const long fixed = (long)c.xf_bytes + c.x_bytes + c.x1_bytes + 2048;
+        if (npieces <= MRF_MAX_STAGES && fixed + res_bytes <= 112 * 1024) { c.resident = 1; c.nstages = npieces; }
+        else { c.resident = 0; c.nstages = (c.slot_bytes <= 4096) ? 8 : 6; }
+        c.bias_off = (c.xf_bytes + c.x_bytes + c.x1_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 5) * 8 + 16 + 15) / 16 * 16;
+        c.smem_bytes = c.bias_off + (MRF_MAX_RB + 1) * a.C * 4;
         if (c.smem_bytes > 225 * 1024) continue;
         int cols = 32; while (cols < 2 * nb * a.C) cols <<= 1;
         c.tmem_cols = cols;
