@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--preset", default="medium")
     ap.add_argument("--max-ids", type=int, default=32768, help="phoneme ids per device batch")
-    ap.add_argument("--chunk-frames", type=int, default=8192)
+    ap.add_argument("--chunk-frames", type=int, default=32768)
     ap.add_argument("--cpu-sample", type=int, default=24, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -137,6 +137,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&p);
 }
+// the two bf16 halves of a packed word, widened back to fp32 (exact)
+__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 }  // namespace tc
 
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kc_total = a.cin >> 3;                    // 16-byte chunks per activation row
+    const int kc_total = a.cin >> 3;                    // 16-byte chunks per activation row (per plane)
+    const int nseg = a.split3 ? 3 : 1;                  // K segments per tap: [xh*wh | xh*wl | xl*wh]
     const uint32_t lbo_a = (uint32_t)c.rows_a * 16u;
     const uint32_t lbo_b = (uint32_t)c.ntile * 16u;
 
@@ -340,6 +344,15 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
                     pk.x = tc::pack_bf16(a0.x, a0.y); pk.y = tc::pack_bf16(a0.z, a0.w);
                     pk.z = tc::pack_bf16(a1.x, a1.y); pk.w = tc::pack_bf16(a1.z, a1.w);
                     *reinterpret_cast<uint4*>(dstA + ((size_t)kk[u] * c.rows_a + rr[u]) * 16) = pk;
+                    if (a.split3) {
+                        // lo plane: bf16(x - bf16(x)), exact subtraction in fp32
+                        uint4 lo;
+                        lo.x = tc::pack_bf16(a0.x - tc::bf16_lo_f(pk.x), a0.y - tc::bf16_hi_f(pk.x));
+                        lo.y = tc::pack_bf16(a0.z - tc::bf16_lo_f(pk.y), a0.w - tc::bf16_hi_f(pk.y));
+                        lo.z = tc::pack_bf16(a1.x - tc::bf16_lo_f(pk.z), a1.y - tc::bf16_hi_f(pk.z));
+                        lo.w = tc::pack_bf16(a1.z - tc::bf16_lo_f(pk.w), a1.w - tc::bf16_hi_f(pk.w));
+                        *reinterpret_cast<uint4*>(dstA + ((size_t)(kk[u] + kc_total) * c.rows_a + rr[u]) * 16) = lo;
+                    }
                 }
             }
             tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 if (c.resident && tile != (int)blockIdx.x) break;
                 const __nv_bfloat16* src = a.wtc + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
-                for (int tap = 0; tap < a.ntaps; tap++) {
+                for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
                         const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
                         if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
@@ -385,8 +398,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
                 const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
                 const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
                 uint32_t accum = 0;
-                for (int tap = 0; tap < a.ntaps; tap++) {
-                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap];
+                for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
+                    const int tap = a.split3 ? tapseg / 3 : tapseg;
+                    const int seg = tapseg - tap * nseg;
+                    // segment 2 multiplies the lo plane, which sits kc_total chunks behind the hi plane
+                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap] + (seg == 2 ? (((uint32_t)kc_total * lbo_a) >> 4) : 0u);
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch, arow16 += piece_a16) {
                         const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
                         if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
@@ -431,29 +447,39 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     int rows = TC_M + (mx - mn);
     rows = ((rows + 7) / 8) * 8 + 1;           // odd row count: (kc + r) mod 8 spreads 16 B chunks over all banks
     c.rows_a = rows;
-    c.a_bytes = ((a.cin / 8) * rows * 16 + 127) / 128 * 128;
+    const int planes = a.split3 ? 2 : 1, nseg = a.split3 ? 3 : 1;
+    c.a_bytes = (planes * (a.cin / 8) * rows * 16 + 127) / 128 * 128;
     c.piece_ch = a.cin < TC_PIECE_CH ? a.cin : TC_PIECE_CH;
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
-    c.npieces = a.ntaps * c.cpt;
+    c.npieces = a.ntaps * nseg * c.cpt;
     const int limit = 200 * 1024;
+    const int epi_bytes = 4 * 32 * TC_EPI_PITCH * 4;
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
     if (!nt) for (int cand = 256; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { nt = cand; break; }
     for (;;) {
         c.ntile = nt;
         c.slot_bytes = c.piece_ch * nt * 2;
-        const int epi_bytes = 4 * 32 * TC_EPI_PITCH * 4;
-        const int bar_bytes = (2 * TC_MAX_STAGES + 8) * 8 + 16 + epi_bytes + 128;
         const long res_bytes = (long)c.npieces * c.slot_bytes;
-        c.nabuf = 2;
-        if (c.npieces <= TC_MAX_STAGES && res_bytes <= 72 * 1024 && 2 * c.a_bytes + res_bytes + bar_bytes <= limit) {
-            c.resident = 1; c.nstages = c.npieces;
+        auto total = [&](int nabuf, int nstages) {
+            return (nabuf * c.a_bytes + nstages * c.slot_bytes + (2 * nstages + 8) * 8 + 16 + 127) / 128 * 128 + epi_bytes;
+        };
+        bool ok = false;
+        if (c.npieces <= TC_MAX_STAGES && res_bytes <= 72 * 1024 && total(2, c.npieces) <= limit) {
+            c.resident = 1; c.nstages = c.npieces; c.nabuf = 2; ok = true;
         } else {
-            c.resident = 0; c.nstages = c.npieces < 4 ? c.npieces : 4;
-            if (2 * c.a_bytes + c.nstages * c.slot_bytes + bar_bytes > limit) c.nabuf = 1;
+            // widest N tile first (the activation tile is re-read once per N tile), then double-buffered
+            // activations, then ring depth
+            c.resident = 0;
+            const int smax = c.npieces < 4 ? c.npieces : 4;
+            for (int nabuf = 2; nabuf >= 1 && !ok; nabuf--)
+                for (int ns = smax; ns >= (smax < 2 ? smax : 2) && !ok; ns--)
+                    if (total(nabuf, ns) <= limit) { c.nabuf = nabuf; c.nstages = ns; ok = true; }
         }
-        c.epi_off = (c.nabuf * c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 8) * 8 + 16 + 127) / 128 * 128;
-        c.smem_bytes = c.epi_off + epi_bytes;
-        if (c.smem_bytes <= limit) break;
+        if (ok) {
+            c.epi_off = (c.nabuf * c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 8) * 8 + 16 + 127) / 128 * 128;
+            c.smem_bytes = c.epi_off + epi_bytes;
+            break;
+        }
         // shrink the N tile (keeps divisibility of npad16)
         int next = 0;
         for (int cand = nt - 16; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { next = cand; break; }

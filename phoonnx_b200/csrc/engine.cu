@@ -11,8 +11,10 @@
 #include "../../include/vits_b200.h"
 #include "common.cuh"
 #include "kernels_f32.cuh"
+#include "attention.cuh"
 #include "conv_tc.cuh"
 #include "mrf_tc.cuh"
+#include "mrf2_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -28,9 +30,12 @@ namespace {
 
 struct DevBlob { void* p = nullptr; size_t bytes = 0; int dtype = 0; };
 
+#define CONV_MAX_SLICES 8
 struct ConvP {
     const float* w = nullptr; const __nv_bfloat16* wtc = nullptr; const float* b = nullptr;
     int cin = 0, n = 0, npad = 0, npad16 = 0, ntaps = 0; int toff[CONV_MAX_TAPS] = {0};
+    // fp32-faithful bf16x3 operands (text side): one blob per K slice of slice_cin input channels
+    const __nv_bfloat16* wtc3[CONV_MAX_SLICES] = {nullptr}; int nsl = 0, slice_cin = 0;
 };
 
 struct LnP { const float* g = nullptr; const float* b = nullptr; };
@@ -54,7 +59,8 @@ struct vits_handle {
     std::map<std::string, double> opts;
     bool finalized = false;
     int precision = 0;
-    int64_t max_chunk_frames = 8192;
+    int text_tc = 1;                 // bf16 mode: text-side GEMMs as bf16x3 on tcgen05 (0: fp32 CUDA cores)
+    int64_t max_chunk_frames = 32768;
     int64_t launches = 0;
     int num_sms = 148;
 
@@ -150,6 +156,21 @@ int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, co
     c.wtc = nullptr;
     if (t && t->dtype == 1 && cin % 16 == 0 && t->bytes >= (size_t)c.ntaps * cin * c.npad16 * 2)
         c.wtc = reinterpret_cast<const __nv_bfloat16*>(t->p);
+    // K slices of the bf16x3 form: largest divisor of cin that is a multiple of 16 and <= 192 (packing.split3_slice)
+    c.nsl = 0; c.slice_cin = 0;
+    if (cin % 16 == 0 && n % 16 == 0) {
+        int sl = 0;
+        for (int v = std::min(cin, 192); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
+        if (sl && cin / sl <= CONV_MAX_SLICES) {
+            bool all = true;
+            for (int j = 0; j < cin / sl; j++) {
+                const DevBlob* t3 = find_blob(h, name + ".wtc3." + std::to_string(j));
+                if (!t3 || t3->dtype != 1 || t3->bytes < (size_t)c.ntaps * 3 * sl * c.npad16 * 2) { all = false; break; }
+                c.wtc3[j] = reinterpret_cast<const __nv_bfloat16*>(t3->p);
+            }
+            if (all) { c.nsl = cin / sl; c.slice_cin = sl; }
+        }
+    }
     return 0;
 }
 
@@ -201,6 +222,7 @@ ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out
 
 int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     a.cu = T.cu; a.B = T.B; a.rate = T.rate;
+    a.split3 = 0;
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
         a.tile_cu = T.t128; a.ntiles = T.n128;
         if (T.n128 == 0) return 0;
@@ -215,6 +237,27 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     k_conv_f32<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+// Text-side convolution (encoder / duration predictor): in bf16 mode it runs on the tensor cores as an fp32-faithful
+// bf16x3 product, K-sliced so the hi+lo activation planes fit shared memory; slices after the first accumulate.
+int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T) {
+    const bool want = h->precision == 1 && h->text_tc && c.nsl > 0 && a.epi == EPI_STORE && a.ldx % 4 == 0 &&
+                      a.xcol % 4 == 0 && !(c.nsl > 1 && (a.out_act != ACT_NONE || a.out_div != 1.f));
+    if (!want) return launch_conv(h, a, T, false);
+    a.cu = T.cu; a.B = T.B; a.rate = T.rate;
+    a.tile_cu = T.t128; a.ntiles = T.n128;
+    if (T.n128 == 0) return 0;
+    const int xcol0 = a.xcol;
+    for (int j = 0; j < c.nsl; j++) {
+        ConvArgs s = a;
+        s.split3 = 1; s.wtc = c.wtc3[j]; s.cin = c.slice_cin; s.xcol = xcol0 + j * c.slice_cin;
+        if (j > 0) { s.bias = nullptr; s.utab = nullptr; s.res = nullptr; s.accumulate = 1; }
+        cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream);
+        if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc (bf16x3) launch: %s", cudaGetErrorString(e));
+        h->launches++;
+    }
     return 0;
 }
 
@@ -236,7 +279,7 @@ int run_dds(vits_handle* h, std::vector<DdsP>& L, float* x, float* tmp1, float* 
         int rc;
         if ((rc = launch_ln(h, x, tmp1, d.ln1, rows, C, 1, &d, T))) return rc;
         ConvArgs a = base_args(d.pw, tmp1, C, 0, tmp2, C, 0);
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, d.pw, a, T))) return rc;
         if ((rc = launch_ln(h, tmp2, x, d.ln2, rows, C, 2, nullptr, T))) return rc;
     }
     return 0;
@@ -345,6 +388,8 @@ int vits_set_option(vits_handle* h, const char* key, double value) {
     if (k == "precision") {
         if (value != 0 && value != 1) return fail(h, VITS_E_INVALID, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
         h->precision = (int)value;
+    } else if (k == "text_tc") {
+        h->text_tc = value != 0;
     } else if (k == "max_chunk_frames") {
         if (value < 1) return fail(h, VITS_E_INVALID, "max_chunk_frames must be >= 1");
         h->max_chunk_frames = (int64_t)value;
@@ -540,21 +585,27 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         for (int i = 0; i < A.n_layers; i++) {
             auto& L = h->enc[i];
             ConvArgs a = base_args(L.qkv, x, H, 0, qkv, 3 * H, 0);
-            if ((rc = launch_conv(h, a, T, false))) return rc;
-            k_rel_attention<<<dim3((R + 3) / 4, A.n_heads), 128, 4 * (dk + nrel) * sizeof(float), st>>>(
-                qkv, L.rel_k, L.rel_v, att, T.cu, B, (int)R, H, A.n_heads, dk, A.window);
+            if ((rc = launch_conv_text(h, L.qkv, a, T))) return rc;
+            cudaError_t ae = cudaSuccess;
+            if (h->opts["attention_v1"] == 0 &&
+                attention_tiled_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {
+                if (ae != cudaSuccess) return fail(h, VITS_E_CUDA, "attention launch: %s", cudaGetErrorString(ae));
+            } else {
+                k_rel_attention<<<dim3((R + 3) / 4, A.n_heads), 128, 4 * (dk + nrel) * sizeof(float), st>>>(
+                    qkv, L.rel_k, L.rel_v, att, T.cu, B, (int)R, H, A.n_heads, dk, A.window);
+            }
             h->launches++;
             a = base_args(L.o, att, H, 0, y, H, 0); a.res = x; a.ldres = H;
-            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_conv_text(h, L.o, a, T))) return rc;
             if ((rc = launch_ln(h, y, x, L.ln1, (int)R, H, 0, nullptr, T))) return rc;
             a = base_args(L.ffn1, x, H, 0, ffn, F, 0); a.out_act = ACT_RELU;
-            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_conv_text(h, L.ffn1, a, T))) return rc;
             a = base_args(L.ffn2, ffn, F, 0, y, H, 0); a.res = x; a.ldres = H;
-            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_conv_text(h, L.ffn2, a, T))) return rc;
             if ((rc = launch_ln(h, y, x, L.ln2, (int)R, H, 0, nullptr, T))) return rc;
         }
         ConvArgs a = base_args(h->enc_proj, x, H, 0, stats, 2 * C, 0);
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, h->enc_proj, a, T))) return rc;
     }
     // ---- duration predictor
     float* logw = ptr<float>(h->logw);
@@ -565,10 +616,10 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         float *z0 = ptr<float>(h->z0), *z1 = ptr<float>(h->z1);
         ConvArgs a = base_args(h->dp_pre, x, H, 0, d0, Fd, 0);
         if (A.n_speakers > 1) { a.utab = h->dp_cond_tab; a.uidx = d_sid; a.utab_ld = Fd; }
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, h->dp_pre, a, T))) return rc;
         if ((rc = run_dds(h, h->dp_dds, d0, d1, y, (int)R, Fd, T))) return rc;
         a = base_args(h->dp_proj, d0, Fd, 0, gdp, Fd, 0);
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, h->dp_proj, a, T))) return rc;
         k_noise_dp<<<(R + 255) / 256, 256, 0, st>>>(z0, z1, d_inj, dp_stride, T.cu, B, (int)R, h->scales[2], seed, h->utt_base);
         h->launches++;
         for (int k = 0; k < A.n_cflows; k++) {
@@ -597,10 +648,10 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
             xin = y;
         }
         ConvArgs a = base_args(h->dpd_c1, xin, H, 0, d0, Fd, 0); a.out_act = ACT_RELU;
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, h->dpd_c1, a, T))) return rc;
         if ((rc = launch_ln(h, d0, d0, h->dpd_n1, (int)R, Fd, 0, nullptr, T))) return rc;
         a = base_args(h->dpd_c2, d0, Fd, 0, d1, Fd, 0); a.out_act = ACT_RELU;
-        if ((rc = launch_conv(h, a, T, false))) return rc;
+        if ((rc = launch_conv_text(h, h->dpd_c2, a, T))) return rc;
         if ((rc = launch_ln(h, d1, d1, h->dpd_n2, (int)R, Fd, 0, nullptr, T))) return rc;
         a = base_args(h->dpd_proj, d1, Fd, 0, logw, 1, 0);
         if ((rc = launch_conv(h, a, T, false))) return rc;
@@ -668,27 +719,43 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         const int f_lo = h->h_cu_y[b_lo];
         std::vector<int> cu_local(nB + 1);
         for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
-        // fused MRF stage kernel (mrf_tc.cuh) where the stage qualifies: bf16 mode, ResBlock2, 32/64 channels
+        // fused MRF stage kernel (mrf2_tc.cuh; mrf_tc.cuh with option mrf_v1) where the stage qualifies: bf16 mode,
+        // ResBlock2, 32/64 channels.  The last stage also absorbs lrelu -> conv_post -> tanh.
         std::vector<MrfArgs> mrf_args(A.n_ups + 1);
         std::vector<MrfCfg> mrf_cfg(A.n_ups + 1);
-        std::vector<int> mrf_on(A.n_ups + 1, 0);
+        std::vector<Mrf2Args> mrf2_args(A.n_ups + 1);
+        std::vector<Mrf2Cfg> mrf2_cfg(A.n_ups + 1);
+        std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: unfused, 1: v1, 2: v2
+        bool post_fused = false;
+        const bool use_v1 = h->opts["mrf_v1"] != 0;
         for (int i = 0; i < A.n_ups; i++) {
             const int co = chans[i + 1];
             if (h->precision != 1 || A.resblock_type != 2 || A.n_rbk > MRF_MAX_RB || h->opts["no_fused_mrf"] != 0) continue;
             MrfArgs& m = mrf_args[i + 1];
-            memset(&m, 0, sizeof m);
+            Mrf2Args& m2 = mrf2_args[i + 1];
+            memset(&m, 0, sizeof m); memset(&m2, 0, sizeof m2);
             m.C = co; m.nrb = A.n_rbk; m.out_div = (float)A.n_rbk; m.slope = 0.1f;
+            m2.C = co; m2.nrb = A.n_rbk; m2.out_div = (float)A.n_rbk; m2.slope = 0.1f;
             bool ok = true;
             for (int j = 0; j < A.n_rbk; j++) {
                 const auto& cv = h->rb_c1[i * A.n_rbk + j];
                 if (A.rb_ndil[j] != 2 || !cv[0].wtc || !cv[1].wtc) { ok = false; break; }
                 m.k[j] = A.rb_kernels[j]; m.d1[j] = A.rb_dilations[j][0]; m.d2[j] = A.rb_dilations[j][1];
                 m.w[j][0] = cv[0].wtc; m.w[j][1] = cv[1].wtc; m.b[j][0] = cv[0].b; m.b[j][1] = cv[1].b;
+                m2.k[j] = m.k[j]; m2.d1[j] = m.d1[j]; m2.d2[j] = m.d2[j];
+                m2.w[j][0] = m.w[j][0]; m2.w[j][1] = m.w[j][1]; m2.b[j][0] = m.b[j][0]; m2.b[j][1] = m.b[j][1];
             }
-            if (ok && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
+            if (!ok) continue;
+            if (!use_v1) {
+                const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
+                const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
+                if (want_post && mrf2_plan(m2, mrf2_cfg[i + 1], nbp, true)) { mrf_on[i + 1] = 2; post_fused = true; }
+                else if (mrf2_plan(m2, mrf2_cfg[i + 1], nbp, false)) mrf_on[i + 1] = 2;
+            }
+            if (!mrf_on[i + 1] && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
         }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
-        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i], mrf_on[i] ? mrf_cfg[i].t_out : 0);
+        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i], mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0));
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
             (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) ||
@@ -724,7 +791,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         for (int s = 0; s < A.n_flow; s++) {
             auto& f = h->flows[s];
             ConvArgs a = base_args(f.pre, P, C, f.xcol, fh, H, 0);
-            if ((rc = launch_conv(h, a, T1, false))) return rc;
+            if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
             for (int i = 0; i < A.wn_layers; i++) {
                 a = base_args(f.in[i], fh, H, 0, facts, H, 0); a.epi = EPI_GATE;
                 if (A.n_speakers > 1) { a.utab = f.cond_tab[i]; a.uidx = d_sid; a.utab_ld = 2 * H; }
@@ -738,7 +805,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
             }
             a = base_args(f.post, fskip, H, 0, P, C, f.ocol); a.epi = EPI_SUBFROM; a.res = P; a.ldres = C; a.rescol = f.ocol;
-            if ((rc = launch_conv(h, a, T1, false))) return rc;
+            if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
         }
         stage_end(h);
         // ---- HiFi-GAN generator (models.py:348-368)
@@ -764,7 +831,16 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             if ((rc = launch_conv(h, a, Tin, true))) return rc;
             a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
             if ((rc = launch_conv(h, a, Tin, true))) return rc;
-            if (mrf_on[i + 1]) {
+            if (mrf_on[i + 1] == 2) {
+                Mrf2Args& m = mrf2_args[i + 1];
+                m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
+                if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
+                if (m.ntiles > 0) {
+                    cudaError_t e = mrf2_launch(m, mrf2_cfg[i + 1], h->num_sms, st);
+                    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf2 launch: %s", cudaGetErrorString(e));
+                    h->launches++;
+                }
+            } else if (mrf_on[i + 1]) {
                 MrfArgs& m = mrf_args[i + 1];
                 m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
                 if (m.ntiles > 0) {
@@ -806,7 +882,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         // ---- lrelu(0.01) -> conv_post -> tanh (models.py:364-366)
         {
             const Tiles Tl = tb.get(meta, rates[A.n_ups]);
-            if (Tl.n256 > 0) {
+            if (Tl.n256 > 0 && !post_fused) {
                 size_t smem = (size_t)(CP_TILE + 6) * (h->post_c + 1) * sizeof(float);
                 k_conv_post<<<Tl.n256, 256, smem, st>>>(cur, h->post_c, h->post_w, Tl.cu, Tl.t256, nB, Tl.rate, 0.01f,
                                                         audio + (int64_t)f_lo * hop);
@@ -918,12 +994,14 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     CK(h, cudaMemcpy(dout, out, out_elems * 4, cudaMemcpyHostToDevice));
     if (bias) { CK(h, cudaMalloc(&db, npad * 4)); CK(h, cudaMemcpy(db, bias, npad * 4, cudaMemcpyHostToDevice)); }
     if (res) { CK(h, cudaMalloc(&dres, (size_t)L * n * 4)); CK(h, cudaMemcpy(dres, res, (size_t)L * n * 4, cudaMemcpyHostToDevice)); }
-    if (wtc) { CK(h, cudaMalloc(&dwtc, (size_t)ntaps * cin * npad16 * 2)); CK(h, cudaMemcpy(dwtc, wtc, (size_t)ntaps * cin * npad16 * 2, cudaMemcpyHostToDevice)); }
+    const size_t wtc_bytes = (size_t)ntaps * cin * npad16 * 2 * (use_tc == 2 ? 3 : 1);
+    if (wtc) { CK(h, cudaMalloc(&dwtc, wtc_bytes)); CK(h, cudaMemcpy(dwtc, wtc, wtc_bytes, cudaMemcpyHostToDevice)); }
     int cu[2] = {0, L};
     TileBuilder tb; tb.begin(cu, 1); tb.add(1);
     CK(h, cudaMemcpy(dmeta, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice));
     const Tiles T = tb.get(dmeta, 1);
     ConvP c; c.w = dw; c.wtc = (const __nv_bfloat16*)dwtc; c.b = db; c.cin = cin; c.n = n; c.npad = npad; c.npad16 = npad16; c.ntaps = ntaps;
+    if (use_tc == 2) { c.nsl = 1; c.slice_cin = cin; c.wtc3[0] = (const __nv_bfloat16*)dwtc; }
     for (int i = 0; i < ntaps; i++) c.toff[i] = taps[i];
     ConvArgs a = base_args(c, dx, cin, 0, dout, out_cols, 0);
     a.in_act = in_act; a.in_slope = in_slope; a.epi = epi; a.res = dres; a.ldres = n; a.accumulate = accumulate;
@@ -933,7 +1011,7 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     h->precision = use_tc ? 1 : 0;
     int rc = 0;
     if (use_tc && !conv_tc_supported(a)) rc = fail(h, VITS_E_INVALID, "shape not supported by the tcgen05 conv kernel");
-    if (!rc) rc = launch_conv(h, a, T, use_tc != 0);
+    if (!rc) rc = (use_tc == 2) ? launch_conv_text(h, c, a, T) : launch_conv(h, a, T, use_tc != 0);
     h->precision = saved;
     cudaError_t e = cudaStreamSynchronize(st);
     if (!rc && e != cudaSuccess) rc = fail(h, VITS_E_CUDA, "test conv failed: %s", cudaGetErrorString(e));

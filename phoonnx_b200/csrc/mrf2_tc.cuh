@@ -1,0 +1,443 @@
+// Fused multi-receptive-field stage of the HiFi-GAN generator, v2 (sm_100a, ResBlock2 family):
+//
+//     out = ( sum_r  rb_r(x) ) / n_r ,   rb_r(x) = x1 + conv_{k_r, d_r2}(lrelu(x1)) ,  x1 = x + conv_{k_r, d_r1}(lrelu(x))
+//     [last stage only]  audio = tanh( conv_post( lrelu_{0.01}(out) ) )
+//
+// (models.py:356-366 + modules.py:355-364) in ONE kernel per stage.  Same tile geometry as mrf_tc.cuh (a CTA owns
+// a window of 128*NB rows, all convs of all resblocks run on the same M=128 blocks, only the central rows are
+// stored); what changed is the schedule, after ncu showed the v1 tensor pipe 11-16 % busy with every warp parked
+// on an mbarrier (profiles/r01_mrf_v1_ncu.md):
+//
+//   * the MMA warp issues conv1 of resblock r+1 BEFORE it waits for the x1 operand of resblock r (conv1
+//     accumulators are double-buffered in TMEM), so the tensor pipe always has queued work while the epilogue
+//     warps turn accumulator r into the conv2 operand;
+//   * weights stay resident in shared memory whenever they fit (C = 32: 61 KB), otherwise the ring is as deep as
+//     shared memory allows -- v1's 2 KB-per-tap ring was bound by L2 latency, not bandwidth;
+//   * raw fp32 rows are staged by a dedicated loader warp with one cp.async.bulk per row into a PADDED buffer
+//     (row pitch C+4 floats), so the thread-per-row residual reads are bank-conflict-free (v1: 8-way), and the
+//     next tile's rows are prefetched under the current tile;
+//   * in the last stage the 7-tap conv_post + tanh runs in the same kernel from a shared-memory copy of the
+//     stage output, which therefore never goes to HBM.
+//
+// Warp roles (352 threads): warps 0-7 operand conversion + epilogues (lane quadrant = warp % 4, block = warp / 4),
+// warp 8 lane 0 = weight producer (+ TMEM allocation), warp 9 lane 0 = MMA issuer, warp 10 = raw-row loader.
+#pragma once
+#include "conv_tc.cuh"
+
+#define MRF2_THREADS 352
+#define MRF2_EPI_THREADS 256
+#define MRF2_MAX_RB 3
+#define MRF2_MAX_STAGES 32
+#define MRF2_POST_K 7
+
+struct Mrf2Args {
+    const float* x;  float* out;  int C;
+    int nrb;  int k[MRF2_MAX_RB];  int d1[MRF2_MAX_RB];  int d2[MRF2_MAX_RB];
+    const __nv_bfloat16* w[MRF2_MAX_RB][2];  const float* b[MRF2_MAX_RB][2];
+    const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
+    float out_div;  float slope;
+    const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
+};
+
+struct Mrf2Cfg {
+    int nb;          // M=128 blocks per window
+    int span;        // 128 * nb
+    int hmax;        // max conv2 half receptive field
+    int h1max;       // max conv1 half receptive field
+    int t_out;       // span - 2*hmax: rows of stage output produced per tile
+    int post_halo;   // 3 when conv_post is fused, else 0
+    int t_step;      // t_out - 2*post_halo: rows a tile advances (== rows of final output per tile)
+    int rx, rx1;     // rows of the two operand tiles (odd)
+    int xf_pitch;    // floats per raw row (C + 4)
+    int xf_bytes, x_bytes, x1_bytes;
+    int slot_bytes, nstages, resident, npieces;
+    int tmem_cols;
+    int bias_off;
+    int smem_bytes;
+};
+
+template <int C, int OWN>
+__global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, const Mrf2Cfg c) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* sXf = reinterpret_cast<float*>(smem);             // raw fp32 rows of x, pitch C+4 (bulk-copied)
+    uint8_t* sX = smem + c.xf_bytes;                          // lrelu(x)  bf16 K-major chunks [C/8][rx][8]
+    uint8_t* sX1 = sX + c.x_bytes;                            // lrelu(x1) bf16 K-major chunks [C/8][rx1][8]
+    uint8_t* sW = sX1 + c.x1_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)c.nstages * c.slot_bytes);
+    const uint32_t bar_full0 = tc::smem_u32(bars);
+    const uint32_t bar_empty0 = bar_full0 + 8u * c.nstages;
+    const uint32_t bar_x = bar_empty0 + 8u * c.nstages;      // X operand staged              (256 arrivals / tile)
+    const uint32_t bar_x1 = bar_x + 8u;                       // x1 operand staged, acc1 drained (256 / resblock)
+    const uint32_t bar_c1 = bar_x1 + 8u;                      // conv1 accumulators ready, 2 buffers (commit / resblock)
+    const uint32_t bar_c2 = bar_c1 + 16u;                     // conv2 MMAs of one resblock complete (commit / resblock)
+    const uint32_t bar_xf = bar_c2 + 8u;                      // raw rows landed               (tx / tile)
+    const uint32_t bar_xf_free = bar_xf + 8u;                 // raw rows consumed             (256 / tile)
+    const uint32_t bar_acc2_free = bar_xf_free + 8u;          // conv2 accumulators drained    (256 / tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 8);
+    float* sB = reinterpret_cast<float*>(smem + c.bias_off);  // bias1 of every resblock, sum_r bias2_r, post weights
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
+        tc::mbar_init(bar_x, MRF2_EPI_THREADS);
+        tc::mbar_init(bar_x1, MRF2_EPI_THREADS);
+        tc::mbar_init(bar_c1, 1);
+        tc::mbar_init(bar_c1 + 8u, 1);
+        tc::mbar_init(bar_c2, 1);
+        tc::mbar_init(bar_xf, 1);
+        tc::mbar_init(bar_xf_free, MRF2_EPI_THREADS);
+        tc::mbar_init(bar_acc2_free, MRF2_EPI_THREADS);
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < C; i += MRF2_THREADS) {
+        float sum = 0.f;
+        for (int r = 0; r < a.nrb; r++) { sB[r * C + i] = __ldg(a.b[r][0] + i); sum += __ldg(a.b[r][1] + i); }
+        sB[a.nrb * C + i] = sum;
+    }
+    if (a.post_w)
+        for (int i = tid; i < MRF2_POST_K * C; i += MRF2_THREADS) sB[(MRF2_MAX_RB + 1) * C + i] = __ldg(a.post_w + i);
+    if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    constexpr int KC = C / 8;                       // 16-byte chunks per row
+    const uint32_t lbo_x = (uint32_t)c.rx * 16u, lbo_x1 = (uint32_t)c.rx1 * 16u, lbo_w = (uint32_t)C * 16u;
+    const uint32_t acc1_cols = (uint32_t)(c.nb * C);            // per conv1 buffer
+    const uint32_t acc2_col = 2u * acc1_cols;
+    const int lead = c.hmax + c.h1max;              // window row 0 of the X tile sits `lead` rows before the first stored row
+
+    // tile -> (utterance rows, first stage-output row).  o0 may be negative by post_halo.
+    auto tile_geom = [&](int tile, long& row0, int& len, int& o0) {
+        const int b = find_segment(a.tile_cu, a.B, tile);
+        o0 = (tile - __ldg(a.tile_cu + b)) * c.t_step - c.post_halo;
+        const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
+        row0 = (long)cb0 * a.rate;
+        len = (cb1 - cb0) * a.rate;
+    };
+
+    if (warp < 8) {
+        // ===================== operand conversion + epilogues (256 threads) =====================
+        const int q = warp & 3, hb = warp >> 2;
+        uint32_t n_c1[2] = {0, 0}, n_c2 = 0, n_xf = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            long row0; int len, o0;
+            tile_geom(tile, row0, len, o0);
+            const int tbase = o0 - lead;
+            const int tstart = tbase > 0 ? tbase : 0;          // time row held at sXf row 0
+            // ---- smem -> smem: lrelu(x) as bf16 K-major chunks; rows outside the utterance are zero padding
+            tc::mbar_wait(bar_xf, n_xf & 1); n_xf++;
+            {
+                const int items = c.rx * KC;
+                for (int i = tid; i < items; i += MRF2_EPI_THREADS) {
+                    const int r = i / KC, kc = i - r * KC;
+                    const int t = tbase + r;
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    if (t >= 0 && t < len) {
+                        const float4* src = reinterpret_cast<const float4*>(sXf + (size_t)(t - tstart) * c.xf_pitch + kc * 8);
+                        const float4 a0 = src[0], a1 = src[1];
+                        pk.x = tc::pack_bf16(leaky(a0.x, a.slope), leaky(a0.y, a.slope)); pk.y = tc::pack_bf16(leaky(a0.z, a.slope), leaky(a0.w, a.slope));
+                        pk.z = tc::pack_bf16(leaky(a1.x, a.slope), leaky(a1.y, a.slope)); pk.w = tc::pack_bf16(leaky(a1.z, a.slope), leaky(a1.w, a.slope));
+                    }
+                    *reinterpret_cast<uint4*>(sX + ((size_t)kc * c.rx + r) * 16) = pk;
+                }
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_x);
+
+            // this thread's rows: block bb (= hb, hb+2, ...), window row wr = 128*bb + 32*q + lane
+            bool inr[OWN];
+            const float* xrow[OWN];
+            float xacc[OWN][C];                     // sum_r (x1_r + bias2_r) for the blocks this thread owns
+#pragma unroll
+            for (int o = 0; o < OWN; o++) {
+                const int bb = hb + 2 * o;
+                const int tm = o0 - c.hmax + 128 * bb + 32 * q + lane;
+                inr[o] = (bb < c.nb) && (tm >= 0 && tm < len);
+                xrow[o] = sXf + (size_t)(inr[o] ? (tm - tstart) : 0) * c.xf_pitch;
+#pragma unroll
+                for (int j = 0; j < C / 4; j++) {
+                    const float4 bs = *reinterpret_cast<const float4*>(sB + a.nrb * C + 4 * j);      // sum_r bias2_r
+                    xacc[o][4 * j] = bs.x; xacc[o][4 * j + 1] = bs.y; xacc[o][4 * j + 2] = bs.z; xacc[o][4 * j + 3] = bs.w;
+                }
+            }
+
+            for (int r = 0; r < a.nrb; r++) {
+                const uint32_t buf = (uint32_t)r & 1u;
+                tc::mbar_wait(bar_c1 + 8u * buf, n_c1[buf] & 1); n_c1[buf]++;
+                tc::tc_fence_after();
+                const float* b1 = sB + r * C;
+                uint32_t pk[OWN][C / 2];
+#pragma unroll
+                for (int o = 0; o < OWN; o++) {
+                    const int bb = hb + 2 * o;
+                    if (bb >= c.nb) break;
+                    const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + buf * acc1_cols + (uint32_t)(bb * C);
+#pragma unroll
+                    for (int n0 = 0; n0 < C; n0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(trow + (uint32_t)n0, v);
+#pragma unroll
+                        for (int qd = 0; qd < 4; qd++) {
+                            const float4 bv = *reinterpret_cast<const float4*>(b1 + n0 + 4 * qd);      // smem broadcast
+                            const float4 xv = *reinterpret_cast<const float4*>(xrow[o] + n0 + 4 * qd);  // conflict-free (pitch C+4)
+                            float x1[4];
+                            x1[0] = v[4 * qd + 0] + bv.x + xv.x; x1[1] = v[4 * qd + 1] + bv.y + xv.y;
+                            x1[2] = v[4 * qd + 2] + bv.z + xv.z; x1[3] = v[4 * qd + 3] + bv.w + xv.w;
+                            if (!inr[o]) { x1[0] = x1[1] = x1[2] = x1[3] = 0.f; }   // conv2 zero-pads x1 beyond the utterance
+                            xacc[o][n0 + 4 * qd + 0] += x1[0]; xacc[o][n0 + 4 * qd + 1] += x1[1];
+                            xacc[o][n0 + 4 * qd + 2] += x1[2]; xacc[o][n0 + 4 * qd + 3] += x1[3];
+                            pk[o][(n0 >> 1) + 2 * qd + 0] = tc::pack_bf16(leaky(x1[0], a.slope), leaky(x1[1], a.slope));
+                            pk[o][(n0 >> 1) + 2 * qd + 1] = tc::pack_bf16(leaky(x1[2], a.slope), leaky(x1[3], a.slope));
+                        }
+                    }
+                }
+                if (r == a.nrb - 1) tc::mbar_arrive(bar_xf_free);        // last read of the raw rows: the loader may prefetch
+                if (r > 0) { tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++; }  // conv2 of resblock r-1 no longer reads sX1
+#pragma unroll
+                for (int o = 0; o < OWN; o++) {
+                    const int bb = hb + 2 * o;
+                    if (bb >= c.nb) break;
+                    const int row1 = 128 * bb + 32 * q + lane + c.hmax;
+#pragma unroll
+                    for (int n8 = 0; n8 < KC; n8++)
+                        *reinterpret_cast<uint4*>(sX1 + ((size_t)n8 * c.rx1 + row1) * 16) =
+                            make_uint4(pk[o][4 * n8], pk[o][4 * n8 + 1], pk[o][4 * n8 + 2], pk[o][4 * n8 + 3]);
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                tc::mbar_arrive(bar_x1);
+            }
+            // ---- final epilogue: out = (acc2 + sum_r(x1_r + b2_r)) / n_r on the central rows
+            tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++;
+            tc::tc_fence_after();
+            float* sPost = reinterpret_cast<float*>(sX);         // [t_out][C+1] fp32, aliases the two operand tiles (both idle now)
+#pragma unroll
+            for (int o = 0; o < OWN; o++) {
+                const int bb = hb + 2 * o;
+                if (bb >= c.nb) break;
+                const int wr = 128 * bb + 32 * q + lane;
+                const int tm = o0 - c.hmax + wr;
+                const bool central = (wr >= c.hmax) && (wr < c.hmax + c.t_out);
+                const bool st = central && (tm >= 0) && (tm < len);
+                float* orow = a.out + (row0 + tm) * C;
+                float* prow = sPost + (size_t)(wr - c.hmax) * (C + 1);
+                const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16) + acc2_col + (uint32_t)(bb * C);
+#pragma unroll
+                for (int n0 = 0; n0 < C; n0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(trow + (uint32_t)n0, v);
+                    if (a.post_w) {
+                        if (central) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                prow[n0 + j] = st ? leaky((v[j] + xacc[o][n0 + j]) / a.out_div, a.post_slope) : 0.f;
+                        }
+                    } else if (st) {
+#pragma unroll
+                        for (int qd = 0; qd < 4; qd++) {
+                            float4 ov;
+                            ov.x = (v[4 * qd + 0] + xacc[o][n0 + 4 * qd + 0]) / a.out_div;
+                            ov.y = (v[4 * qd + 1] + xacc[o][n0 + 4 * qd + 1]) / a.out_div;
+                            ov.z = (v[4 * qd + 2] + xacc[o][n0 + 4 * qd + 2]) / a.out_div;
+                            ov.w = (v[4 * qd + 3] + xacc[o][n0 + 4 * qd + 3]) / a.out_div;
+                            *(reinterpret_cast<float4*>(orow + n0) + qd) = ov;
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_acc2_free);       // the next tile's conv2 may overwrite the accumulators
+            if (a.post_w) {
+                // ---- conv_post (C -> 1, k7, no bias) + tanh (models.py:364-366) on the staged lrelu(out) rows
+                asm volatile("bar.sync 1, %0;" ::"n"(MRF2_EPI_THREADS) : "memory");
+                const float* pw = sB + (MRF2_MAX_RB + 1) * C;
+                for (int j = tid; j < c.t_step; j += MRF2_EPI_THREADS) {
+                    const int t = o0 + c.post_halo + j;              // output sample (stage row) index
+                    if (t >= len) break;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MRF2_POST_K; k++) {
+                        const float* xr = sPost + (size_t)(j + k) * (C + 1);
+                        const float* wr = pw + k * C;
+#pragma unroll
+                        for (int ch = 0; ch < C; ch++) acc = fmaf(xr[ch], wr[ch], acc);
+                    }
+                    a.audio[row0 + t] = tanhf(acc);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(MRF2_EPI_THREADS) : "memory");   // sPost is the next tile's operand space
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                if (c.resident && tile != (int)blockIdx.x) break;
+                // issue order of the MMA warp: C1(0) | C1(1) C2(0) | C1(2) C2(1) | C2(2)
+                for (int step = 0; step <= a.nrb; step++)
+                    for (int cv = 0; cv < 2; cv++) {
+                        const int r = cv ? step - 1 : step;
+                        if (r < 0 || r >= a.nrb) continue;
+                        const __nv_bfloat16* wsrc = a.w[r][cv];
+                        for (int tap = 0; tap < a.k[r]; tap++) {
+                            if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
+                            const uint32_t fb = bar_full0 + 8u * s;
+                            tc::mbar_expect_tx(fb, (uint32_t)c.slot_bytes);
+                            tc::bulk_g2s(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb);
+                            wsrc += C * C;
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc(128, C);
+            const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
+            const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
+            const uint64_t bd_step = (uint64_t)((2u * lbo_w) >> 4);
+            const uint64_t ad_step_x = (uint64_t)((2u * lbo_x) >> 4), ad_step_x1 = (uint64_t)((2u * lbo_x1) >> 4);
+            const uint32_t x16 = (sX_u >> 4) + (uint32_t)c.h1max, x116 = (sX1_u >> 4) + (uint32_t)c.hmax;   // 16-byte units == rows
+            uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                tc::mbar_wait(bar_x, it & 1);
+                tc::tc_fence_after();
+                for (int step = 0; step <= a.nrb; step++) {
+#pragma unroll
+                    for (int cv = 0; cv < 2; cv++) {
+                        const int r = cv ? step - 1 : step;
+                        if (r < 0 || r >= a.nrb) continue;
+                        if (cv == 1) {
+                            tc::mbar_wait(bar_x1, n_x1 & 1); n_x1++;                       // x1(r) staged, acc1[r&1] drained
+                            if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
+                            tc::tc_fence_after();
+                        }
+                        const int kr = a.k[r];
+                        const int dil = cv ? a.d2[r] : a.d1[r];
+                        const uint64_t dhi = cv ? dhi_x1 : dhi_x;
+                        const uint64_t ad_step = cv ? ad_step_x1 : ad_step_x;
+                        const uint32_t dcol0 = tmem_base + (cv ? acc2_col : ((uint32_t)r & 1u) * acc1_cols);
+                        uint32_t arow16 = (cv ? x116 : x16) - (uint32_t)(((kr - 1) >> 1) * dil);     // tap 0
+                        for (int tap = 0; tap < kr; tap++, arow16 += (uint32_t)dil) {
+                            if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
+                            const uint64_t bd0 = dhi_w | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                            // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks (and taps)
+                            const uint32_t acc0 = (tap > 0 || (cv && r > 0)) ? 1u : 0u;
+                            for (int bb = 0; bb < c.nb; bb++) {
+                                uint64_t ad = dhi | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
+                                uint64_t bd = bd0;
+                                const uint32_t dcol = dcol0 + (uint32_t)(bb * C);
+#pragma unroll
+                                for (int k16 = 0; k16 < C / 16; k16++) {
+                                    tc::umma_bf16(dcol, ad, bd, idesc, k16 ? 1u : acc0);
+                                    ad += ad_step; bd += bd_step;
+                                }
+                            }
+                            if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
+                        }
+                        tc::umma_commit(cv ? bar_c2 : (bar_c1 + 8u * ((uint32_t)r & 1u)));
+                    }
+                }
+                if (c.resident) { s = 0; }
+            }
+        }
+    } else {
+        // ===================== raw-row loader (warp 10) =====================
+        uint32_t n_free = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            long row0; int len, o0;
+            tile_geom(tile, row0, len, o0);
+            const int tbase = o0 - lead;
+            const int ts = tbase > 0 ? tbase : 0;
+            const int te = (tbase + c.rx < len) ? (tbase + c.rx) : len;
+            if (tile != (int)blockIdx.x) { tc::mbar_wait(bar_xf_free, n_free & 1); n_free++; }
+            if (lane == 0) tc::mbar_expect_tx(bar_xf, (uint32_t)(te - ts) * (uint32_t)(C * 4));
+            __syncwarp();
+            for (int r = ts + lane; r < te; r += 32)
+                tc::bulk_g2s(tc::smem_u32(sXf + (size_t)(r - ts) * c.xf_pitch), a.x + (row0 + r) * C, (uint32_t)(C * 4), bar_xf);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static inline bool mrf2_plan(const Mrf2Args& a, Mrf2Cfg& c, int nb_pref, bool fuse_post) {
+    if (a.C != 32 && a.C != 64) return false;
+    if (a.nrb < 1 || a.nrb > MRF2_MAX_RB) return false;
+    int hmax = 0, h1max = 0, npieces = 0;
+    for (int r = 0; r < a.nrb; r++) {
+        if (a.k[r] % 2 == 0 || !a.w[r][0] || !a.w[r][1]) return false;
+        const int h1 = a.d1[r] * (a.k[r] - 1) / 2, h2 = a.d2[r] * (a.k[r] - 1) / 2;
+        hmax = h2 > hmax ? h2 : hmax; h1max = h1 > h1max ? h1 : h1max;
+        npieces += 2 * a.k[r];
+    }
+    c.hmax = hmax; c.h1max = h1max; c.npieces = npieces;
+    c.slot_bytes = a.C * a.C * 2;
+    c.post_halo = fuse_post ? (MRF2_POST_K - 1) / 2 : 0;
+    c.xf_pitch = a.C + 4;
+    const int limit = 225 * 1024;
+    for (int nb = nb_pref; nb >= 1; nb--) {
+        if (nb == 3) continue;
+        if (3 * nb * a.C > 512) continue;                 // two conv1 buffers + the conv2 accumulators
+        c.nb = nb; c.span = 128 * nb; c.t_out = c.span - 2 * hmax; c.t_step = c.t_out - 2 * c.post_halo;
+        if (c.t_step < 32) continue;
+        c.rx = ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
+        c.rx1 = ((c.span + 2 * hmax + 7) / 8) * 8 + 1;
+        c.xf_bytes = (c.rx * c.xf_pitch * 4 + 127) / 128 * 128;
+        c.x_bytes = ((a.C / 8) * c.rx * 16 + 127) / 128 * 128;
+        c.x1_bytes = ((a.C / 8) * c.rx1 * 16 + 127) / 128 * 128;
+        if (fuse_post && (long)c.t_out * (a.C + 1) * 4 > (long)c.x_bytes + c.x1_bytes) continue;   // sPost aliases sX | sX1
+        const long fixed = (long)c.xf_bytes + c.x_bytes + c.x1_bytes;
+        const long tail = (2 * MRF2_MAX_STAGES + 8) * 8 + 32 + (MRF2_MAX_RB + 1 + MRF2_POST_K) * a.C * 4 + 256;
+        const long res_bytes = (long)npieces * c.slot_bytes;
+        if (npieces <= MRF2_MAX_STAGES && fixed + res_bytes + tail <= limit) { c.resident = 1; c.nstages = npieces; }
+        else {
+            c.resident = 0;
+            long room = limit - fixed - tail;
+            int ns = (int)(room / c.slot_bytes);
+            if (ns > MRF2_MAX_STAGES) ns = MRF2_MAX_STAGES;
+            if (ns > npieces) ns = npieces;
+            if (ns < 3) continue;
+            c.nstages = ns;
+        }
+        c.bias_off = (int)((fixed + (long)c.nstages * c.slot_bytes + (2 * c.nstages + 8) * 8 + 32 + 15) / 16 * 16);
+        c.smem_bytes = c.bias_off + (MRF2_MAX_RB + 1 + MRF2_POST_K) * a.C * 4;
+        if (c.smem_bytes > limit) continue;
+        int cols = 32; while (cols < 3 * nb * a.C) cols <<= 1;
+        c.tmem_cols = cols;
+        return true;
+    }
+    return false;
+}
+
+template <int C, int OWN>
+static inline cudaError_t mrf2_launch_t(const Mrf2Args& a, const Mrf2Cfg& c, int num_sms, cudaStream_t st) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_mrf2_tc<C, OWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_mrf2_tc<C, OWN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    int gx = num_sms;                       // one persistent CTA per SM (TMEM: up to 512 columns each)
+    if (gx > a.ntiles) gx = a.ntiles;
+    if (gx < 1) return cudaSuccess;
+    k_mrf2_tc<C, OWN><<<gx, MRF2_THREADS, c.smem_bytes, st>>>(a, c);
+    return cudaGetLastError();
+}
+
+static inline cudaError_t mrf2_launch(const Mrf2Args& a, const Mrf2Cfg& c, int num_sms, cudaStream_t st) {
+    if (c.nb > 4) return cudaErrorInvalidConfiguration;
+    if (a.C == 32) return c.nb <= 2 ? mrf2_launch_t<32, 1>(a, c, num_sms, st) : mrf2_launch_t<32, 2>(a, c, num_sms, st);
+    if (a.C == 64) return c.nb <= 2 ? mrf2_launch_t<64, 1>(a, c, num_sms, st) : cudaErrorInvalidConfiguration;
+    return cudaErrorInvalidConfiguration;
+}

@@ -42,8 +42,32 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return (f32_to_bf16_bits(x).astype(np.uint32) << 16).view(np.float32)
 
 
-def pack_conv(out: Dict[str, np.ndarray], name: str, w_tcn: np.ndarray, bias, tc: bool = False) -> None:
-    """w_tcn: [taps, C_in, N] (already in kernel tap order)."""
+SPLIT3_MAX_CIN = 192   # widest K slice whose hi+lo activation planes fit one CTA's shared memory
+
+
+def split3_slice(cin: int) -> int:
+    """Input channels per K slice of a bf16x3 convolution: the largest divisor of ``cin`` that is a multiple
+    of 16 and <= SPLIT3_MAX_CIN (0: shape unsupported).  Must match ``mkconv`` in csrc/engine.cu."""
+    for s in range(min(cin, SPLIT3_MAX_CIN), 15, -1):
+        if cin % s == 0 and s % 16 == 0:
+            return s
+    return 0
+
+
+def tc_layout(w_tcn16: np.ndarray) -> np.ndarray:
+    """[tap][ci][n16] fp32 -> tcgen05 K-major no-swizzle chunks [tap][ci/8][n16][8] as bf16 bits."""
+    taps, cin, n16 = w_tcn16.shape
+    wt = w_tcn16.reshape(taps, cin // 8, 8, n16).transpose(0, 1, 3, 2)
+    return f32_to_bf16_bits(np.ascontiguousarray(wt))
+
+
+def pack_conv(out: Dict[str, np.ndarray], name: str, w_tcn: np.ndarray, bias, tc: bool = False,
+              tc3: bool = False) -> None:
+    """w_tcn: [taps, C_in, N] (already in kernel tap order).
+
+    tc3: additionally emit the fp32-faithful bf16x3 operands "<n>.wtc3.<j>" (one per K slice j): per tap the
+    input channels are [wh | wl | wh] with wh = bf16(w), wl = bf16(w - wh); the kernel multiplies them with
+    [xh | xh | xl] (csrc/conv_tc.cuh, ConvArgs::split3)."""
     taps, cin, n = w_tcn.shape
     n4, n16 = _rup(n, 4), _rup(n, 16)
     w = np.zeros((taps, cin, n4), np.float32)
@@ -56,9 +80,15 @@ def pack_conv(out: Dict[str, np.ndarray], name: str, w_tcn: np.ndarray, bias, tc
     if tc and cin % 16 == 0 and n % 16 == 0:
         wt = np.zeros((taps, cin, n16), np.float32)
         wt[:, :, :n] = w_tcn
-        # [tap][ci][n] -> [tap][ci/8][n][8]
-        wt = wt.reshape(taps, cin // 8, 8, n16).transpose(0, 1, 3, 2)
-        out[name + ".wtc"] = f32_to_bf16_bits(np.ascontiguousarray(wt))
+        out[name + ".wtc"] = tc_layout(wt)
+    if tc3 and cin % 16 == 0 and n % 16 == 0 and split3_slice(cin):
+        sl = split3_slice(cin)
+        hi = bf16_round(np.asarray(w_tcn, np.float32))
+        lo = bf16_round(np.asarray(w_tcn, np.float32) - hi)
+        for j in range(cin // sl):
+            seg = slice(j * sl, (j + 1) * sl)
+            out[f"{name}.wtc3.{j}"] = tc_layout(np.ascontiguousarray(
+                np.concatenate([hi[:, seg], lo[:, seg], hi[:, seg]], axis=1)))
 
 
 def _conv_std(W, name) -> Tuple[np.ndarray, np.ndarray]:
@@ -77,16 +107,16 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         wq, bq = _conv_std(W, p + ".conv_q")
         wk, bk = _conv_std(W, p + ".conv_k")
         wv, bv = _conv_std(W, p + ".conv_v")
-        pack_conv(o, f"enc.{i}.qkv", np.concatenate([wq, wk, wv], axis=2), np.concatenate([bq, bk, bv]))
+        pack_conv(o, f"enc.{i}.qkv", np.concatenate([wq, wk, wv], axis=2), np.concatenate([bq, bk, bv]), tc3=tc)
         o[f"enc.{i}.rel_k"] = np.ascontiguousarray(W[p + ".emb_rel_k"][0], np.float32)
         o[f"enc.{i}.rel_v"] = np.ascontiguousarray(W[p + ".emb_rel_v"][0], np.float32)
-        pack_conv(o, f"enc.{i}.o", *_conv_std(W, p + ".conv_o"))
-        pack_conv(o, f"enc.{i}.ffn1", *_conv_std(W, f"enc_p.encoder.ffn_layers.{i}.conv_1"))
-        pack_conv(o, f"enc.{i}.ffn2", *_conv_std(W, f"enc_p.encoder.ffn_layers.{i}.conv_2"))
+        pack_conv(o, f"enc.{i}.o", *_conv_std(W, p + ".conv_o"), tc3=tc)
+        pack_conv(o, f"enc.{i}.ffn1", *_conv_std(W, f"enc_p.encoder.ffn_layers.{i}.conv_1"), tc3=tc)
+        pack_conv(o, f"enc.{i}.ffn2", *_conv_std(W, f"enc_p.encoder.ffn_layers.{i}.conv_2"), tc3=tc)
         for j in (1, 2):
             o[f"enc.{i}.ln{j}.g"] = W[f"enc_p.encoder.norm_layers_{j}.{i}.gamma"]
             o[f"enc.{i}.ln{j}.b"] = W[f"enc_p.encoder.norm_layers_{j}.{i}.beta"]
-    pack_conv(o, "enc.proj", *_conv_std(W, "enc_p.proj"))
+    pack_conv(o, "enc.proj", *_conv_std(W, "enc_p.proj"), tc3=tc)
 
     emb_g = W.get("emb_g.weight") if a.n_speakers > 1 else None
 
@@ -98,15 +128,15 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         for i in range(a.dds_layers):
             o[f"{dst}.{i}.dw_w"] = np.ascontiguousarray(W[f"{src}.convs_sep.{i}.weight"][:, 0, :].T, np.float32)  # [k][C]
             o[f"{dst}.{i}.dw_b"] = W[f"{src}.convs_sep.{i}.bias"]
-            pack_conv(o, f"{dst}.{i}.pw", *_conv_std(W, f"{src}.convs_1x1.{i}"))
+            pack_conv(o, f"{dst}.{i}.pw", *_conv_std(W, f"{src}.convs_1x1.{i}"), tc3=tc)
             o[f"{dst}.{i}.ln1.g"] = W[f"{src}.norms_1.{i}.gamma"]
             o[f"{dst}.{i}.ln1.b"] = W[f"{src}.norms_1.{i}.beta"]
             o[f"{dst}.{i}.ln2.g"] = W[f"{src}.norms_2.{i}.gamma"]
             o[f"{dst}.{i}.ln2.b"] = W[f"{src}.norms_2.{i}.beta"]
 
     if a.use_sdp:
-        pack_conv(o, "dp.pre", *_conv_std(W, "dp.pre"))
-        pack_conv(o, "dp.proj", *_conv_std(W, "dp.proj"))
+        pack_conv(o, "dp.pre", *_conv_std(W, "dp.pre"), tc3=tc)
+        pack_conv(o, "dp.proj", *_conv_std(W, "dp.proj"), tc3=tc)
         pack_dds("dp.convs", "dp.convs")
         for fi in a.cflows:
             o[f"dp.flows.{fi}.pre_w"] = np.ascontiguousarray(W[f"dp.flows.{fi}.pre.weight"][:, 0, 0], np.float32)
@@ -117,8 +147,8 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         opts["dp.ea_m"] = float(W["dp.flows.0.m"][0, 0])
         opts["dp.ea_logs"] = float(W["dp.flows.0.logs"][0, 0])
     else:
-        pack_conv(o, "dp.conv_1", *_conv_std(W, "dp.conv_1"))
-        pack_conv(o, "dp.conv_2", *_conv_std(W, "dp.conv_2"))
+        pack_conv(o, "dp.conv_1", *_conv_std(W, "dp.conv_1"), tc3=tc)
+        pack_conv(o, "dp.conv_2", *_conv_std(W, "dp.conv_2"), tc3=tc)
         pack_conv(o, "dp.proj", *_conv_std(W, "dp.proj"))
         for j in (1, 2):
             o[f"dp.norm_{j}.g"] = W[f"dp.norm_{j}.gamma"]
@@ -137,7 +167,7 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         w, b = _conv_std(W, p + ".pre")             # [1, half, H]
         if flipped:
             w = w[:, ::-1, :]
-        pack_conv(o, f"flow.{s}.pre", np.ascontiguousarray(w), b)
+        pack_conv(o, f"flow.{s}.pre", np.ascontiguousarray(w), b, tc=tc)
         for i in range(a.wn_layers):
             w, b = _conv_std(W, f"{p}.enc.in_layers.{i}")      # [k, H, 2H]
             pack_conv(o, f"flow.{s}.in.{i}", np.ascontiguousarray(w[:, :, inter]), b[inter], tc=tc)
@@ -150,7 +180,7 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         w, b = _conv_std(W, p + ".post")            # [1, H, half]
         if flipped:
             w, b = w[:, :, ::-1], b[::-1]
-        pack_conv(o, f"flow.{s}.post", np.ascontiguousarray(w), np.ascontiguousarray(b))
+        pack_conv(o, f"flow.{s}.post", np.ascontiguousarray(w), np.ascontiguousarray(b), tc=tc)
 
     pack_conv(o, "dec.pre", *_conv_std(W, "dec.conv_pre"), tc=tc)
     nk = len(a.rb_kernels)

@@ -32,8 +32,10 @@ def lib(built_lib):
 
 
 # ------------------------------------------------------------------------------------------ conv kernels
-@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 def test_conv_kernels_vs_numpy(lib, use_tc):
+    """use_tc 0: fp32 CUDA-core kernel; 1: tcgen05 bf16 (vs bf16-rounded operands); 2: tcgen05 bf16x3 (hi/lo split,
+    fp32-faithful: compared against the UNROUNDED fp32 reference)."""
     import gpu_diag as gd
     eng = gd.mini_engine()
     rs = np.random.RandomState(0)
@@ -41,14 +43,16 @@ def test_conv_kernels_vs_numpy(lib, use_tc):
         kw = dict(kw)
         if use_tc and (cin % 16 or n % 16):
             continue
+        if use_tc == 2 and (kw.get("epi", 0) != 0 or cin > 192):
+            continue
         x = rs.randn(L, cin).astype(np.float32)
         w = (rs.randn(len(taps), cin, n) / np.sqrt(cin * len(taps))).astype(np.float32)
         b = rs.randn(n).astype(np.float32)
         res = rs.randn(L, n).astype(np.float32) if kw.pop("with_res", False) else None
         oi = rs.randn(L, n // 2 if kw.get("epi") == 1 else n).astype(np.float32) if kw.get("accumulate") else None
         got = gd.run_conv(eng, use_tc, x, w, b, taps, res=res, out_init=oi, **kw)
-        want = gd.ref_conv(x, w, b, taps, res=res, out_init=oi, bf16=bool(use_tc), **kw)
-        assert np.abs(got - want).max() < 5e-5, (L, cin, n, taps, kw)
+        want = gd.ref_conv(x, w, b, taps, res=res, out_init=oi, bf16=(use_tc == 1), **kw)
+        assert np.abs(got - want).max() < (2e-4 if use_tc == 2 else 5e-5), (L, cin, n, taps, kw)
 
 
 # ------------------------------------------------------------------------------------------ golden fixtures
@@ -351,8 +355,9 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
     assert np.array_equal(alen, blen)
     assert n_fused < n_plain                      # the fused path really ran
     assert np.abs(a - b).max() < 1e-4, np.abs(a - b).max()
-    for nb in (1, 4):
+    for opts in ({"mrf_nb": 1}, {"mrf_nb": 2}, {"mrf_nb": 4}, {"no_fused_post": 1}, {"mrf_v1": 1}, {"mrf_v1": 1, "mrf_nb": 1}):
         alt = B200Session(p, precision="bf16")
-        alt.engine.set_option("mrf_nb", nb)
+        for k, v in opts.items():
+            alt.engine.set_option(k, v)
         c, _ = alt.synthesize_packed(feed)
-        assert np.abs(a - c).max() < 1e-4, (nb, np.abs(a - c).max())
+        assert np.abs(a - c).max() < 1e-4, (opts, np.abs(a - c).max())

@@ -43,3 +43,29 @@ def test_tc_weight_layout_and_bf16_rounding():
     out2 = {}
     packing.pack_conv(out2, "d", rs.randn(1, 32, 29).astype(np.float32), None, tc=True)
     assert "d.wtc" not in out2 and out2["d.w"].shape == (1, 32, 32)
+
+
+def test_bf16x3_operands_reproduce_fp32_products():
+    """The text side runs x*w as xh*wh + xh*wl + xl*wh on the tensor cores (csrc/conv_tc.cuh split3); the packed
+    operand "<n>.wtc3.<j>" must hold [wh | wl | wh] per K slice, and the three-term sum must be fp32-faithful."""
+    from phoonnx_b200 import packing
+    rs = np.random.RandomState(0)
+    taps, cin, n = 3, 384, 32
+    w = (rs.randn(taps, cin, n) / np.sqrt(cin * taps)).astype(np.float32)
+    blobs = {}
+    packing.pack_conv(blobs, "c", w, None, tc3=True)
+    sl = packing.split3_slice(cin)
+    assert sl == 192 and "c.wtc3.1" in blobs and "c.wtc3.2" not in blobs
+    x = rs.randn(50, cin).astype(np.float32)
+    xh = packing.bf16_round(x)
+    xl = packing.bf16_round(x - xh)
+    acc = np.zeros((50, n), np.float64)
+    for j in range(cin // sl):
+        blob = blobs[f"c.wtc3.{j}"]                                   # [tap][3*sl/8][n16][8] bf16 bits
+        wk = (blob.astype(np.uint32) << 16).view(np.float32).transpose(0, 1, 3, 2).reshape(taps, 3 * sl, -1)[:, :, :n]
+        xs = np.concatenate([xh[:, j * sl:(j + 1) * sl], xh[:, j * sl:(j + 1) * sl], xl[:, j * sl:(j + 1) * sl]], axis=1)
+        acc += xs.astype(np.float64) @ wk[1].astype(np.float64)       # centre tap only: a plain GEMM
+    want = x.astype(np.float64) @ w[1].astype(np.float64)
+    assert np.abs(acc - want).max() < 2e-5 * np.abs(want).max() + 1e-6
+    plain = xh.astype(np.float64) @ packing.bf16_round(w[1]).astype(np.float64)
+    assert np.abs(plain - want).max() > 50 * np.abs(acc - want).max()   # the split really buys ~2^8

@@ -26,7 +26,7 @@ def run_conv(eng, use_tc, x, w_tcn, bias, taps, in_slope=None, epi=0, res=None, 
              out_act=0, out_init=None):
     from phoonnx_b200 import packing
     blobs = {}
-    packing.pack_conv(blobs, "c", w_tcn, bias, tc=True)
+    packing.pack_conv(blobs, "c", w_tcn, bias, tc=True, tc3=(use_tc == 2))
     L, cin = x.shape
     n = w_tcn.shape[2]
     out_cols = n // 2 if epi == 1 else n
@@ -39,6 +39,10 @@ def run_conv(eng, use_tc, x, w_tcn, bias, taps, in_slope=None, epi=0, res=None, 
     lib.vits_test_conv.restype = C.c_int
     p = lambda a_: None if a_ is None else a_.ctypes.data_as(C.c_void_p)
     wtc = blobs.get("c.wtc")
+    if use_tc == 2:
+        if "c.wtc3.1" in blobs or "c.wtc3.0" not in blobs:
+            raise ValueError("test hook runs single-slice bf16x3 convolutions only")
+        wtc = blobs["c.wtc3.0"]
     xb = np.ascontiguousarray(x, np.float32)
     rc = lib.vits_test_conv(eng._h, int(use_tc), p(xb), L, cin, p(taps_a), len(taps), p(blobs["c.w"]), p(wtc),
                             p(blobs.get("c.b")), n, 0 if in_slope is None else 1, float(in_slope or 1.0), epi,
