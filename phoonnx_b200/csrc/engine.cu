@@ -93,7 +93,7 @@ struct vits_handle {
 
     Buf ids, cu_t, tile_t, sid, x, y, qkv, att, ffn, stats, d0, d1, gdp, hp, z0, z1, logw, dur, cum, ylen;
     Buf inj_dp, inj_z;
-    Buf chunk_meta, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp;
+    Buf chunk_meta, tdesc, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp;
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<StagePair> stage_events;
@@ -836,9 +836,11 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
                 if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
                 if (m.ntiles > 0) {
+                    if ((rc = ensure(h, h->tdesc, (size_t)m.ntiles * sizeof(int4)))) return rc;
+                    m.tdesc = ptr<int4>(h->tdesc);
                     cudaError_t e = mrf2_launch(m, mrf2_cfg[i + 1], h->num_sms, st);
                     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf2 launch: %s", cudaGetErrorString(e));
-                    h->launches++;
+                    h->launches += 2;
                 }
             } else if (mrf_on[i + 1]) {
                 MrfArgs& m = mrf_args[i + 1];
@@ -1032,7 +1034,7 @@ void vits_destroy(vits_handle* h) {
     for (auto& kv : h->blobs) cudaFree(kv.second.p);
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
-                   &h->chunk_meta, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
+                   &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
                    &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto e : h->event_pool) cudaEventDestroy(e);

@@ -344,6 +344,7 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
     nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
     feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
     fused = B200Session(p, precision="bf16")
+    fused.engine.set_option("no_fused_post", 1)   # conv_post stays the fp32 kernel: same operand rounding as the unfused path
     n0 = fused.engine.launch_count()
     a, alen = fused.synthesize_packed(feed)
     n_fused = fused.engine.launch_count() - n0
@@ -355,9 +356,21 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
     assert np.array_equal(alen, blen)
     assert n_fused < n_plain                      # the fused path really ran
     assert np.abs(a - b).max() < 1e-4, np.abs(a - b).max()
-    for opts in ({"mrf_nb": 1}, {"mrf_nb": 2}, {"mrf_nb": 4}, {"no_fused_post": 1}, {"mrf_v1": 1}, {"mrf_v1": 1, "mrf_nb": 1}):
+    for opts in ({"mrf_nb": 1, "no_fused_post": 1}, {"mrf_nb": 2, "no_fused_post": 1}, {"mrf_nb": 4, "no_fused_post": 1},
+                 {"mrf_v1": 1}, {"mrf_v1": 1, "mrf_nb": 1}):
         alt = B200Session(p, precision="bf16")
         for k, v in opts.items():
             alt.engine.set_option(k, v)
         c, _ = alt.synthesize_packed(feed)
         assert np.abs(a - c).max() < 1e-4, (opts, np.abs(a - c).max())
+    # default: lrelu -> conv_post -> tanh fused as a tensor-core pass, i.e. the stage output is rounded to bf16 like
+    # every other conv operand of the decoder in this mode
+    for opts in ({}, {"mrf_nb": 1}, {"mrf_nb": 2}):
+        alt = B200Session(p, precision="bf16")
+        for k, v in opts.items():
+            alt.engine.set_option(k, v)
+        n0 = alt.engine.launch_count()
+        c, clen = alt.synthesize_packed(feed)
+        assert np.array_equal(alen, clen)
+        assert alt.engine.launch_count() - n0 < n_fused       # no separate conv_post launch
+        assert snr_db(a, c) > 45.0, (opts, snr_db(a, c))
