@@ -138,6 +138,11 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
                    const float* w32, const uint16_t* wtc, const float* bias, int n, int in_act, float in_slope,
                    int epi, const float* res, int accumulate, float out_div, int out_act, float* out, int out_cols);
 
+/* Test hook: tcgen05.mma issue-rate probe (M=128, K=16, N=n; `nd` accumulators and `na` activation row offsets in
+ * rotation, operand tile of `rows` rows).  Returns the average cycles per MMA (issue only / issue + completion). */
+int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
+                        double* total_cycles);
+
 const char* vits_last_error(vits_handle* h);
 void vits_destroy(vits_handle* h);
 

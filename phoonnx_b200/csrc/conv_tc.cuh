@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// one lane of a converged warp; ptxas knows the predicate is single-lane, so UTCHMMA / UBLKCP / UTCBAR inside the
+// elected region take their uniform-register operands directly (a plain `lane == 0` test makes it wrap EVERY such
+// instruction in an ELECT / BRA.U.ANY waterfall loop plus R2UR moves: ~100 cycles per MMA issued, measured)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&p);
@@ -156,6 +164,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 //   warp  9    MMA issuer (lane 0)
 // Activation tiles and TMEM accumulators are double-buffered when they fit, so the load of tile
 // i+1, the MMAs of tile i and the epilogue of tile i-1 overlap inside one CTA.
+#define TC_DBG_TILES 16
+#define TC_STAMP(it_, slot_) do { if (dbg_on && (it_) < TC_DBG_TILES) a.dbg[(it_) * 16 + (slot_)] = (unsigned long long)clock64(); } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const TcCfg c) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
@@ -172,6 +183,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ny = blockIdx.y;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 8);
+    if (dbg_on && warp == 0) a.dbg[15] = (unsigned long long)clock64();
 
     if (tid == 0) {
         for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
@@ -198,13 +211,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
         // ================= epilogue (128 threads) =================
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            TC_STAMP(it, 0);
             const int b = find_segment(a.tile_cu, a.B, tile);
             const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
             const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
+            TC_STAMP(it, 1);
             const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
             tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
+            TC_STAMP(it, 2);
             tc::tc_fence_after();
             // Two-phase epilogue.  Phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias /
             // gate, then a warp-private smem transpose buffer.  Phase 2 (8 lanes = 128 contiguous bytes of one row,
@@ -296,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             }
             tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
             tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
+            TC_STAMP(it, 3);
         }
     } else if (warp < 8) {
         // ================= activation loaders (128 threads) =================
@@ -310,7 +327,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
             const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
+            TC_STAMP(it, 4);
             tc::mbar_wait(bar_aempty0 + 8u * abuf, (ause & 1u) ^ 1u);     // MMAs that read this buffer have retired
+            TC_STAMP(it, 5);
             uint8_t* dstA = sA + (size_t)abuf * c.a_bytes;
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
             // flight per thread before any conversion so the load latency is paid once per batch
@@ -357,16 +376,19 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             }
             tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc::mbar_arrive(bar_afull0 + 8u * abuf);
+            TC_STAMP(it, 6);
         }
     } else if (warp == 8) {
         // ================= weight producer (one thread, cp.async.bulk ring) =================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             uint32_t s = 0, ph = 1;                       // ring slot and the parity to wait for on its "empty" barrier
             const uint32_t kc_bytes = (uint32_t)c.ntile * 16u;
             const uint32_t sW_u = tc::smem_u32(sW);
             const long kc_stride = (long)a.npad16 * 8;          // elements between consecutive 8-channel chunks
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            int itp = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, itp++) {
                 if (c.resident && tile != (int)blockIdx.x) break;
+                TC_STAMP(itp, 7);
                 const __nv_bfloat16* src = a.wtc + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
                 for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
@@ -379,11 +401,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
                 }
+                TC_STAMP(itp, 8);
             }
         }
     } else {
         // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const uint32_t idesc = tc::make_idesc(TC_M, c.ntile);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_a = tc::make_desc(0, lbo_a, 128u), dhi_b = tc::make_desc(0, lbo_b, 128u);   // start-address field = 0
@@ -392,8 +415,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             uint32_t s = 0, ph = 0, it = 0;                   // ring slot / parity of its "full" barrier
             uint32_t abuf = 0, aph = 0, cbuf = 0, cph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                TC_STAMP((int)it, 9);
                 tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
+                TC_STAMP((int)it, 10);
                 tc::mbar_wait(bar_accempty0 + 8u * cbuf, cph ^ 1u);
+                TC_STAMP((int)it, 11);
                 tc::tc_fence_after();
                 const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
                 const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
@@ -421,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
                 if (c.resident) s = 0;
                 tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
                 tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
+                TC_STAMP((int)it, 12);
                 if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
                 if (++cbuf == (uint32_t)c.naccbuf) { cbuf = 0; cph ^= 1u; }
             }

@@ -15,6 +15,7 @@
 #include "conv_tc.cuh"
 #include "mrf_tc.cuh"
 #include "mrf2_tc.cuh"
+#include "probe_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -93,7 +94,8 @@ struct vits_handle {
 
     Buf ids, cu_t, tile_t, sid, x, y, qkv, att, ffn, stats, d0, d1, gdp, hp, z0, z1, logw, dur, cum, ylen;
     Buf inj_dp, inj_z;
-    Buf chunk_meta, tdesc, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp;
+    Buf chunk_meta, tdesc, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp, mrf_dbg, conv_dbg;
+    int conv_counter = 0;
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<StagePair> stage_events;
@@ -226,6 +228,13 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
         a.tile_cu = T.t128; a.ntiles = T.n128;
         if (T.n128 == 0) return 0;
+        a.dbg = nullptr;
+        if (h->opts.count("conv_dbg") && (int)h->opts["conv_dbg"] == ++h->conv_counter) {
+            int rc = ensure(h, h->conv_dbg, (size_t)TC_DBG_TILES * 16 * 8);
+            if (rc) return rc;
+            CK(h, cudaMemsetAsync(h->conv_dbg.p, 0, (size_t)TC_DBG_TILES * 16 * 8, h->stream));
+            a.dbg = ptr<unsigned long long>(h->conv_dbg);
+        }
         cudaError_t e = conv_tc_launch(a, h->num_sms, h->stream);
         if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc launch: %s", cudaGetErrorString(e));
         h->launches++;
@@ -685,6 +694,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
     if (!h->prepared) return fail(h, VITS_E_STATE, "vits_decode() before a successful vits_prepare()");
     const vits_arch& A = h->A;
     const int B = h->B, H = A.hidden, C = A.inter;
+    h->conv_counter = 0;
     int hop = 1; for (int i = 0; i < A.n_ups; i++) hop *= A.up_rates[i];
     const int64_t total_samples = h->total_frames * hop;
     if (out_kind < 0 || out_kind > 2) return fail(h, VITS_E_INVALID, "out_kind %d", out_kind);
@@ -835,6 +845,12 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 Mrf2Args& m = mrf2_args[i + 1];
                 m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
                 if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
+                m.dbg = nullptr;
+                if (h->opts.count("mrf_dbg") && (int)h->opts["mrf_dbg"] == i + 1) {
+                    if ((rc = ensure(h, h->mrf_dbg, (size_t)MRF2_DBG_TILES * 48 * 8))) return rc;
+                    CK(h, cudaMemsetAsync(h->mrf_dbg.p, 0, (size_t)MRF2_DBG_TILES * 48 * 8, st));
+                    m.dbg = ptr<unsigned long long>(h->mrf_dbg);
+                }
                 if (m.ntiles > 0) {
                     if ((rc = ensure(h, h->tdesc, (size_t)m.ntiles * sizeof(int4)))) return rc;
                     m.tdesc = ptr<int4>(h->tdesc);
@@ -934,6 +950,8 @@ int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity
     else if (k == "frame_index") { src = h->fidx.p; n = Fr; }
     else if (k == "z_p") { src = h->dbg_zp.p; n = h->dbg_zp.p ? Fr * A.inter : 0; }
     else if (k == "z") { src = h->P.p; n = Fr * A.inter; }
+    else if (k == "conv_dbg") { src = h->conv_dbg.p; n = h->conv_dbg.p ? TC_DBG_TILES * 16 * 2 : 0; }
+    else if (k == "mrf_dbg") { src = h->mrf_dbg.p; n = h->mrf_dbg.p ? MRF2_DBG_TILES * 48 * 2 : 0; }
     else return fail(h, VITS_E_INVALID, "unknown stage tensor '%s'", name);
     if (!src || n == 0) return fail(h, VITS_E_STATE, "stage tensor '%s' is not available", name);
     if (n > capacity_elems) return fail(h, VITS_E_INVALID, "fetch '%s': capacity %lld < %lld", name, (long long)capacity_elems, (long long)n);
@@ -1022,6 +1040,27 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     return rc;
 }
 
+int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles, double* total_cycles) {
+    if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > 512 || rows < 128 + 3 * na || rows > 700 || nctas < 1) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CK(h, cudaMalloc(&d, (size_t)nctas * 16));
+    const int smem = 8 * rows * 16 + 8 * 256 * 16;
+    CK(h, cudaFuncSetAttribute(k_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_mma_probe<<<nctas, 128, smem, h->stream>>>(n, iters, nd, na, rows, d);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cudaFree(d); return fail(h, VITS_E_CUDA, "mma probe: %s", cudaGetErrorString(e)); }
+    std::vector<unsigned long long> r(2 * (size_t)nctas);
+    cudaMemcpy(r.data(), d, r.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double a = 0, b = 0;
+    for (int i = 0; i < nctas; i++) { a += (double)r[2 * i]; b += (double)r[2 * i + 1]; }
+    if (issue_cycles) *issue_cycles = a / nctas / iters;
+    if (total_cycles) *total_cycles = b / nctas / iters;
+    return VITS_OK;
+}
+
 int64_t vits_launch_count(vits_handle* h) { return h ? h->launches : 0; }
 
 const char* vits_last_error(vits_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -1035,7 +1074,7 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);

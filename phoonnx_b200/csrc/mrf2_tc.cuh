@@ -43,6 +43,7 @@ struct Mrf2Args {
     const int4* tdesc;                                           // per tile {first row of the utterance, its rows, o0, -} (k_mrf2_tiles)
     float out_div;  float slope;
     const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
+    unsigned long long* dbg;                                     // test-only phase timeline of CTA 0 ([tile][48] clock64 stamps) or null
 };
 
 struct Mrf2Cfg {
@@ -81,6 +82,9 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 
 // leaky-relu for 0 < slope < 1 in two instructions
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+
+#define MRF2_DBG_TILES 24
+#define MRF2_STAMP(it_, slot_) do { if (dbg_on && (it_) < MRF2_DBG_TILES) a.dbg[(it_) * 48 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
 template <int C>
 __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, const Mrf2Cfg c) {
@@ -166,6 +170,8 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
         const float inv_div = 1.f / a.out_div;
         uint32_t n_c1[2] = {0, 0}, n_c2 = 0, n_xf = 0, n_post = 0;
         long p_row0 = 0; int p_len = 0, p_o0 = 0; bool have_prev = false;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+        int it = 0;
         // conv_post epilogue of the previous tile: acc_post column 0 -> tanh -> audio (thread per row, 32-channel group 0)
         auto post_epilogue = [&]() {
             tc::mbar_wait(bar_post_done, n_post & 1); n_post++;
@@ -177,13 +183,15 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
             }
             tc::tc_fence_before();
         };
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
             long row0; int len, o0;
             tile_geom(tile, row0, len, o0);
             const int tbase = o0 - lead;
             const int tstart = tbase > 0 ? tbase : 0;          // time row held at sXf row 0
+            MRF2_STAMP(it, 0);
             // ---- smem -> smem: lrelu(x) as bf16 K-major chunks; rows outside the utterance are zero padding
             tc::mbar_wait(bar_xf, n_xf & 1); n_xf++;
+            MRF2_STAMP(it, 1);
             {
                 const int items = c.rx * KC;
                 for (int i = tid; i < items; i += MRF2_EPI_THREADS) {
@@ -201,9 +209,11 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_x);
+            MRF2_STAMP(it, 2);
             // the previous tile's conv_post accumulators drain here, under this tile's first conv1 MMAs; this also
             // guarantees its MMAs no longer read sX1 before E1(0) below overwrites it
             if (post && have_prev) post_epilogue();
+            MRF2_STAMP(it, 3);
 
             const int tm = o0 - c.hmax + wr;
             const bool inr = active && (tm >= 0 && tm < len);
@@ -219,6 +229,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
             for (int r = 0; r < a.nrb; r++) {
                 const uint32_t buf = (uint32_t)r & 1u;
                 tc::mbar_wait(bar_c1 + 8u * buf, n_c1[buf] & 1); n_c1[buf]++;
+                MRF2_STAMP(it, 4 + 4 * r);
                 tc::tc_fence_after();
                 uint32_t pk[16];
 #pragma unroll
@@ -243,8 +254,10 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                         }
                     }
                 }
+                MRF2_STAMP(it, 5 + 4 * r);
                 if (r == a.nrb - 1) tc::mbar_arrive(bar_xf_free);        // last read of the raw rows: the loader may prefetch
                 if (r > 0) { tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++; }  // conv2 of resblock r-1 no longer reads sX1
+                MRF2_STAMP(it, 6 + 4 * r);
                 if (active) {
                     const int row1 = wr + c.hmax;
 #pragma unroll
@@ -255,9 +268,11 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
                 tc::mbar_arrive(bar_x1);
+                MRF2_STAMP(it, 7 + 4 * r);
             }
             // ---- final epilogue: out = (acc2 + sum_r(x1_r + b2_r)) / n_r on the central rows
             tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++;
+            MRF2_STAMP(it, 16);
             tc::tc_fence_after();
             if (active) {
                 const bool central = (wr >= c.hmax) && (wr < c.hmax + c.t_out);
@@ -302,6 +317,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
             }
             tc::tc_fence_before();
             tc::mbar_arrive(bar_acc2_free);       // the next tile's conv2 may overwrite the accumulators
+            MRF2_STAMP(it, 17);
             if (post) {
                 tc::fence_proxy_async();
                 tc::mbar_arrive(bar_post_rdy);
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
         if (post && have_prev) post_epilogue();
     } else if (warp == MRF2_EPI_WARPS) {
         // ===================== weight producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 if (c.resident && tile != (int)blockIdx.x) break;
@@ -334,7 +350,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
         }
     } else if (warp == MRF2_EPI_WARPS + 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const uint32_t idesc = tc::make_idesc(128, C), idesc_post = tc::make_idesc(128, 16);
             const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
@@ -344,8 +360,11 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
             const uint32_t x16 = (sX_u >> 4) + (uint32_t)c.h1max, x116 = (sX1_u >> 4) + (uint32_t)c.hmax;   // 16-byte units == rows
             const uint32_t wp16 = tc::smem_u32(sWp) >> 4;
             uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
+            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                MRF2_STAMP((int)it, 20);
                 tc::mbar_wait(bar_x, it & 1);
+                MRF2_STAMP((int)it, 21);
                 tc::tc_fence_after();
                 for (int step = 0; step <= a.nrb; step++) {
 #pragma unroll
@@ -357,6 +376,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                             if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
                             tc::tc_fence_after();
                         }
+                        MRF2_STAMP((int)it, 22 + 2 * (2 * step + cv));
                         const int kr = a.k[r];
                         const int dil = cv ? a.d2[r] : a.d1[r];
                         const uint64_t dhi = cv ? dhi_x1 : dhi_x;
@@ -382,12 +402,14 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
                         tc::umma_commit(cv ? bar_c2 : (bar_c1 + 8u * ((uint32_t)r & 1u)));
+                        MRF2_STAMP((int)it, 23 + 2 * (2 * step + cv));
                     }
                 }
                 if (c.resident) { s = 0; }
                 if (post) {
                     // conv_post: 7 taps, dilation 1, over the stage output sitting in sX1; N = 16 (column 0 is the filter)
                     tc::mbar_wait(bar_post_rdy, it & 1);
+                    MRF2_STAMP((int)it, 40);
                     tc::tc_fence_after();
                     uint32_t arow16 = x116 - (uint32_t)((MRF2_POST_K - 1) >> 1);
                     for (int tap = 0; tap < MRF2_POST_K; tap++, arow16++) {
@@ -403,6 +425,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                         }
                     }
                     tc::umma_commit(bar_post_done);
+                    MRF2_STAMP((int)it, 41);
                 }
             }
         }
@@ -410,13 +433,17 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
         // ===================== raw-row loader (warp 18): cp.async, 16 B per lane =====================
         uint32_t n_free = 0;
         constexpr int CH = C / 4;                    // 16-byte chunks per fp32 row
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
             long row0; int len, o0;
             tile_geom(tile, row0, len, o0);
             const int tbase = o0 - lead;
             const int ts = tbase > 0 ? tbase : 0;
             const int te = (tbase + c.rx < len) ? (tbase + c.rx) : len;
+            MRF2_STAMP(it, 44);
             if (tile != (int)blockIdx.x) { tc::mbar_wait(bar_xf_free, n_free & 1); n_free++; }
+            MRF2_STAMP(it, 45);
             const float* src0 = a.x + (row0 + ts) * C;
             const uint32_t dst0 = tc::smem_u32(sXf);
             const int total = (te - ts) * CH;
@@ -425,6 +452,7 @@ __global__ void __launch_bounds__(MRF2_THREADS, 1) k_mrf2_tc(const Mrf2Args a, c
                 tc::cp_async16(dst0 + (uint32_t)(r * c.xf_pitch + 4 * ch) * 4u, src0 + (size_t)r * C + 4 * ch);
             }
             tc::cp_async_mbar_arrive(bar_xf);
+            MRF2_STAMP(it, 46);
         }
     }
     tc::tc_fence_before();

@@ -1,0 +1,52 @@
+"""GPU diagnostics: phase timeline of k_conv_tc (CTA (0,0)) for selected launches of one decode call."""
+import ctypes as C
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from phoonnx_b200 import modelgen  # noqa: E402
+from phoonnx_b200.session import B200Session  # noqa: E402
+
+NAMES = {0: "E top", 1: "E geom", 2: "E acc full", 3: "E done", 4: "L top", 5: "L buf free", 6: "L staged", 7: "W top", 8: "W all issued",
+         9: "M top", 10: "M A full", 11: "M acc free", 12: "M issued", 15: "kernel start"}
+
+
+def main():
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "m.onnx")
+    _, arch = modelgen.make_voice(path, "medium", n_speakers=1, seed=1234)
+    sess = B200Session(path, precision="bf16", max_chunk_frames=int(sys.argv[1]) if len(sys.argv) > 1 else 131072)
+    eng = sess.engine
+    rs = np.random.RandomState(0)
+    B = 96
+    lens = rs.randint(150, 257, size=(B,)).astype(np.int64)
+    x = np.zeros((B, int(lens.max())), np.int64)
+    for b in range(B):
+        x[b, :lens[b]] = rs.randint(0, arch.n_vocab, size=(int(lens[b]),))
+    feed = {"input": x, "input_lengths": lens, "scales": np.asarray((0.667, 1.0, 0.8), np.float32)}
+    sess.synthesize_packed(feed, out="none")
+    print("frames", int(sess.last_lengths.sum()) // 256)
+    for idx, what in ((1, "flow pre 1x1 96->192"), (2, "flow in-layer k5 192->384 gate"), (3, "flow res-skip 1x1 192->384 split+acc"),
+                      (10, "flow post 192->96 subfrom"), (41, "dec conv_pre k7 192->256"), (42, "ups0 A"), (44, "stage1 rb k3 d1 128->128"),
+                      (49, "stage1 rb k7 d12 accumulate /3"), (50, "ups1 A 128->4*64"), (52, "ups2 A 64->2*32")):
+        eng.set_option("conv_dbg", idx)
+        sess.synthesize_packed(feed, out="none")
+        buf = np.zeros((16 * 16 * 2,), np.float32)
+        n = eng.lib.vits_fetch(eng._h, b"conv_dbg", buf.ctypes.data_as(C.c_void_p), buf.size)
+        st = buf.view(np.uint64).reshape(16, 16).astype(np.int64)
+        t0 = int(st[0, 15])
+        print(f"=== conv launch {idx}: {what} (fetched {n})")
+        for it in range(6):
+            ev = sorted((int(st[it, s]) - t0, NAMES.get(s, str(s))) for s in range(15) if st[it, s])
+            if not ev:
+                break
+            print(f" tile {it}: " + "  ".join(f"{nm}@{t}" for t, nm in ev))
+    eng.set_option("conv_dbg", 0)
+
+
+if __name__ == "__main__":
+    main()
