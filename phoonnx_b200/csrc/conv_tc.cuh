@@ -24,8 +24,10 @@
 #endif
 
 #define TC_M 128
-#define TC_THREADS 320
-#define TC_LOAD_THREADS 128
+#define TC_EPI_WARPS 8
+#define TC_LOAD_WARPS 8
+#define TC_THREADS ((TC_EPI_WARPS + TC_LOAD_WARPS + 2) * 32)
+#define TC_LOAD_THREADS (TC_LOAD_WARPS * 32)
 #define TC_EPI_PITCH 36            // floats per staged row: 16 B aligned, conflict-free for 8-lane phases
 #define TC_PIECE_CH 64
 #define TC_MAX_STAGES 24
@@ -157,17 +159,184 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
-// Warp-specialised persistent kernel (TC_THREADS = 320):
-//   warps 0-3  epilogue  (TMEM -> registers -> global), one TMEM lane quadrant each
-//   warps 4-7  activation loaders (global fp32 -> lrelu -> bf16 -> smem operand tile)
-//   warp  8    weight producer (lane 0) + TMEM allocator
-//   warp  9    MMA issuer (lane 0)
-// Activation tiles and TMEM accumulators are double-buffered when they fit, so the load of tile
-// i+1, the MMAs of tile i and the epilogue of tile i-1 overlap inside one CTA.
+// Warp-specialised persistent kernel (TC_THREADS = 576):
+//   warps 0-7   epilogue  (TMEM -> registers -> smem transpose -> coalesced global), TMEM lane quadrant = warp % 4,
+//               the two warps of a quadrant alternate over the 32-column groups of the accumulator
+//   warps 8-15  activation loaders (global fp32 -> lrelu -> bf16 -> smem operand tile)
+//   warp  16    weight producer (elected lane) + TMEM allocator
+//   warp  17    MMA issuer (elected lane)
+// Activation tiles and TMEM accumulators are double-buffered when they fit, so the load of tile i+1, the MMAs of
+// tile i and the epilogue of tile i-1 overlap inside one CTA.
+// r01 timeline (profiles/r01c_conv_timeline.log): with 4 epilogue warps and one generic, branchy epilogue the
+// TMEM -> HBM drain of one 128 x 192 tile took 40-80k cycles (2100 warp-instructions per 32 x 32 sub-tile at one warp
+// per scheduler) against 6-12k for the loaders and 1-9k for the MMAs -- hence 8 + 8 warps, a lean epilogue
+// specialised per mode at compile time, and batched (independent) residual / accumulate loads.
 #define TC_DBG_TILES 16
 #define TC_STAMP(it_, slot_) do { if (dbg_on && (it_) < TC_DBG_TILES) a.dbg[(it_) * 16 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
-__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const TcCfg c) {
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, uint8_t* smem, uint32_t tmem_base,
+                                            uint32_t bar_accfull0, uint32_t bar_accempty0, int warp, int lane, bool dbg_on) {
+    const int q = warp & 3, hh = warp >> 2, ny = blockIdx.y;
+    float* sE = reinterpret_cast<float*>(smem + c.epi_off) + warp * (32 * TC_EPI_PITCH);
+    float* srow = sE + lane * TC_EPI_PITCH;
+    const int ngroups = (c.ntile + 31) >> 5;
+    const float inv_div = 1.f / a.out_div;
+    const bool has_res = a.res != nullptr;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+        TC_STAMP(it, 0);
+        const int b = find_segment(a.tile_cu, a.B, tile);
+        const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
+        const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
+        const long row0 = (long)cb0 * a.rate;
+        const int len = (cb1 - cb0) * a.rate;
+        TC_STAMP(it, 1);
+        const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
+        tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
+        TC_STAMP(it, 2);
+        tc::tc_fence_after();
+        const int trow0 = t0 + q * 32;                    // first time row of this warp
+        const int nrows = len - trow0;                    // rows of this warp inside the utterance (<= 0: nothing to store)
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
+        const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
+        if (nrows > 0) {                                  // warp-uniform
+            for (int g = hh; g < ngroups; g += 2) {
+                const int n0 = g * 32;
+                const int ng = ny * c.ntile + n0;         // global accumulator column of this 32-wide group
+                const int ncols = min(32, c.ntile - n0);  // 16 or 32
+                // ---- phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias / gate -> transpose buffer
+#pragma unroll
+                for (int hcol = 0; hcol < 32; hcol += 16) {
+                    if (hcol < ncols) {
+                        float v[16];
+                        tc::tmem_ld16(trow + (uint32_t)(n0 + hcol), v);
+                        const int nc = ng + hcol;
+                        if (a.bias) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nc) + k); v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w; }
+                        }
+                        if (ur) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { const float4 uu = __ldg(reinterpret_cast<const float4*>(ur + nc) + k); v[4 * k] += uu.x; v[4 * k + 1] += uu.y; v[4 * k + 2] += uu.z; v[4 * k + 3] += uu.w; }
+                        }
+                        if (EPI == EPI_GATE) {
+                            // interleaved (tanh-arg, sigmoid-arg) pairs (commons.py:99-106); MUFU tanh: the gate output is
+                            // rounded to bf16 by the next conv's loader, far coarser than tanh.approx's 2^-11
+                            float gt[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) gt[j] = tanh_fast(v[2 * j]) * fmaf(0.5f, tanh_fast(0.5f * v[2 * j + 1]), 0.5f);
+                            *reinterpret_cast<float4*>(srow + (hcol >> 1)) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+                            *reinterpret_cast<float4*>(srow + (hcol >> 1) + 4) = make_float4(gt[4], gt[5], gt[6], gt[7]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                *reinterpret_cast<float4*>(srow + hcol + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction; all global
+                // loads of 4 iterations are issued before their first use
+                const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
+                const int og = (EPI == EPI_GATE) ? (ng >> 1) : ng;               // first output column
+                const int lsh = ocols == 32 ? 3 : (ocols == 16 ? 2 : 1);
+                const int lpr = 1 << lsh, rpi = 32 >> lsh;                       // lanes per row, rows per instruction; iterations = lpr
+                const int cq = (lane & (lpr - 1)) * 4, rsub = lane >> lsh;
+                const int n = og + cq;
+                float* dst0; long ldd; int acc;
+                if (EPI == EPI_SPLIT && n >= a.split) { dst0 = a.out2 + a.ocol2 + (n - a.split); ldd = a.ldo2; acc = a.accumulate2; }
+                else { dst0 = a.out + a.ocol + n; ldd = a.ldo; acc = a.accumulate; }
+                dst0 += (row0 + trow0 + rsub) * ldd;
+                const float* res0 = has_res ? (a.res + (row0 + trow0 + rsub) * a.ldres + a.rescol + n) : nullptr;
+                const float* st0 = sE + rsub * TC_EPI_PITCH + cq;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    if (h2 * 4 < lpr) {
+                        float4 o[4], rr[4], pp[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int itr = h2 * 4 + u;
+                            const int rl = itr * rpi + rsub;
+                            ok[u] = (itr < lpr) && (rl < nrows);
+                            rr[u] = make_float4(0.f, 0.f, 0.f, 0.f); pp[u] = rr[u];
+                            if (ok[u]) {
+                                if (has_res) rr[u] = *reinterpret_cast<const float4*>(res0 + (long)(itr * rpi) * a.ldres);
+                                if (EPI != EPI_GATE && EPI != EPI_SUBFROM && acc) pp[u] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd);
+                                o[u] = *reinterpret_cast<const float4*>(st0 + itr * rpi * TC_EPI_PITCH);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (!ok[u]) continue;
+                            const int itr = h2 * 4 + u;
+                            float4 v4 = o[u];
+                            if (EPI == EPI_SUBFROM) {
+                                v4 = make_float4(rr[u].x - v4.x, rr[u].y - v4.y, rr[u].z - v4.z, rr[u].w - v4.w);
+                            } else if (EPI != EPI_GATE) {
+                                v4.x += rr[u].x; v4.y += rr[u].y; v4.z += rr[u].z; v4.w += rr[u].w;
+                                if (a.out_act == ACT_RELU) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+                                v4.x += pp[u].x; v4.y += pp[u].y; v4.z += pp[u].z; v4.w += pp[u].w;
+                                if (a.out_div != 1.f) { v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div; }
+                                if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
+                            }
+                            *reinterpret_cast<float4*>(dst0 + (long)(itr * rpi) * ldd) = v4;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
+        tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
+        TC_STAMP(it, 3);
+    }
+}
+
+// scalar epilogue for layouts that cannot use 128-bit accesses (never on the production shapes; kept for generality)
+__device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCfg& c, uint32_t tmem_base, uint32_t bar_accfull0,
+                                                   uint32_t bar_accempty0, int warp, int lane) {
+    const int q = warp & 3, hh = warp >> 2, ny = blockIdx.y;
+    const int ngroups = (c.ntile + 15) >> 4;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+        const int b = find_segment(a.tile_cu, a.B, tile);
+        const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
+        const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
+        const long row0 = (long)cb0 * a.rate;
+        const int len = (cb1 - cb0) * a.rate;
+        const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
+        tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
+        tc::tc_fence_after();
+        const int t = t0 + q * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
+        for (int g = hh; g < ngroups; g += 2) {
+            float v[16];
+            tc::tmem_ld16(trow + (uint32_t)(g * 16), v);
+            if (t < len) {
+                const int nc = ny * c.ntile + g * 16;
+                if (a.epi == EPI_GATE) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int n2 = nc + 2 * j;
+                        float va = v[2 * j], vb = v[2 * j + 1];
+                        if (a.bias) { va += __ldg(a.bias + n2); vb += __ldg(a.bias + n2 + 1); }
+                        if (a.utab) { const float* ur = a.utab + (long)__ldg(a.uidx + b) * a.utab_ld; va += __ldg(ur + n2); vb += __ldg(ur + n2 + 1); }
+                        if (n2 < a.n) a.out[(row0 + t) * a.ldo + a.ocol + (n2 >> 1)] = tanhf(va) * (1.f / (1.f + __expf(-vb)));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (nc + j < a.n) conv_epilogue_store(a, b, row0 + t, nc + j, v[j]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sW = smem + (size_t)c.nabuf * c.a_bytes;
@@ -183,7 +352,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ny = blockIdx.y;
-    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 4 || warp >= 8);
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 &&
+                        (warp == 0 || warp == TC_EPI_WARPS || warp >= TC_EPI_WARPS + TC_LOAD_WARPS);
     if (dbg_on && warp == 0) a.dbg[15] = (unsigned long long)clock64();
 
     if (tid == 0) {
@@ -192,11 +362,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             tc::mbar_init(bar_afull0 + 8u * i, TC_LOAD_THREADS);
             tc::mbar_init(bar_aempty0 + 8u * i, 1);
             tc::mbar_init(bar_accfull0 + 8u * i, 1);
-            tc::mbar_init(bar_accempty0 + 8u * i, 128);
+            tc::mbar_init(bar_accempty0 + 8u * i, TC_EPI_WARPS * 32);
         }
         tc::fence_mbar_init();
     }
-    if (warp == 8) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
+    if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -207,130 +377,32 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
     const uint32_t lbo_a = (uint32_t)c.rows_a * 16u;
     const uint32_t lbo_b = (uint32_t)c.ntile * 16u;
 
-    if (warp < 4) {
-        // ================= epilogue (128 threads) =================
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-            TC_STAMP(it, 0);
-            const int b = find_segment(a.tile_cu, a.B, tile);
-            const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
-            const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
-            const long row0 = (long)cb0 * a.rate;
-            const int len = (cb1 - cb0) * a.rate;
-            TC_STAMP(it, 1);
-            const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
-            tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
-            TC_STAMP(it, 2);
-            tc::tc_fence_after();
-            // Two-phase epilogue.  Phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias /
-            // gate, then a warp-private smem transpose buffer.  Phase 2 (8 lanes = 128 contiguous bytes of one row,
-            // 4 rows per warp instruction): residual / accumulate / activation with fully coalesced 128-bit global
-            // accesses.  (A thread-per-row epilogue touches 32 different 128 B lines per instruction.)
-            float* sE = reinterpret_cast<float*>(smem + c.epi_off) + warp * (32 * TC_EPI_PITCH);
-            const int trow0 = t0 + warp * 32;                 // first time row of this warp
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + cbuf * (uint32_t)c.ntile;
-            const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
-            const bool gate = (a.epi == EPI_GATE);
-            for (int n0 = 0; n0 < c.ntile; n0 += 32) {
-                const int ng = ny * c.ntile + n0;             // global accumulator column of this 32-wide group
-                const int ncols = min(32, c.ntile - n0);      // 16 or 32
-#pragma unroll
-                for (int hcol = 0; hcol < 32; hcol += 16) {
-                    if (hcol >= ncols) break;
-                    float v[16];
-                    tc::tmem_ld16(trow + (uint32_t)(n0 + hcol), v);
-                    const int nc = ng + hcol;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (nc + 4 * q < a.npad) {
-                            if (a.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nc) + q); v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w; }
-                            if (ur) { const float4 uu = __ldg(reinterpret_cast<const float4*>(ur + nc) + q); v[4 * q] += uu.x; v[4 * q + 1] += uu.y; v[4 * q + 2] += uu.z; v[4 * q + 3] += uu.w; }
-                        }
-                    }
-                    float* srow = sE + lane * TC_EPI_PITCH;
-                    if (gate) {
-                        // interleaved (tanh-arg, sigmoid-arg) pairs (commons.py:99-106); MUFU tanh: the gate output is
-                        // rounded to bf16 by the next conv's loader, far coarser than tanh.approx's 2^-11
-                        float g[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) g[j] = tanh_fast(v[2 * j]) * fmaf(0.5f, tanh_fast(0.5f * v[2 * j + 1]), 0.5f);
-                        *reinterpret_cast<float4*>(srow + (hcol >> 1)) = make_float4(g[0], g[1], g[2], g[3]);
-                        *reinterpret_cast<float4*>(srow + (hcol >> 1) + 4) = make_float4(g[4], g[5], g[6], g[7]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            *reinterpret_cast<float4*>(srow + hcol + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                }
-                __syncwarp();
-                // ---- phase 2
-                const int ocols = gate ? (ncols >> 1) : ncols;          // staged output columns of this group
-                const int og = gate ? (ng >> 1) : ng;                   // first output column
-                const int olim = gate ? (a.n >> 1) : a.n;               // valid output columns
-                const int cq = (lane & 7) * 4;
-                if (c.vec) {
-#pragma unroll
-                    for (int itr = 0; itr < 8; itr++) {
-                        const int rl = itr * 4 + (lane >> 3);
-                        const int t = trow0 + rl;
-                        if (t >= len || cq >= ocols || og + cq >= olim) continue;
-                        const long row = row0 + t;
-                        const int n = og + cq;
-                        float4 o = *reinterpret_cast<const float4*>(sE + rl * TC_EPI_PITCH + cq);
-                        if (a.epi == EPI_SUBFROM) {
-                            const float4 rr = *reinterpret_cast<const float4*>(a.res + row * a.ldres + a.rescol + n);
-                            *reinterpret_cast<float4*>(a.out + row * a.ldo + a.ocol + n) = make_float4(rr.x - o.x, rr.y - o.y, rr.z - o.z, rr.w - o.w);
-                            continue;
-                        }
-                        float* dst; int acc;
-                        if (a.epi == EPI_SPLIT && n >= a.split) { dst = a.out2 + row * a.ldo2 + a.ocol2 + (n - a.split); acc = a.accumulate2; }
-                        else { dst = a.out + row * a.ldo + a.ocol + n; acc = a.accumulate; }
-                        if (a.res) { const float4 rr = *reinterpret_cast<const float4*>(a.res + row * a.ldres + a.rescol + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                        if (a.out_act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        if (acc) { const float4 pp = *reinterpret_cast<const float4*>(dst); o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
-                        if (a.out_div != 1.f) { o.x = o.x / a.out_div; o.y = o.y / a.out_div; o.z = o.z / a.out_div; o.w = o.w / a.out_div; }
-                        if (a.out_act == ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-                        *reinterpret_cast<float4*>(dst) = o;
-                    }
-                } else {
-                    // unaligned / ragged-N fallback: scalar, still row-contiguous per warp instruction
-                    for (int rl = 0; rl < 32; rl++) {
-                        const int t = trow0 + rl;
-                        if (t >= len) break;
-                        const long row = row0 + t;
-                        if (lane < ocols && og + lane < olim) {
-                            const float val = sE[rl * TC_EPI_PITCH + lane];
-                            if (gate) a.out[row * a.ldo + a.ocol + og + lane] = val;
-                            else {
-                                ConvArgs a2 = a; a2.bias = nullptr; a2.utab = nullptr;      // already applied in phase 1
-                                conv_epilogue_store(a2, b, row, og + lane, val);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
-            tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
-            TC_STAMP(it, 3);
-        }
-    } else if (warp < 8) {
-        // ================= activation loaders (128 threads) =================
-        const int lt = tid - 128;
+    if (warp < TC_EPI_WARPS) {
+        // ================= epilogue (256 threads) =================
+        if (!c.vec) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
+        else if (a.epi == EPI_GATE) tc_epilogue<EPI_GATE>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
+        else if (a.epi == EPI_SPLIT) tc_epilogue<EPI_SPLIT>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
+        else if (a.epi == EPI_SUBFROM) tc_epilogue<EPI_SUBFROM>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
+        else tc_epilogue<EPI_STORE>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
+    } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
+        // ================= activation loaders (256 threads) =================
+        const int lt = tid - TC_EPI_WARPS * 32;
         uint32_t it = 0;
         const int items = c.rows_a * kc_total;
-        const int dr = TC_LOAD_THREADS / kc_total, dk = TC_LOAD_THREADS - dr * kc_total;   // advance of (r, kc) per 128 items
+        const int dr = TC_LOAD_THREADS / kc_total, dk = TC_LOAD_THREADS - dr * kc_total;   // advance of (r, kc) per TC_LOAD_THREADS items
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            TC_STAMP(it, 4);
             const int b = find_segment(a.tile_cu, a.B, tile);
             const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
             const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
             const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
-            TC_STAMP(it, 4);
             tc::mbar_wait(bar_aempty0 + 8u * abuf, (ause & 1u) ^ 1u);     // MMAs that read this buffer have retired
             TC_STAMP(it, 5);
             uint8_t* dstA = sA + (size_t)abuf * c.a_bytes;
+            const float* xbase = a.x + (row0 + t0 + c.min_off) * a.ldx + a.xcol;
+            const int tlo = -(t0 + c.min_off), thi = len - (t0 + c.min_off);      // valid tile rows: tlo <= r < thi
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
             // flight per thread before any conversion so the load latency is paid once per batch
             int r = lt / kc_total, kc = lt - r * kc_total;
@@ -341,11 +413,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     rr[u] = r; kk[u] = kc;
-                    const int t = t0 + c.min_off + r;
                     ok[u] = (base + u * TC_LOAD_THREADS < items);
                     v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
-                    if (ok[u] && t >= 0 && t < len) {
-                        const float4* src = reinterpret_cast<const float4*>(a.x + (row0 + t) * a.ldx + a.xcol + kc * 8);
+                    if (ok[u] && r >= tlo && r < thi) {
+                        const float4* src = reinterpret_cast<const float4*>(xbase + (long)r * a.ldx + kc * 8);
                         v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
                     }
                     r += dr; kc += dk;
@@ -378,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
             tc::mbar_arrive(bar_afull0 + 8u * abuf);
             TC_STAMP(it, 6);
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= weight producer (one thread, cp.async.bulk ring) =================
         if (tc::elect_one()) {
             uint32_t s = 0, ph = 1;                       // ring slot and the parity to wait for on its "empty" barrier
@@ -455,7 +526,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const ConvArgs a, const 
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
+    if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -479,8 +550,8 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     c.piece_ch = a.cin < TC_PIECE_CH ? a.cin : TC_PIECE_CH;
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
     c.npieces = a.ntaps * nseg * c.cpt;
-    const int limit = 200 * 1024;
-    const int epi_bytes = 4 * 32 * TC_EPI_PITCH * 4;
+    const int limit = 222 * 1024;
+    const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
     if (!nt) for (int cand = 256; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { nt = cand; break; }
     for (;;) {
