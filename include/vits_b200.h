@@ -112,6 +112,15 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
 int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t out_kind,
                 void* out, int64_t out_capacity, float volume, int32_t normalize);
 
+/* Output buffers.  onnxruntime allocates the array run() returns (voice.py:374-377); here the caller does, and a
+ * page-locked buffer from vits_host_alloc() makes the device->host transfer a true asynchronous DMA on the handle's
+ * copy stream: with option "async_output" = 1, vits_decode(out_kind = 1) returns once the transfer is enqueued and
+ * vits_wait_output() (or the second-next vits_decode on the same handle) completes it, so the transfer of one batch
+ * overlaps the kernels of the next.  Without the option vits_decode() blocks until `out` is complete. */
+int vits_host_alloc(size_t nbytes, void** out);
+int vits_host_free(void* p);
+int vits_wait_output(vits_handle* h, int older_only);   /* older_only: leave the most recent vits_decode's transfer in flight */
+
 /* Test / debugging: copy a stage tensor of the last prepare/decode to the host.
  * names: "x" [sumT,H], "m_p" [sumT,C], "logs_p" [sumT,C], "logw" [sumT], "durations" (int32
  * bits, [sumT]), "frame_index" (int32 bits, [frames of last chunk]), "z_p" / "z"

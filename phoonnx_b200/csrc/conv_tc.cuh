@@ -200,8 +200,10 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
         const int nrows = len - trow0;                    // rows of this warp inside the utterance (<= 0: nothing to store)
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
         const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
+        long long ph1 = 0, ph2 = 0, tq = 0;
         if (nrows > 0) {                                  // warp-uniform
             for (int g = hh; g < ngroups; g += 2) {
+                if (dbg_on) tq = clock64();
                 const int n0 = g * 32;
                 const int ng = ny * c.ntile + n0;         // global accumulator column of this 32-wide group
                 const int ncols = min(32, c.ntile - n0);  // 16 or 32
@@ -236,6 +238,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                     }
                 }
                 __syncwarp();
+                if (dbg_on) { const long long t2 = clock64(); ph1 += t2 - tq; tq = t2; }
                 // ---- phase 2: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction; all global
                 // loads of 4 iterations are issued before their first use
                 const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
@@ -286,8 +289,10 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                     }
                 }
                 __syncwarp();
+                if (dbg_on) ph2 += clock64() - tq;
             }
         }
+        if (dbg_on && it < TC_DBG_TILES) { a.dbg[it * 16 + 13] = (unsigned long long)ph1; a.dbg[it * 16 + 14] = (unsigned long long)ph2; }
         tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
         tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
         TC_STAMP(it, 3);

@@ -98,6 +98,13 @@ struct vits_handle {
     int conv_counter = 0;
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // output path: the audio of one vits_decode lands in one of two device buffers and leaves through a copy stream, so the
+    // device->host DMA of call k overlaps the kernels of call k+1 (and chunk c's DMA those of chunk c+1)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
+    bool out_pending[2] = {false, false};
+    int audio_sel = 0;
+    Buf audio_alt;
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
     float stage_ms[3] = {0, 0, 0};
@@ -373,6 +380,9 @@ int vits_create(const vits_arch* arch, int device_id, vits_handle** out) {
         delete h; return VITS_E_CUDA;
     }
     cudaEventCreate(&h->ev_t0); cudaEventCreate(&h->ev_t1);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
     *out = h;
     return VITS_OK;
 }
@@ -710,8 +720,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         CK(h, cudaMemcpyAsync(h->inj_z.p, noise_z, nb, cudaMemcpyHostToDevice, st));
         d_injz = ptr<float>(h->inj_z);
     }
-    if ((rc = ensure(h, h->audio, std::max<int64_t>(total_samples, 1) * 4))) return rc;
-    float* audio = ptr<float>(h->audio);
+    // alternate between two device audio buffers; the one chosen must have finished leaving for the host
+    h->audio_sel ^= 1;
+    const int asel = h->audio_sel;
+    if (h->out_pending[asel]) { CK(h, cudaEventSynchronize(h->ev_out[asel])); h->out_pending[asel] = false; }
+    Buf& abuf = asel ? h->audio_alt : h->audio;
+    if ((rc = ensure(h, abuf, std::max<int64_t>(total_samples, 1) * 4))) return rc;
+    float* audio = ptr<float>(abuf);
+    const bool async_out = h->opts.count("async_output") && h->opts["async_output"] != 0;
     // per-stage geometry
     std::vector<int> rates(A.n_ups + 1), chans(A.n_ups + 1);
     rates[0] = 1; chans[0] = A.up_init;
@@ -909,12 +925,20 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         CK(h, cudaGetLastError());
         stage_end(h);
+        if (out_kind == 1) {
+            // this chunk's audio leaves on the copy stream while the next chunk computes
+            CK(h, cudaEventRecord(h->ev_chunk, st));
+            CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk, 0));
+            CK(h, cudaMemcpyAsync(static_cast<float*>(out) + (int64_t)f_lo * hop, audio + (int64_t)f_lo * hop, (size_t)Fr * hop * 4,
+                                  cudaMemcpyDeviceToHost, h->copy_stream));
+        }
         b_lo = b_hi;
     }
     // ---- output
     if (out_kind == 1) {
-        CK(h, cudaMemcpyAsync(out, audio, total_samples * 4, cudaMemcpyDeviceToHost, st));
-        CK(h, cudaStreamSynchronize(st));
+        CK(h, cudaEventRecord(h->ev_out[asel], h->copy_stream));
+        h->out_pending[asel] = true;
+        if (!async_out) { CK(h, cudaEventSynchronize(h->ev_out[asel])); h->out_pending[asel] = false; }
     } else if (out_kind == 2) {
         // caller-side post-processing on device (voice.py:271-282, 88-91)
         if ((rc = ensure(h, h->peaks, B * 4)) || (rc = ensure(h, h->cu_y_dev, (B + 1) * 4)) ||
@@ -1040,6 +1064,30 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     return rc;
 }
 
+int vits_wait_output(vits_handle* h, int older_only) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    for (int i = 0; i < 2; i++) {
+        if (older_only && i == h->audio_sel) continue;      // the most recent vits_decode keeps running
+        if (h->out_pending[i]) { CK(h, cudaEventSynchronize(h->ev_out[i])); h->out_pending[i] = false; }
+    }
+    return VITS_OK;
+}
+
+int vits_host_alloc(size_t nbytes, void** out) {
+    if (!out || nbytes == 0) return VITS_E_INVALID;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, nbytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return VITS_E_NOMEM; }
+    *out = p;
+    return VITS_OK;
+}
+
+int vits_host_free(void* p) {
+    if (!p) return VITS_OK;
+    return cudaFreeHost(p) == cudaSuccess ? VITS_OK : VITS_E_CUDA;
+}
+
 int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles, double* total_cycles) {
     if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > 512 || rows < 128 + 3 * na || rows > 700 || nctas < 1) return VITS_E_INVALID;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1074,9 +1122,12 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
+    for (int i = 0; i < 2; i++) if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -101,8 +102,11 @@ def load_library(path: Optional[str] = None):
     lib.vits_last_error.restype = C.c_char_p
     lib.vits_destroy.argtypes = [H]
     lib.vits_destroy.restype = None
+    lib.vits_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.vits_host_free.argtypes = [C.c_void_p]
+    lib.vits_wait_output.argtypes = [H, C.c_int]
     for fn in ("vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare", "vits_decode",
-               "vits_timer_start", "vits_timer_stop", "vits_stage_ms"):
+               "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_host_alloc", "vits_host_free", "vits_wait_output"):
         getattr(lib, fn).restype = C.c_int
     if path is None:
         _lib = lib
@@ -112,7 +116,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = (
     "vits_abi_version", "vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare",
     "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_launch_count",
-    "vits_last_error", "vits_destroy",
+    "vits_last_error", "vits_destroy", "vits_host_alloc", "vits_host_free", "vits_wait_output",
 )
 
 _DT = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.int32): 2}
@@ -120,6 +124,55 @@ _DT = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.int32): 2}
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedBlock:
+    """One page-locked host allocation; exposes the buffer protocol numpy needs and goes back to its pool when the
+    last array over it is garbage-collected (so the array run() returns is owned by Python, as with onnxruntime)."""
+
+    def __init__(self, pool, ptr: int, nbytes: int):
+        self.pool, self.ptr, self.nbytes = pool, ptr, nbytes
+
+    def array(self, n: int, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        raw = (C.c_uint8 * (n * dt.itemsize)).from_address(self.ptr)
+        arr = np.frombuffer(raw, dtype=dt, count=n)
+        weakref.finalize(raw, self.pool._give_back, self)       # `raw` lives exactly as long as arrays over it
+        return arr
+
+
+class PinnedPool:
+    """Size-classed pool of cudaHostAlloc'd blocks (vits_host_alloc): allocation costs milliseconds, reuse is free."""
+
+    def __init__(self, lib, max_cached_bytes: int = 8 << 30):
+        self.lib, self.free, self.cached, self.max_cached = lib, {}, 0, max_cached_bytes
+
+    def take(self, n: int, dtype) -> np.ndarray:
+        nbytes = max(1, n * np.dtype(dtype).itemsize)
+        cls = 1 << max(16, (nbytes - 1).bit_length())
+        lst = self.free.get(cls)
+        if lst:
+            blk = lst.pop()
+            self.cached -= cls
+        else:
+            p = C.c_void_p()
+            if self.lib.vits_host_alloc(cls, C.byref(p)) != 0 or not p.value:
+                return np.empty((n,), dtype)                    # pageable fallback: still correct, just a staged copy
+            blk = _PinnedBlock(self, p.value, cls)
+        return blk.array(n, dtype)
+
+    def _give_back(self, blk):
+        if self.cached + blk.nbytes > self.max_cached:
+            self.lib.vits_host_free(C.c_void_p(blk.ptr))
+            return
+        self.free.setdefault(blk.nbytes, []).append(blk)
+        self.cached += blk.nbytes
+
+    def drain(self):
+        for lst in self.free.values():
+            for blk in lst:
+                self.lib.vits_host_free(C.c_void_p(blk.ptr))
+        self.free, self.cached = {}, 0
 
 
 class Engine:
@@ -146,6 +199,7 @@ class Engine:
         self._check(self.lib.vits_finalize(self._h))
         self._B = 0
         self._ylen = None
+        self._pool = PinnedPool(self.lib)
 
     # ------------------------------------------------------------------
     def _check(self, rc: int):
@@ -211,14 +265,22 @@ class Engine:
             self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 0, None, 0, volume, int(normalize)))
             return None
         if out == "f32":
-            buf = np.empty((total,), np.float32)
+            # page-locked result: the device->host transfer is a DMA on the copy stream; with set_async_output(True)
+            # it is still in flight when this returns and wait_output() completes it
+            buf = self._pool.take(total, np.float32)
             self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 1, _ptr(buf), total, volume, int(normalize)))
             return buf
         if out == "i16":
-            buf = np.empty((total,), np.int16)
+            buf = self._pool.take(total, np.int16)
             self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 2, _ptr(buf), total, volume, int(normalize)))
             return buf
         raise ValueError("out must be 'none', 'f32' or 'i16'")
+
+    def set_async_output(self, on: bool):
+        self.set_option("async_output", 1 if on else 0)
+
+    def wait_output(self, older_only: bool = False):
+        self._check(self.lib.vits_wait_output(self._h, 1 if older_only else 0))
 
     def fetch(self, name: str) -> np.ndarray:
         a = self.arch
@@ -252,6 +314,7 @@ class Engine:
         if getattr(self, "_h", None):
             self.lib.vits_destroy(self._h)
             self._h = C.c_void_p()
+            self._pool.drain()
 
     def __del__(self):
         try:

@@ -123,5 +123,26 @@ class B200Session:
         self.last_lengths = ylen * self.engine.hop
         return audio, self.last_lengths
 
+    def synthesize_many(self, feeds, out: str = "f32", volume: float = 1.0, normalize: bool = True):
+        """Batched form of the serial loop in ``TTSVoice.synthesize`` (voice.py:265-269): yields
+        ``(packed audio, samples per utterance)`` per feed, in order, with the device->host transfer of batch k
+        overlapping the kernels of batch k+1 (page-locked results, copy stream; include/vits_b200.h)."""
+        eng = self.engine
+        eng.set_async_output(True)
+        try:
+            prev = None
+            for feed in feeds:
+                cur = self.synthesize_packed(feed, out=out, volume=volume, normalize=normalize)
+                if prev is not None:
+                    eng.wait_output(older_only=True)
+                    yield prev
+                prev = cur
+            if prev is not None:
+                eng.wait_output()
+                yield prev
+        finally:
+            eng.wait_output()
+            eng.set_async_output(False)
+
     def end_profiling(self):
         return None

@@ -374,3 +374,30 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
         assert np.array_equal(alen, clen)
         assert alt.engine.launch_count() - n0 < n_fused       # no separate conv_post launch
         assert snr_db(a, c) > 45.0, (opts, snr_db(a, c))
+
+
+def test_synthesize_many_equals_serial_calls(lib, tmp_path_factory):
+    """The pipelined batch call (page-locked results, device->host transfer of batch k under the kernels of batch
+    k+1, alternating device audio buffers) returns exactly what the serial per-batch calls return."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, "x_low", 1)
+    rs = np.random.RandomState(5)
+    feeds = []
+    for B in (3, 1, 4, 2, 5):
+        lens = rs.randint(5, 60, size=(B,)).astype(np.int64)
+        ids = rs.randint(0, arch.n_vocab, (B, int(lens.max()))).astype(np.int64)
+        feeds.append({"input": ids, "input_lengths": lens, "scales": SCALES})
+    for prec in ("fp32", "bf16"):
+        a = B200Session(p, precision=prec, seed=77)
+        serial = [a.synthesize_packed(f) for f in feeds]
+        serial = [(x.copy(), n.copy()) for x, n in serial]
+        b = B200Session(p, precision=prec, seed=77)
+        b.engine.set_option("max_chunk_frames", 96)          # several chunks per batch: per-chunk transfers
+        many = list(b.synthesize_many(feeds))
+        assert len(many) == len(serial)
+        for (x0, n0), (x1, n1) in zip(serial, many):
+            assert np.array_equal(n0, n1)
+            assert x0.shape == x1.shape and np.array_equal(x0, x1)
+        # the session is back in blocking mode afterwards and page-locked blocks are recycled
+        again, alen = b.synthesize_packed(feeds[0])              # (a new call number => new noise, new durations)
+        assert again.dtype == np.float32 and again.shape == (int(alen.sum()),) and np.isfinite(again).all()

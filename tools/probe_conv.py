@@ -41,10 +41,10 @@ def main():
         t0 = int(st[0, 15])
         print(f"=== conv launch {idx}: {what} (fetched {n})")
         for it in range(6):
-            ev = sorted((int(st[it, s]) - t0, NAMES.get(s, str(s))) for s in range(15) if st[it, s])
+            ev = sorted((int(st[it, s]) - t0, NAMES.get(s, str(s))) for s in range(13) if st[it, s])
             if not ev:
                 break
-            print(f" tile {it}: " + "  ".join(f"{nm}@{t}" for t, nm in ev))
+            print(f" tile {it}: " + "  ".join(f"{nm}@{t}" for t, nm in ev) + f"  | epi phase1 {int(st[it, 13])} phase2 {int(st[it, 14])}")
     eng.set_option("conv_dbg", 0)
 
 
