@@ -34,6 +34,7 @@ struct ConvArgs {
     // bf16(x - xh)).  The activation tile holds a hi and a lo plane; wtc then holds 3*cin input channels per tap
     // ([wh | wl | wh]).  Used for the text side, whose output feeds ceil(exp(logw)).
     int split3;
+    __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
     unsigned long long* dbg;   // test-only phase timeline of CTA (0,0): [tile][16] clock64 stamps, or null
 };
 

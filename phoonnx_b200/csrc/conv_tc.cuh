@@ -284,6 +284,13 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                                 if (a.out_div != 1.f) { v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div; }
                                 if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
                             }
+                            if (EPI == EPI_STORE && a.outb) {
+                                // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
+                                const float sl = a.outb_slope;
+                                const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(v4.x, v4.x * sl), fmaxf(v4.y, v4.y * sl)),
+                                                             tc::pack_bf16(fmaxf(v4.z, v4.z * sl), fmaxf(v4.w, v4.w * sl)));
+                                *reinterpret_cast<uint2*>(a.outb + (row0 + trow0 + rsub + itr * rpi) * (long)a.ldo + a.ocol + n) = pk2;
+                            } else
                             *reinterpret_cast<float4*>(dst0 + (long)(itr * rpi) * ldd) = v4;
                         }
                     }

@@ -15,6 +15,7 @@
 #include "conv_tc.cuh"
 #include "mrf_tc.cuh"
 #include "mrf2_tc.cuh"
+#include "mrf3_tc.cuh"
 #include "probe_tc.cuh"
 
 #include <algorithm>
@@ -751,9 +752,13 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         std::vector<MrfCfg> mrf_cfg(A.n_ups + 1);
         std::vector<Mrf2Args> mrf2_args(A.n_ups + 1);
         std::vector<Mrf2Cfg> mrf2_cfg(A.n_ups + 1);
-        std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: unfused, 1: v1, 2: v2
+        std::vector<Mrf3Args> mrf3_args(A.n_ups + 1);
+        std::vector<Mrf3Cfg> mrf3_cfg(A.n_ups + 1);
+        std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: unfused, 1: v1, 2: v2, 3: v3 (bf16 inter-stage rows, optional fused ConvTranspose)
+        std::vector<int> up_fused(A.n_ups + 2, 0);    // stage's ConvTranspose runs inside its v3 kernel
         bool post_fused = false;
         const bool use_v1 = h->opts["mrf_v1"] != 0;
+        const bool use_v2 = h->opts["mrf_v2"] != 0;
         for (int i = 0; i < A.n_ups; i++) {
             const int co = chans[i + 1];
             if (h->precision != 1 || A.resblock_type != 2 || A.n_rbk > MRF_MAX_RB || h->opts["no_fused_mrf"] != 0) continue;
@@ -772,7 +777,31 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 m2.w[j][0] = m.w[j][0]; m2.w[j][1] = m.w[j][1]; m2.b[j][0] = m.b[j][0]; m2.b[j][1] = m.b[j][1];
             }
             if (!ok) continue;
-            if (!use_v1) {
+            if (!use_v1 && !use_v2) {
+                // v3: the stage's input arrives as bf16 lrelu rows; when the previous stage is v3 as well and the geometry
+                // allows (u = 4), the ConvTranspose runs inside the kernel on the previous stage's bf16 output
+                Mrf3Args& m3 = mrf3_args[i + 1];
+                memset(&m3, 0, sizeof m3);
+                m3.C = co; m3.nrb = A.n_rbk; m3.out_div = (float)A.n_rbk; m3.slope = 0.1f;
+                for (int j = 0; j < A.n_rbk; j++) {
+                    m3.k[j] = m.k[j]; m3.d1[j] = m.d1[j]; m3.d2[j] = m.d2[j];
+                    m3.w[j][0] = m.w[j][0]; m3.w[j][1] = m.w[j][1]; m3.b[j][0] = m.b[j][0]; m3.b[j][1] = m.b[j][1];
+                }
+                const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
+                const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
+                const auto& U = h->ups[i];
+                const bool can_up = i >= 1 && mrf_on[i] == 3 && U.rate == 4 && U.A.wtc && U.B.wtc && h->opts["no_fused_ups"] == 0;
+                bool done = false;
+                for (int tryu = can_up ? 1 : 0; tryu >= 0 && !done; tryu--) {
+                    m3.up_u = tryu ? U.rate : 0; m3.up_cin = tryu ? U.A.cin : 0;
+                    for (int tryp = want_post ? 1 : 0; tryp >= 0 && !done; tryp--)
+                        if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0)) {
+                            mrf_on[i + 1] = 3; up_fused[i + 1] = tryu; if (tryp) post_fused = true; done = true;
+                        }
+                }
+                if (!done) { m3.up_u = 0; m3.up_cin = 0; }
+            }
+            if (!mrf_on[i + 1] && !use_v1) {
                 const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
                 const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
                 if (want_post && mrf2_plan(m2, mrf2_cfg[i + 1], nbp, true)) { mrf_on[i + 1] = 2; post_fused = true; }
@@ -781,7 +810,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             if (!mrf_on[i + 1] && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
         }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
-        for (int i = 0; i <= A.n_ups; i++) tb.add(rates[i], mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0));
+        for (int i = 0; i <= A.n_ups; i++)
+            tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0)));
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
             (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) ||
@@ -845,6 +875,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             if ((rc = launch_conv(h, a, T1, true))) return rc;
         }
         const float* cur = dpre; int cur_c = A.up_init;
+        const __nv_bfloat16* cur_b = nullptr;          // previous stage's output as bf16 lrelu rows (feeds a fused ConvTranspose)
         for (int i = 0; i < A.n_ups; i++) {
             auto& U = h->ups[i];
             const Tiles Tin = tb.get(meta, rates[i]);
@@ -853,11 +884,40 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             float* XS = XSab[i & 1];      // stage output; the next stage reads it while writing the other one
             // polyphase ConvTranspose1d (models.py:320-332): output row-block q holds u*co contiguous floats
             // == rows q*u .. q*u+u-1 of the [rows*u, co] result; phases [0,u/2) use taps {-1,0}, the rest {0,+1}
-            ConvArgs a = base_args(U.A, cur, cur_c, 0, X, u * co, 0); a.in_act = 1; a.in_slope = 0.1f;
-            if ((rc = launch_conv(h, a, Tin, true))) return rc;
-            a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
-            if ((rc = launch_conv(h, a, Tin, true))) return rc;
-            if (mrf_on[i + 1] == 2) {
+            ConvArgs a;
+            __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(X);          // v3: the stage input as bf16 lrelu rows
+            if (!up_fused[i + 1]) {
+                a = base_args(U.A, cur, cur_c, 0, X, u * co, 0); a.in_act = 1; a.in_slope = 0.1f;
+                if (mrf_on[i + 1] == 3) { a.outb = Xb; a.outb_slope = 0.1f; }
+                if ((rc = launch_conv(h, a, Tin, true))) return rc;
+                a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
+                if (mrf_on[i + 1] == 3) { a.outb = Xb; a.outb_slope = 0.1f; }
+                if ((rc = launch_conv(h, a, Tin, true))) return rc;
+            }
+            if (mrf_on[i + 1] == 3) {
+                Mrf3Args& m = mrf3_args[i + 1];
+                m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
+                if (up_fused[i + 1]) {
+                    m.hb = cur_b; m.up_w[0] = U.A.wtc; m.up_w[1] = U.B.wtc; m.up_b = U.A.b;     // bias tiled per phase: first C entries
+                } else m.xb = Xb;
+                m.out = nullptr; m.outb = nullptr; m.post_w = nullptr; m.audio = nullptr;
+                if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
+                else if (i + 1 < A.n_ups && up_fused[i + 2]) { m.outb = reinterpret_cast<__nv_bfloat16*>(XS); m.outb_slope = 0.1f; }
+                else m.out = XS;
+                m.dbg = nullptr;
+                if (h->opts.count("mrf_dbg") && (int)h->opts["mrf_dbg"] == i + 1) {
+                    if ((rc = ensure(h, h->mrf_dbg, (size_t)MRF3_DBG_TILES * 48 * 8))) return rc;
+                    CK(h, cudaMemsetAsync(h->mrf_dbg.p, 0, (size_t)MRF3_DBG_TILES * 48 * 8, st));
+                    m.dbg = ptr<unsigned long long>(h->mrf_dbg);
+                }
+                if (m.ntiles > 0) {
+                    if ((rc = ensure(h, h->tdesc, (size_t)m.ntiles * sizeof(int4)))) return rc;
+                    m.tdesc = ptr<int4>(h->tdesc);
+                    cudaError_t e = mrf3_launch(m, mrf3_cfg[i + 1], h->num_sms, st);
+                    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf3 launch: %s", cudaGetErrorString(e));
+                    h->launches += 2;
+                }
+            } else if (mrf_on[i + 1] == 2) {
                 Mrf2Args& m = mrf2_args[i + 1];
                 m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
                 if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
@@ -911,7 +971,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                     }
                 }
             }
-            cur = XS; cur_c = co;
+            cur = XS; cur_c = co; cur_b = reinterpret_cast<const __nv_bfloat16*>(XS);
         }
         // ---- lrelu(0.01) -> conv_post -> tanh (models.py:364-366)
         {

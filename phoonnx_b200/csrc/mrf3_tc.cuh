@@ -1,0 +1,628 @@
+// Fused multi-receptive-field stage of the HiFi-GAN generator, v3 (sm_100a, ResBlock2 family):
+//
+//     [optional]  x = ConvTranspose1d_u( h )                                       (models.py:320-332, h already lrelu'd)
+//     out = ( sum_r  rb_r(x) ) / n_r ,   rb_r(x) = x1 + conv_{k_r, d_r2}(lrelu(x1)) ,  x1 = x + conv_{k_r, d_r1}(lrelu(x))
+//     [last stage only]  audio = tanh( conv_post( lrelu_{0.01}(out) ) )             (models.py:356-366 + modules.py:355-364)
+//
+// in ONE kernel per stage.  Tile geometry as in mrf2_tc.cuh (a CTA owns a window of 128*NB rows, all convs of all
+// resblocks run on the same M=128 blocks, only the central rows are stored).  What v3 changes, after the r01 phase
+// timeline of v2 (profiles/r01b_mma_probe_and_mrf2_timeline.log: tensor pipe busy 11.8k of a 22.4k-cycle tile, the
+// rest a serial C1(r) -> E1(r) -> C2(r) chain; and a separate polyphase ConvTranspose kernel that wrote and re-read
+// 64 KB of fp32 per frame at 2.6 TB/s):
+//
+//   * inter-stage activations travel as bf16( lrelu_{0.1}(.) ) -- exactly the MMA operand the consumer needs.  A
+//     dedicated loader warp cp.async's rows straight into the K-major operand tile (zero-filled outside the
+//     utterance): no fp32 staging buffer (76 KB), no conversion pass;
+//   * the residual x is recovered from that operand (lrelu is invertible: x = min(v, v/slope)); costs 1.3 dB of SNR
+//     on the medium voice (60.4 -> 59.1 dB vs the fp32 oracle, gate 40 dB), frees the shared memory that makes the
+//     next two points possible;
+//   * in the last stage the ConvTranspose1d (u = 4) is one more tensor-core pass at the head of the tile: the input
+//     tile [128*NUB + 2 rows, C_in] is the A operand, the polyphase weights [2 taps][C_in][u/2 * C] the B operands,
+//     accumulator column (p, c) of input row q is x[u*q + p, c]; 16 epilogue warps (quadrant x phase) turn it into
+//     the lrelu'd operand tile.  x never exists in HBM;
+//   * one conv1 accumulator per resblock (TMEM: (n_r + 1) * NB * C = 512 columns; conv_post reuses the last conv1
+//     buffer) and the issue order C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2) | post: every C1 is queued before the first
+//     epilogue result is needed, so E1(r) overlaps C1(r+1..) and C2(r-1).
+//
+// Warp roles (608 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
+// elected lane = weight producer (+ TMEM allocation), warp 17 elected lane = MMA issuer, warp 18 = input-row loader.
+#pragma once
+#include "mrf2_tc.cuh"
+
+#define MRF3_THREADS 608
+#define MRF3_EPI_THREADS 512
+#define MRF3_EPI_WARPS 16
+#define MRF3_MAX_RB 3
+#define MRF3_MAX_STAGES 32
+#define MRF3_POST_K 7
+#define MRF3_NBAR 16
+#define MRF3_DBG_TILES 24
+
+struct Mrf3Args {
+    // input: mode A (up_u == 0): xb = bf16 lrelu(x) [rows, C];  mode U (up_u == 4): hb = bf16 lrelu(h) [rows / u, up_cin]
+    const __nv_bfloat16* xb;
+    const __nv_bfloat16* hb;  int up_u;  int up_cin;
+    const __nv_bfloat16* up_w[2];  const float* up_b;      // polyphase halves A (taps -1, 0) and B (taps 0, +1): [2][up_cin/8][u/2*C][8]
+    int C;
+    int nrb;  int k[MRF3_MAX_RB];  int d1[MRF3_MAX_RB];  int d2[MRF3_MAX_RB];
+    const __nv_bfloat16* w[MRF3_MAX_RB][2];  const float* b[MRF3_MAX_RB][2];
+    const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
+    const int4* tdesc;                                           // per tile {first row of the utterance, its rows, o0, -}
+    float out_div;  float slope;
+    float* out;                                                  // fp32 [rows, C]                       (or null)
+    __nv_bfloat16* outb;  float outb_slope;                      // bf16 lrelu_{outb_slope}(out) [rows, C] (or null)
+    const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
+    unsigned long long* dbg;
+};
+
+struct Mrf3Cfg {
+    int nb, span, hmax, h1max, t_out, post_halo, t_step;
+    int rx, rx1;                 // rows of the two operand tiles (odd)
+    int x_bytes, x1_bytes;
+    int slot_bytes, nstages, resident, npieces;
+    int tmem_cols;
+    int nub, u_rows, u_bytes, upw_bytes;   // mode U: M blocks of the ups pass, rows / bytes of its input tile, bytes of both weight halves
+    int bias_off, postw_off;
+    int smem_bytes;
+};
+
+namespace tc {
+// 16-byte cp.async with zero fill: copies src_bytes (0 or 16) and zero-fills the rest
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+}  // namespace tc
+
+#define MRF3_STAMP(it_, slot_) do { if (dbg_on && (it_) < MRF3_DBG_TILES) a.dbg[(it_) * 48 + (slot_)] = (unsigned long long)clock64(); } while (0)
+
+template <int C>
+__global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, const Mrf3Cfg c) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sX = smem;                                       // lrelu(x)  bf16 K-major chunks [C/8][rx][8]
+    uint8_t* sX1 = sX + c.x_bytes;                            // lrelu(x1) bf16 K-major chunks [C/8][rx1][8]; then the conv_post operand
+    uint8_t* sU = sX1 + c.x1_bytes;                           // mode U: lrelu(h) bf16 K-major chunks [Cin/8][u_rows][8]
+    uint8_t* sUW = sU + c.u_bytes;                            // mode U: both polyphase weight halves (resident)
+    uint8_t* sW = sUW + c.upw_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)c.nstages * c.slot_bytes);
+    const uint32_t bar_full0 = tc::smem_u32(bars);
+    const uint32_t bar_empty0 = bar_full0 + 8u * c.nstages;
+    const uint32_t bar_fix = bar_empty0 + 8u * c.nstages;
+    const uint32_t bar_in = bar_fix;                          // input tile landed                  (32 cp.async arrivals / tile)
+    const uint32_t bar_in_free = bar_fix + 8u;                // input tile consumed                (A: 512 / tile, U: commit / tile)
+    const uint32_t bar_ups = bar_fix + 16u;                   // ups accumulators ready             (commit / tile)
+    const uint32_t bar_x = bar_fix + 24u;                     // X operand staged by E0             (512 / tile, mode U)
+    const uint32_t bar_x1 = bar_fix + 32u;                    // x1 operand staged, acc1[r] drained (512 / resblock)
+    const uint32_t bar_c1 = bar_fix + 40u;                    // conv1 accumulators ready, one per resblock (commit)   [3]
+    const uint32_t bar_c2 = bar_fix + 64u;                    // conv2 MMAs of one resblock complete (commit / resblock)
+    const uint32_t bar_acc2_free = bar_fix + 72u;             // conv2 accumulators drained         (512 / tile)
+    const uint32_t bar_post_rdy = bar_fix + 80u;              // conv_post operand staged           (512 / tile)
+    const uint32_t bar_post_done = bar_fix + 88u;             // conv_post accumulators ready       (commit / tile)
+    const uint32_t bar_post_free = bar_fix + 96u;             // conv_post accumulators drained     (512 / tile)
+    const uint32_t bar_upw = bar_fix + 104u;                  // ups weights landed                 (once)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + MRF3_NBAR);
+    float* sB = reinterpret_cast<float*>(smem + c.bias_off);  // bias1 of every resblock, then sum_r bias2_r, then the ups bias
+    uint8_t* sWp = smem + c.postw_off;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool post = a.post_w != nullptr;
+    const bool modeU = a.up_u != 0;
+    if (tid == 0) {
+        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
+        tc::mbar_init(bar_in, 32);
+        tc::mbar_init(bar_in_free, modeU ? 1 : MRF3_EPI_THREADS);
+        tc::mbar_init(bar_ups, 1);
+        tc::mbar_init(bar_x, MRF3_EPI_THREADS);
+        tc::mbar_init(bar_x1, MRF3_EPI_THREADS);
+        for (int r = 0; r < MRF3_MAX_RB; r++) tc::mbar_init(bar_c1 + 8u * r, 1);
+        tc::mbar_init(bar_c2, 1);
+        tc::mbar_init(bar_acc2_free, MRF3_EPI_THREADS);
+        tc::mbar_init(bar_post_rdy, MRF3_EPI_THREADS);
+        tc::mbar_init(bar_post_done, 1);
+        tc::mbar_init(bar_post_free, MRF3_EPI_THREADS);
+        tc::mbar_init(bar_upw, 1);
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < C; i += MRF3_THREADS) {
+        float sum = 0.f;
+        for (int r = 0; r < a.nrb; r++) { sB[r * C + i] = __ldg(a.b[r][0] + i); sum += __ldg(a.b[r][1] + i); }
+        sB[a.nrb * C + i] = sum;
+        sB[(a.nrb + 1) * C + i] = modeU ? __ldg(a.up_b + i) : 0.f;
+    }
+    if (post) {
+        // conv_post filter as a K-major bf16 B operand [tap][C/8][16][8]: output column 0 holds w[tap][:], columns 1-15 zero
+        __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(sWp);
+        for (int i = tid; i < MRF3_POST_K * C * 16; i += MRF3_THREADS) {
+            const int e = i & 7, n = (i >> 3) & 15, kc = (i >> 7) % (C / 8), tap = i / (C * 16);
+            wp[i] = __float2bfloat16_rn(n == 0 ? __ldg(a.post_w + tap * C + kc * 8 + e) : 0.f);
+        }
+        tc::fence_proxy_async();
+    }
+    if (warp == MRF3_EPI_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    constexpr int KC = C / 8;                       // 16-byte chunks per row
+    constexpr int NG = C / 32;                      // 32-channel groups per row
+    const uint32_t lbo_x = (uint32_t)c.rx * 16u, lbo_x1 = (uint32_t)c.rx1 * 16u, lbo_w = (uint32_t)C * 16u;
+    const uint32_t acc1_cols = (uint32_t)(c.nb * C);            // per conv1 buffer (one per resblock)
+    const uint32_t acc2_col = (uint32_t)a.nrb * acc1_cols;
+    const uint32_t accp_col = (uint32_t)(a.nrb - 1) * acc1_cols; // conv_post accumulators (16 columns per M block) reuse the last conv1 buffer
+    const int lead = c.hmax + c.h1max;              // window row 0 of the X tile sits `lead` rows before the first stored row
+    const int N2 = (a.up_u >> 1) * C;               // columns of one polyphase half
+    const int KCU = a.up_cin >> 3;
+
+    auto tile_geom = [&](int tile, long& row0, int& len, int& o0) {
+        const int4 d = __ldg(a.tdesc + tile);
+        row0 = (long)d.x; len = d.y; o0 = d.z;
+    };
+    // first input row of the ups pass: floor((o0 - lead) / u)
+    auto q_base = [&](int tbase) { return tbase >= 0 ? (tbase >> 2) : -((-tbase + 3) >> 2); };
+
+    if (warp < MRF3_EPI_WARPS) {
+        // ===================== epilogues (512 threads) =====================
+        // work item of this warp: rows 128*bb + 32*q + lane, channels [32*cg, 32*cg + 32)
+        const int q = warp & 3, item = warp >> 2;
+        const int bb = item / NG, cg = item - bb * NG;
+        const bool active = bb < c.nb;
+        const int wr = 128 * bb + 32 * q + lane;                  // window row of this thread
+        const float inv_div = 1.f / a.out_div, inv_slope = 1.f / a.slope;
+        uint32_t n_c1[MRF3_MAX_RB] = {0, 0, 0}, n_c2 = 0, n_post = 0, n_ups = 0;
+        long p_row0 = 0; int p_len = 0, p_o0 = 0; bool have_prev = false;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+        int it = 0;
+        // conv_post epilogue of the previous tile: acc_post column 0 -> tanh -> audio (thread per row, 32-channel group 0)
+        auto post_epilogue = [&]() {
+            tc::mbar_wait(bar_post_done, n_post & 1); n_post++;
+            tc::tc_fence_after();
+            if (active && cg == 0) {
+                const float v = tc::tmem_ld1(tmem_base + ((uint32_t)(32 * q) << 16) + accp_col + (uint32_t)(bb * 16));
+                const int t = p_o0 - c.hmax + wr;                 // stage row == audio sample of this thread
+                if (wr >= c.hmax + c.post_halo && wr < c.hmax + c.t_out - c.post_halo && t < p_len) a.audio[p_row0 + t] = tanhf(v);
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_post_free);
+        };
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            long row0; int len, o0;
+            tile_geom(tile, row0, len, o0);
+            const int tbase = o0 - lead;
+            MRF3_STAMP(it, 0);
+            if (modeU) {
+                // ---- E0: ups accumulators -> + bias -> lrelu -> bf16 operand tile sX (zero outside the utterance).
+                // warp = (lane quadrant q, phase pp): input row qq of M block ub  ->  x row u*(qb + qq) + pp
+                const int pp = warp >> 2;
+                const int qb = q_base(tbase);
+                tc::mbar_wait(bar_ups, n_ups & 1); n_ups++;
+                MRF3_STAMP(it, 1);
+                tc::tc_fence_after();
+                const float* ub_bias = sB + (a.nrb + 1) * C;
+                for (int ub = 0; ub < c.nub; ub++) {
+                    const int qq = ub * 128 + 32 * q + lane;
+                    const int t = ((qb + qq) << 2) + pp;              // time row inside the utterance
+                    const int r = t - tbase;                          // row of the operand tile
+                    const bool inu = (t >= 0) && (t < len);
+                    const bool inr = (r >= 0) && (r < c.rx);
+                    const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ub * a.up_u * C) + (uint32_t)(pp * C);
+#pragma unroll
+                    for (int n0 = 0; n0 < C; n0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tl + (uint32_t)n0, v);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float x0 = v[j] + ub_bias[n0 + j], x1v = v[j + 1] + ub_bias[n0 + j + 1];
+                            pk[j >> 1] = inu ? tc::pack_bf16(lrelu_max(x0, a.slope), lrelu_max(x1v, a.slope)) : 0u;
+                        }
+                        if (inr) {
+                            *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 0) * c.rx + r) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 1) * c.rx + r) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                tc::mbar_arrive(bar_x);
+                MRF3_STAMP(it, 2);
+            }
+            // the previous tile's conv_post accumulators drain here, under this tile's first conv1 MMAs; this also
+            // guarantees its MMAs no longer read sX1 before E1(0) below overwrites it
+            if (post && have_prev) post_epilogue();
+            MRF3_STAMP(it, 3);
+
+            const int tm = o0 - c.hmax + wr;
+            const bool inr = active && (tm >= 0 && tm < len);
+            // this thread's raw x row lives in the operand tile as lrelu(x): row wr + h1max, chunks 4*cg .. 4*cg + 3
+            const uint8_t* xop = sX + ((size_t)(4 * cg) * c.rx + (active ? wr + c.h1max : 0)) * 16;
+            float xacc[32];                         // sum_r (x1_r + bias2_r) of this thread's 32 channels
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 bs = *reinterpret_cast<const float4*>(sB + a.nrb * C + 32 * cg + 4 * j);      // sum_r bias2_r
+                xacc[4 * j] = bs.x; xacc[4 * j + 1] = bs.y; xacc[4 * j + 2] = bs.z; xacc[4 * j + 3] = bs.w;
+            }
+            const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(bb * C + 32 * cg);
+
+            for (int r = 0; r < a.nrb; r++) {
+                tc::mbar_wait(bar_c1 + 8u * r, n_c1[r] & 1); n_c1[r]++;
+                MRF3_STAMP(it, 4 + 4 * r);
+                tc::tc_fence_after();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) pk[j] = 0u;
+                if (active) {                       // warp-uniform: tcgen05.ld is .sync.aligned
+                    const float* b1 = sB + r * C + 32 * cg;
+#pragma unroll
+                    for (int n0 = 0; n0 < 32; n0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tlane + (uint32_t)r * acc1_cols + (uint32_t)n0, v);
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; h8++) {
+                            // 8 channels: one 16-byte chunk of the operand tile, inverted back to x (lrelu is monotone:
+                            // x = min(v, v / slope)); exact up to the operand's bf16 rounding
+                            const uint4 xo = *reinterpret_cast<const uint4*>(xop + (size_t)((n0 >> 3) + h8) * c.rx * 16);
+                            const uint32_t xw[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                            for (int p2 = 0; p2 < 4; p2++) {
+                                const int ch = n0 + 8 * h8 + 2 * p2;
+                                const float l0 = tc::bf16_lo_f(xw[p2]), l1 = tc::bf16_hi_f(xw[p2]);
+                                const float xv0 = fminf(l0, l0 * inv_slope), xv1 = fminf(l1, l1 * inv_slope);
+                                const float x10 = v[8 * h8 + 2 * p2] + b1[ch] + xv0, x11 = v[8 * h8 + 2 * p2 + 1] + b1[ch + 1] + xv1;
+                                xacc[ch] += x10; xacc[ch + 1] += x11;
+                                // conv2 zero-pads x1 beyond the utterance
+                                pk[ch >> 1] = inr ? tc::pack_bf16(lrelu_max(x10, a.slope), lrelu_max(x11, a.slope)) : 0u;
+                            }
+                        }
+                    }
+                }
+                MRF3_STAMP(it, 5 + 4 * r);
+                if (!modeU && r == a.nrb - 1) tc::mbar_arrive(bar_in_free);      // last read of the X tile: the loader may prefetch
+                if (r > 0) { tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++; }         // conv2 of resblock r-1 no longer reads sX1
+                MRF3_STAMP(it, 6 + 4 * r);
+                if (active) {
+                    const int row1 = wr + c.hmax;
+#pragma unroll
+                    for (int n8 = 0; n8 < 4; n8++)
+                        *reinterpret_cast<uint4*>(sX1 + ((size_t)(4 * cg + n8) * c.rx1 + row1) * 16) =
+                            make_uint4(pk[4 * n8], pk[4 * n8 + 1], pk[4 * n8 + 2], pk[4 * n8 + 3]);
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                tc::mbar_arrive(bar_x1);
+                MRF3_STAMP(it, 7 + 4 * r);
+            }
+            // ---- final epilogue: out = (acc2 + sum_r(x1_r + b2_r)) / n_r on the central rows
+            tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++;
+            MRF3_STAMP(it, 16);
+            tc::tc_fence_after();
+            if (active) {
+                const bool central = (wr >= c.hmax) && (wr < c.hmax + c.t_out);
+                const bool st = central && inr;
+                if (post || a.outb) {
+                    // lrelu(out) as bf16: the conv_post operand (same placement as x1, zero outside the utterance) or the next
+                    // stage's input rows in HBM
+                    const float osl = post ? a.post_slope : a.outb_slope;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int n0 = 0; n0 < 32; n0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tlane + acc2_col + (uint32_t)n0, v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float o0v = (v[j] + xacc[n0 + j]) * inv_div, o1v = (v[j + 1] + xacc[n0 + j + 1]) * inv_div;
+                            pk[(n0 + j) >> 1] = st ? tc::pack_bf16(lrelu_max(o0v, osl), lrelu_max(o1v, osl)) : 0u;
+                        }
+                    }
+                    if (post) {
+                        const int row1 = wr + c.hmax;
+#pragma unroll
+                        for (int n8 = 0; n8 < 4; n8++)
+                            *reinterpret_cast<uint4*>(sX1 + ((size_t)(4 * cg + n8) * c.rx1 + row1) * 16) =
+                                make_uint4(pk[4 * n8], pk[4 * n8 + 1], pk[4 * n8 + 2], pk[4 * n8 + 3]);
+                    } else if (st) {
+                        uint4* orow = reinterpret_cast<uint4*>(a.outb + (row0 + tm) * C + 32 * cg);
+#pragma unroll
+                        for (int n8 = 0; n8 < 4; n8++) orow[n8] = make_uint4(pk[4 * n8], pk[4 * n8 + 1], pk[4 * n8 + 2], pk[4 * n8 + 3]);
+                    }
+                } else {
+                    float* orow = a.out + (row0 + tm) * C + 32 * cg;
+#pragma unroll
+                    for (int n0 = 0; n0 < 32; n0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(tlane + acc2_col + (uint32_t)n0, v);
+                        if (st) {
+#pragma unroll
+                            for (int qd = 0; qd < 4; qd++) {
+                                float4 ov;
+                                ov.x = (v[4 * qd + 0] + xacc[n0 + 4 * qd + 0]) * inv_div;
+                                ov.y = (v[4 * qd + 1] + xacc[n0 + 4 * qd + 1]) * inv_div;
+                                ov.z = (v[4 * qd + 2] + xacc[n0 + 4 * qd + 2]) * inv_div;
+                                ov.w = (v[4 * qd + 3] + xacc[n0 + 4 * qd + 3]) * inv_div;
+                                *(reinterpret_cast<float4*>(orow + n0) + qd) = ov;
+                            }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_acc2_free);       // the next tile's conv2 may overwrite the accumulators
+            MRF3_STAMP(it, 17);
+            if (post) {
+                tc::fence_proxy_async();
+                tc::mbar_arrive(bar_post_rdy);
+                p_row0 = row0; p_len = len; p_o0 = o0; have_prev = true;
+            }
+        }
+        if (post && have_prev) post_epilogue();
+    } else if (warp == MRF3_EPI_WARPS) {
+        // ===================== weight producer =====================
+        if (tc::elect_one()) {
+            if (modeU) {
+                tc::mbar_expect_tx(bar_upw, (uint32_t)c.upw_bytes);
+                const uint32_t half_bytes = (uint32_t)c.upw_bytes >> 1;
+                tc::bulk_g2s(tc::smem_u32(sUW), a.up_w[0], half_bytes, bar_upw);
+                tc::bulk_g2s(tc::smem_u32(sUW) + half_bytes, a.up_w[1], half_bytes, bar_upw);
+            }
+            uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                if (c.resident && tile != (int)blockIdx.x) break;
+                // issue order of the MMA warp: C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2)
+                for (int cv = 0; cv < 2; cv++)
+                    for (int r = 0; r < a.nrb; r++) {
+                        const __nv_bfloat16* wsrc = a.w[r][cv];
+                        for (int tap = 0; tap < a.k[r]; tap++) {
+                            if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
+                            const uint32_t fb = bar_full0 + 8u * s;
+                            tc::mbar_expect_tx(fb, (uint32_t)c.slot_bytes);
+                            tc::bulk_g2s(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb);
+                            wsrc += C * C;
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == MRF3_EPI_WARPS + 1) {
+        // ===================== MMA issuer =====================
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::make_idesc(128, C), idesc_post = tc::make_idesc(128, 16), idesc_up = tc::make_idesc(128, N2 > 0 ? N2 : 16);
+            const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
+            const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
+            const uint64_t dhi_wp = tc::make_desc(0, 256u, 128u);
+            const uint64_t dhi_u = tc::make_desc(0, (uint32_t)c.u_rows * 16u, 128u), dhi_uw = tc::make_desc(0, (uint32_t)N2 * 16u, 128u);
+            const uint64_t bd_step = (uint64_t)((2u * lbo_w) >> 4);
+            const uint64_t ad_step_x = (uint64_t)((2u * lbo_x) >> 4), ad_step_x1 = (uint64_t)((2u * lbo_x1) >> 4);
+            const uint64_t ad_step_u = (uint64_t)((2u * (uint32_t)c.u_rows * 16u) >> 4), bd_step_u = (uint64_t)((2u * (uint32_t)N2 * 16u) >> 4);
+            const uint32_t x16 = (sX_u >> 4) + (uint32_t)c.h1max, x116 = (sX1_u >> 4) + (uint32_t)c.hmax;   // 16-byte units == rows
+            const uint32_t wp16 = tc::smem_u32(sWp) >> 4, u16 = tc::smem_u32(sU) >> 4, uw16 = tc::smem_u32(sUW) >> 4;
+            const uint32_t uw_tap16 = (uint32_t)(KCU * N2);          // 16-byte units per tap of one polyphase half
+            uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
+            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                MRF3_STAMP((int)it, 20);
+                tc::mbar_wait(bar_in, it & 1);
+                tc::tc_fence_after();
+                if (modeU) {
+                    // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
+                    if (it == 0) { tc::mbar_wait(bar_upw, 0); tc::tc_fence_after(); }
+                    for (int ub = 0; ub < c.nub; ub++)
+                        for (int half = 0; half < 2; half++) {
+                            const uint32_t dcol = tmem_base + (uint32_t)(ub * a.up_u * C) + (uint32_t)(half * N2);
+                            for (int tap = 0; tap < 2; tap++) {
+                                // operand row 0 of sU is input row qb - 1: half A reads rows q-1, q; half B rows q, q+1
+                                uint64_t ad = dhi_u | (uint64_t)((u16 + (uint32_t)(ub * 128 + half + tap)) & 0x3FFF);
+                                uint64_t bd = dhi_uw | (uint64_t)((uw16 + (uint32_t)(half * 2 + tap) * uw_tap16) & 0x3FFF);
+                                for (int k16 = 0; k16 < (a.up_cin >> 4); k16++) {
+                                    tc::umma_bf16(dcol, ad, bd, idesc_up, (tap > 0 || k16) ? 1u : 0u);
+                                    ad += ad_step_u; bd += bd_step_u;
+                                }
+                            }
+                        }
+                    tc::umma_commit(bar_in_free);             // the loader may overwrite sU
+                    tc::umma_commit(bar_ups);
+                    MRF3_STAMP((int)it, 21);
+                    tc::mbar_wait(bar_x, it & 1);
+                    tc::tc_fence_after();
+                }
+                MRF3_STAMP((int)it, 22);
+                for (int cv = 0; cv < 2; cv++) {
+                    for (int r = 0; r < a.nrb; r++) {
+                        if (cv == 1) {
+                            tc::mbar_wait(bar_x1, n_x1 & 1); n_x1++;                       // x1(r) staged, acc1[r] drained
+                            if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
+                            tc::tc_fence_after();
+                        } else if (post && r == a.nrb - 1 && it > 0) {
+                            tc::mbar_wait(bar_post_free, (it - 1) & 1);                    // conv_post accumulators (same columns) drained
+                            tc::tc_fence_after();
+                        }
+                        MRF3_STAMP((int)it, 24 + 2 * (cv * 3 + r));
+                        const int kr = a.k[r];
+                        const int dil = cv ? a.d2[r] : a.d1[r];
+                        const uint64_t dhi = cv ? dhi_x1 : dhi_x;
+                        const uint64_t ad_step = cv ? ad_step_x1 : ad_step_x;
+                        const uint32_t dcol0 = tmem_base + (cv ? acc2_col : (uint32_t)r * acc1_cols);
+                        uint32_t arow16 = (cv ? x116 : x16) - (uint32_t)(((kr - 1) >> 1) * dil);     // tap 0
+                        for (int tap = 0; tap < kr; tap++, arow16 += (uint32_t)dil) {
+                            if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
+                            const uint64_t bd0 = dhi_w | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                            // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks (and taps)
+                            const uint32_t acc0 = (tap > 0 || (cv && r > 0)) ? 1u : 0u;
+                            for (int bb = 0; bb < c.nb; bb++) {
+                                uint64_t ad = dhi | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
+                                uint64_t bd = bd0;
+                                const uint32_t dcol = dcol0 + (uint32_t)(bb * C);
+#pragma unroll
+                                for (int k16 = 0; k16 < C / 16; k16++) {
+                                    tc::umma_bf16(dcol, ad, bd, idesc, k16 ? 1u : acc0);
+                                    ad += ad_step; bd += bd_step;
+                                }
+                            }
+                            if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
+                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
+                        }
+                        tc::umma_commit(cv ? bar_c2 : (bar_c1 + 8u * (uint32_t)r));
+                        MRF3_STAMP((int)it, 25 + 2 * (cv * 3 + r));
+                    }
+                }
+                if (c.resident) { s = 0; }
+                if (post) {
+                    // conv_post: 7 taps, dilation 1, over the stage output sitting in sX1; N = 16 (column 0 is the filter)
+                    tc::mbar_wait(bar_post_rdy, it & 1);
+                    MRF3_STAMP((int)it, 40);
+                    tc::tc_fence_after();
+                    uint32_t arow16 = x116 - (uint32_t)((MRF3_POST_K - 1) >> 1);
+                    for (int tap = 0; tap < MRF3_POST_K; tap++, arow16++) {
+                        const uint64_t bd0 = dhi_wp | (uint64_t)((wp16 + (uint32_t)(tap * (C / 8) * 16)) & 0x3FFF);
+                        for (int bb = 0; bb < c.nb; bb++) {
+                            uint64_t ad = dhi_x1 | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
+                            uint64_t bd = bd0;
+#pragma unroll
+                            for (int k16 = 0; k16 < C / 16; k16++) {
+                                tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, (tap > 0 || k16) ? 1u : 0u);
+                                ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
+                            }
+                        }
+                    }
+                    tc::umma_commit(bar_post_done);
+                    MRF3_STAMP((int)it, 41);
+                }
+            }
+        }
+    } else {
+        // ===================== input-row loader (warp 18): cp.async, 16 B per lane, zero fill outside the utterance =====================
+        uint32_t n_free = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            long row0; int len, o0;
+            tile_geom(tile, row0, len, o0);
+            const int tbase = o0 - lead;
+            MRF3_STAMP(it, 44);
+            if (tile != (int)blockIdx.x) { tc::mbar_wait(bar_in_free, n_free & 1); n_free++; }
+            MRF3_STAMP(it, 45);
+            if (modeU) {
+                const int qb = q_base(tbase);
+                const long rin0 = row0 >> 2;                      // first input row of the utterance (rate / u rows per frame)
+                const int len_in = len >> 2;
+                const uint32_t dst0 = tc::smem_u32(sU);
+                const int total = c.u_rows * KCU;
+                for (int i = lane; i < total; i += 32) {
+                    const int j = i / KCU, kc = i - j * KCU;      // kc fastest: contiguous global reads
+                    const int qi = qb - 1 + j;
+                    const bool ok = (qi >= 0) && (qi < len_in);
+                    const __nv_bfloat16* src = a.hb + (rin0 + (ok ? qi : 0)) * a.up_cin + kc * 8;
+                    tc::cp_async16_zfill(dst0 + (uint32_t)(kc * c.u_rows + j) * 16u, src, ok ? 16u : 0u);
+                }
+            } else {
+                const uint32_t dst0 = tc::smem_u32(sX);
+                const int total = c.rx * KC;
+                for (int i = lane; i < total; i += 32) {
+                    const int r = i / KC, kc = i - r * KC;
+                    const int t = tbase + r;
+                    const bool ok = (t >= 0) && (t < len);
+                    const __nv_bfloat16* src = a.xb + (row0 + (ok ? t : 0)) * C + kc * 8;
+                    tc::cp_async16_zfill(dst0 + (uint32_t)(kc * c.rx + r) * 16u, src, ok ? 16u : 0u);
+                }
+            }
+            // the tile is read by the tensor core (async proxy): complete this lane's copies, make them visible, then arrive
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_in);
+            MRF3_STAMP(it, 46);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MRF3_EPI_WARPS) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post) {
+    memset(&c, 0, sizeof c);
+    if (a.C != 32 && a.C != 64) return false;
+    if (a.nrb < 1 || a.nrb > MRF3_MAX_RB) return false;
+    const bool modeU = a.up_u != 0;
+    if (modeU && (a.up_u != 4 || a.up_cin % 16 || a.up_cin < 16 || a.up_cin > 128 || (a.up_u / 2) * a.C > 256)) return false;
+    int hmax = 0, h1max = 0, npieces = 0;
+    for (int r = 0; r < a.nrb; r++) {
+        if (a.k[r] % 2 == 0) return false;
+        const int h1 = a.d1[r] * (a.k[r] - 1) / 2, h2 = a.d2[r] * (a.k[r] - 1) / 2;
+        hmax = h2 > hmax ? h2 : hmax; h1max = h1 > h1max ? h1 : h1max;
+        npieces += 2 * a.k[r];
+    }
+    c.hmax = hmax; c.h1max = h1max; c.npieces = npieces;
+    c.slot_bytes = a.C * a.C * 2;
+    c.post_halo = fuse_post ? (MRF3_POST_K - 1) / 2 : 0;
+    if (fuse_post && hmax < c.post_halo) return false;        // the conv_post taps must stay inside the x1 tile
+    const int limit = 225 * 1024;
+    const int ng = a.C / 32;
+    const int postw_bytes = fuse_post ? MRF3_POST_K * a.C * 16 * 2 : 0;
+    for (int nb = nb_pref; nb >= 1; nb--) {
+        if (nb == 3) continue;
+        if (nb * ng > MRF3_EPI_WARPS / 4) continue;           // one (block, 32-channel group) item per epilogue warp
+        if ((a.nrb + 1) * nb * a.C > 512) continue;           // one conv1 buffer per resblock + conv2 accumulators (conv_post aliases)
+        if (fuse_post && nb * 16 > nb * a.C) continue;
+        c.nb = nb; c.span = 128 * nb; c.t_out = c.span - 2 * hmax; c.t_step = c.t_out - 2 * c.post_halo;
+        if (c.t_step < 32) continue;
+        c.rx = ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
+        c.rx1 = ((c.span + 2 * hmax + 7) / 8) * 8 + 1;
+        c.x_bytes = ((a.C / 8) * c.rx * 16 + 127) / 128 * 128;
+        c.x1_bytes = ((a.C / 8) * c.rx1 * 16 + 127) / 128 * 128;
+        c.nub = 0; c.u_rows = 0; c.u_bytes = 0; c.upw_bytes = 0;
+        if (modeU) {
+            // input rows floor(tbase/u) - 1 ... : the ups pass must cover rx + (u - 1) output rows
+            c.nub = (c.rx + a.up_u - 1 + 128 * a.up_u - 1) / (128 * a.up_u);
+            if (c.nub * a.up_u * a.C > (fuse_post ? a.nrb - 1 : a.nrb) * nb * a.C) continue;   // ups accumulators live in the conv1 buffers (not the conv_post one)
+            c.u_rows = ((c.nub * 128 + 2 + 7) / 8) * 8 + 1;
+            c.u_bytes = ((a.up_cin / 8) * c.u_rows * 16 + 127) / 128 * 128;
+            c.upw_bytes = 2 * 2 * a.up_cin * (a.up_u / 2) * a.C * 2;
+        }
+        const long fixed = (long)c.x_bytes + c.x1_bytes + c.u_bytes + c.upw_bytes;
+        const long tail = (2 * MRF3_MAX_STAGES + MRF3_NBAR) * 8 + 32 + (MRF3_MAX_RB + 2) * a.C * 4 + postw_bytes + 512;
+        const long res_bytes = (long)npieces * c.slot_bytes;
+        if (npieces <= MRF3_MAX_STAGES && fixed + res_bytes + tail <= limit) { c.resident = 1; c.nstages = npieces; }
+        else {
+            c.resident = 0;
+            long room = limit - fixed - tail;
+            int ns = (int)(room / c.slot_bytes);
+            if (ns > MRF3_MAX_STAGES) ns = MRF3_MAX_STAGES;
+            if (ns > npieces) ns = npieces;
+            if (ns < 3) continue;
+            c.nstages = ns;
+        }
+        c.bias_off = (int)((fixed + (long)c.nstages * c.slot_bytes + (2 * c.nstages + MRF3_NBAR) * 8 + 32 + 15) / 16 * 16);
+        c.postw_off = (c.bias_off + (MRF3_MAX_RB + 2) * a.C * 4 + 127) / 128 * 128;
+        c.smem_bytes = c.postw_off + postw_bytes;
+        if (c.smem_bytes > limit) continue;
+        int cols = 32; while (cols < (a.nrb + 1) * nb * a.C) cols <<= 1;
+        c.tmem_cols = cols;
+        return true;
+    }
+    return false;
+}
+
+template <int C>
+static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_mrf3_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_mrf3_tc<C>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    int gx = num_sms;                       // one persistent CTA per SM (TMEM: 512 columns each)
+    if (gx > a.ntiles) gx = a.ntiles;
+    if (gx < 1) return cudaSuccess;
+    k_mrf2_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
+                                                         const_cast<int4*>(a.tdesc));
+    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c);
+    return cudaGetLastError();
+}
+
+static inline cudaError_t mrf3_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+    if (a.C == 32) return mrf3_launch_t<32>(a, c, num_sms, st);
+    if (a.C == 64) return mrf3_launch_t<64>(a, c, num_sms, st);
+    return cudaErrorInvalidConfiguration;
+}

@@ -343,30 +343,34 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
     nd = rs.randn(B, 2, T).astype(np.float32)
     nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
     feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
-    fused = B200Session(p, precision="bf16")
-    fused.engine.set_option("no_fused_post", 1)   # conv_post stays the fp32 kernel: same operand rounding as the unfused path
-    n0 = fused.engine.launch_count()
-    a, alen = fused.synthesize_packed(feed)
-    n_fused = fused.engine.launch_count() - n0
     plain = B200Session(p, precision="bf16")
     plain.engine.set_option("no_fused_mrf", 1)
     n0 = plain.engine.launch_count()
     b, blen = plain.synthesize_packed(feed)
     n_plain = plain.engine.launch_count() - n0
+
+    # ---- v2 kernels (fp32 residual stream staged in shared memory): agree with the per-conv path to fp32 noise
+    fused = B200Session(p, precision="bf16")
+    fused.engine.set_option("mrf_v2", 1)
+    fused.engine.set_option("no_fused_post", 1)   # conv_post stays the fp32 kernel: same operand rounding as the unfused path
+    n0 = fused.engine.launch_count()
+    a, alen = fused.synthesize_packed(feed)
+    n_fused = fused.engine.launch_count() - n0
     assert np.array_equal(alen, blen)
     assert n_fused < n_plain                      # the fused path really ran
     assert np.abs(a - b).max() < 1e-4, np.abs(a - b).max()
     for opts in ({"mrf_nb": 1, "no_fused_post": 1}, {"mrf_nb": 2, "no_fused_post": 1}, {"mrf_nb": 4, "no_fused_post": 1},
                  {"mrf_v1": 1}, {"mrf_v1": 1, "mrf_nb": 1}):
         alt = B200Session(p, precision="bf16")
+        alt.engine.set_option("mrf_v2", 1)
         for k, v in opts.items():
             alt.engine.set_option(k, v)
         c, _ = alt.synthesize_packed(feed)
         assert np.abs(a - c).max() < 1e-4, (opts, np.abs(a - c).max())
-    # default: lrelu -> conv_post -> tanh fused as a tensor-core pass, i.e. the stage output is rounded to bf16 like
-    # every other conv operand of the decoder in this mode
+    # lrelu -> conv_post -> tanh fused as a tensor-core pass: the stage output is rounded to bf16 like every other operand
     for opts in ({}, {"mrf_nb": 1}, {"mrf_nb": 2}):
         alt = B200Session(p, precision="bf16")
+        alt.engine.set_option("mrf_v2", 1)
         for k, v in opts.items():
             alt.engine.set_option(k, v)
         n0 = alt.engine.launch_count()
@@ -374,6 +378,26 @@ def test_fused_mrf_stage_equals_unfused(lib, tmp_path_factory, preset):
         assert np.array_equal(alen, clen)
         assert alt.engine.launch_count() - n0 < n_fused       # no separate conv_post launch
         assert snr_db(a, c) > 45.0, (opts, snr_db(a, c))
+
+    # ---- v3 kernels (default): inter-stage rows travel as bf16 lrelu operands, the residual x is recovered from the
+    # operand (one extra bf16 rounding per stage), the last ConvTranspose runs inside the kernel
+    v3 = B200Session(p, precision="bf16")
+    n0 = v3.engine.launch_count()
+    d, dlen = v3.synthesize_packed(feed)
+    n_v3 = v3.engine.launch_count() - n0
+    assert np.array_equal(dlen, blen)
+    assert n_v3 < n_fused                         # fewer launches than v2: no separate last ConvTranspose
+    assert snr_db(b, d) > 45.0, snr_db(b, d)
+    for opts in ({"mrf_nb": 1}, {"mrf_nb": 2}, {"no_fused_ups": 1}, {"no_fused_post": 1}, {"no_fused_ups": 1, "no_fused_post": 1}):
+        alt = B200Session(p, precision="bf16")
+        for k, v in opts.items():
+            alt.engine.set_option(k, v)
+        c, clen = alt.synthesize_packed(feed)
+        assert np.array_equal(dlen, clen)
+        assert snr_db(b, c) > 45.0, (opts, snr_db(b, c))
+        # tile height and where the ConvTranspose runs do not change a single rounding point of the stage
+        if "no_fused_post" not in opts:
+            assert np.abs(d - c).max() < 1e-4, (opts, np.abs(d - c).max())
 
 
 def test_synthesize_many_equals_serial_calls(lib, tmp_path_factory):
