@@ -24,12 +24,17 @@
 //     buffer) and the issue order C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2) | post: every C1 is queued before the first
 //     epilogue result is needed, so E1(r) overlaps C1(r+1..) and C2(r-1).
 //
-// Warp roles (608 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
-// elected lane = weight producer (+ TMEM allocation), warp 17 elected lane = MMA issuer, warp 18 = input-row loader.
+//   * two MMA-issuing warps, each owning half of the M blocks (distinct accumulators, so the result does not depend on
+//     how their instructions interleave): one thread's descriptor set-up (R2UR moves, uniform adds) does not overlap
+//     the execution of its own MMAs -- measured 60-75 cycles per N=32 MMA issued against 40 executed -- but it does
+//     overlap the other warp's.
+//
+// Warp roles (640 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
+// elected lane = weight producer (+ TMEM allocation), warps 17 and 19 elected lane = MMA issuers, warp 18 = input-row loader.
 #pragma once
 #include "mrf2_tc.cuh"
 
-#define MRF3_THREADS 608
+#define MRF3_THREADS 640
 #define MRF3_EPI_THREADS 512
 #define MRF3_EPI_WARPS 16
 #define MRF3_MAX_RB 3
@@ -61,6 +66,7 @@ struct Mrf3Cfg {
     int x_bytes, x1_bytes;
     int slot_bytes, nstages, resident, npieces;
     int tmem_cols;
+    int nmw;                     // MMA-issuing warps (2 when the M blocks split evenly)
     int nub, u_rows, u_bytes, upw_bytes;   // mode U: M blocks of the ups pass, rows / bytes of its input tile, bytes of both weight halves
     int bias_off, postw_off;
     int smem_bytes;
@@ -107,17 +113,18 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     const bool post = a.post_w != nullptr;
     const bool modeU = a.up_u != 0;
     if (tid == 0) {
-        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
+        const uint32_t nmw = (uint32_t)c.nmw;           // every commit-tracked barrier gets one arrival per MMA warp
+        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, nmw); }
         tc::mbar_init(bar_in, 32);
-        tc::mbar_init(bar_in_free, modeU ? 1 : MRF3_EPI_THREADS);
-        tc::mbar_init(bar_ups, 1);
+        tc::mbar_init(bar_in_free, modeU ? nmw : MRF3_EPI_THREADS);
+        tc::mbar_init(bar_ups, nmw);
         tc::mbar_init(bar_x, MRF3_EPI_THREADS);
         tc::mbar_init(bar_x1, MRF3_EPI_THREADS);
-        for (int r = 0; r < MRF3_MAX_RB; r++) tc::mbar_init(bar_c1 + 8u * r, 1);
-        tc::mbar_init(bar_c2, 1);
+        for (int r = 0; r < MRF3_MAX_RB; r++) tc::mbar_init(bar_c1 + 8u * r, nmw);
+        tc::mbar_init(bar_c2, nmw);
         tc::mbar_init(bar_acc2_free, MRF3_EPI_THREADS);
         tc::mbar_init(bar_post_rdy, MRF3_EPI_THREADS);
-        tc::mbar_init(bar_post_done, 1);
+        tc::mbar_init(bar_post_done, nmw);
         tc::mbar_init(bar_post_free, MRF3_EPI_THREADS);
         tc::mbar_init(bar_upw, 1);
         tc::fence_mbar_init();
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     const int r = t - tbase;                          // row of the operand tile
                     const bool inu = (t >= 0) && (t < len);
                     const bool inr = (r >= 0) && (r < c.rx);
+                    if (__all_sync(0xffffffffu, !inr)) continue;       // e.g. the tail of the last M block: nothing of this warp lands in the tile
                     const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ub * a.up_u * C) + (uint32_t)(pp * C);
 #pragma unroll
                     for (int n0 = 0; n0 < C; n0 += 16) {
@@ -381,9 +389,12 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     }
             }
         }
-    } else if (warp == MRF3_EPI_WARPS + 1) {
-        // ===================== MMA issuer =====================
-        if (tc::elect_one()) {
+    } else if (warp == MRF3_EPI_WARPS + 1 || warp == MRF3_EPI_WARPS + 3) {
+        // ===================== MMA issuers: warp mw owns M blocks [bb_lo, bb_hi) =====================
+        const int mw = (warp == MRF3_EPI_WARPS + 3) ? 1 : 0;
+        const int bb_lo = mw * (c.nb / c.nmw), bb_hi = bb_lo + c.nb / c.nmw;
+        const int ub_lo = (c.nmw == 2 && c.nub == 2) ? mw : 0, ub_hi = (c.nmw == 2 && c.nub == 2) ? mw + 1 : (mw == 0 ? c.nub : 0);
+        if (mw < c.nmw && tc::elect_one()) {
             const uint32_t idesc = tc::make_idesc(128, C), idesc_post = tc::make_idesc(128, 16), idesc_up = tc::make_idesc(128, N2 > 0 ? N2 : 16);
             const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             const uint32_t wp16 = tc::smem_u32(sWp) >> 4, u16 = tc::smem_u32(sU) >> 4, uw16 = tc::smem_u32(sUW) >> 4;
             const uint32_t uw_tap16 = (uint32_t)(KCU * N2);          // 16-byte units per tap of one polyphase half
             uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
-            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
+            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && mw == 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
                 MRF3_STAMP((int)it, 20);
                 tc::mbar_wait(bar_in, it & 1);
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 if (modeU) {
                     // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
                     if (it == 0) { tc::mbar_wait(bar_upw, 0); tc::tc_fence_after(); }
-                    for (int ub = 0; ub < c.nub; ub++)
+                    for (int ub = ub_lo; ub < ub_hi; ub++)
                         for (int half = 0; half < 2; half++) {
                             const uint32_t dcol = tmem_base + (uint32_t)(ub * a.up_u * C) + (uint32_t)(half * N2);
                             for (int tap = 0; tap < 2; tap++) {
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                             const uint64_t bd0 = dhi_w | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
                             // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks (and taps)
                             const uint32_t acc0 = (tap > 0 || (cv && r > 0)) ? 1u : 0u;
-                            for (int bb = 0; bb < c.nb; bb++) {
+                            for (int bb = bb_lo; bb < bb_hi; bb++) {
                                 uint64_t ad = dhi | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
                                 uint64_t bd = bd0;
                                 const uint32_t dcol = dcol0 + (uint32_t)(bb * C);
@@ -472,7 +483,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     uint32_t arow16 = x116 - (uint32_t)((MRF3_POST_K - 1) >> 1);
                     for (int tap = 0; tap < MRF3_POST_K; tap++, arow16++) {
                         const uint64_t bd0 = dhi_wp | (uint64_t)((wp16 + (uint32_t)(tap * (C / 8) * 16)) & 0x3FFF);
-                        for (int bb = 0; bb < c.nb; bb++) {
+                        for (int bb = bb_lo; bb < bb_hi; bb++) {
                             uint64_t ad = dhi_x1 | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
                             uint64_t bd = bd0;
 #pragma unroll
@@ -561,7 +572,7 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
         if (nb * ng > MRF3_EPI_WARPS / 4) continue;           // one (block, 32-channel group) item per epilogue warp
         if ((a.nrb + 1) * nb * a.C > 512) continue;           // one conv1 buffer per resblock + conv2 accumulators (conv_post aliases)
         if (fuse_post && nb * 16 > nb * a.C) continue;
-        c.nb = nb; c.span = 128 * nb; c.t_out = c.span - 2 * hmax; c.t_step = c.t_out - 2 * c.post_halo;
+        c.nb = nb; c.nmw = (nb % 2 == 0) ? 2 : 1; c.span = 128 * nb; c.t_out = c.span - 2 * hmax; c.t_step = c.t_out - 2 * c.post_halo;
         if (c.t_step < 32) continue;
         c.rx = ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
         c.rx1 = ((c.span + 2 * hmax + 7) / 8) * 8 + 1;

@@ -41,14 +41,14 @@ def timeline(sess, stage, arch):
     n = eng.lib.vits_fetch(eng._h, b"mrf_dbg", buf.ctypes.data_as(C.c_void_p), buf.size)
     st = buf.view(np.uint64).reshape(24, 48).astype(np.int64)
     t0 = st[0, 0]
-    names = {0: "E top", 1: "E xf landed", 2: "E X staged", 3: "E post(prev) done", 16: "E c2 final done", 17: "E final epi done",
-             20: "M top", 21: "M X ready", 40: "M post rdy", 41: "M post issued", 44: "L top", 45: "L xf free", 46: "L issued"}
+    names = {0: "E top", 1: "E ups acc ready", 2: "E X staged (E0)", 3: "E post(prev) done", 16: "E c2 final done", 17: "E final epi done",
+             20: "M top", 21: "M ups issued", 22: "M X ready", 40: "M post rdy", 41: "M post issued", 44: "L top", 45: "L in free", 46: "L landed"}
     for r in range(3):
         names[4 + 4 * r] = f"E c1({r}) done"; names[5 + 4 * r] = f"E E1({r}) math done"
         names[6 + 4 * r] = f"E c2({r - 1}) done"; names[7 + 4 * r] = f"E x1({r}) staged"
-    for step in range(4):
-        for cv in range(2):
-            names[22 + 2 * (2 * step + cv)] = f"M start C{cv + 1}({step - cv})"; names[23 + 2 * (2 * step + cv)] = f"M issued C{cv + 1}({step - cv})"
+    for cv in range(2):
+        for r in range(3):
+            names[24 + 2 * (cv * 3 + r)] = f"M start C{cv + 1}({r})"; names[25 + 2 * (cv * 3 + r)] = f"M issued C{cv + 1}({r})"
     print(f"--- stage {stage} timeline (cycles rel. to tile 0 start), fetched {n}")
     for it in (1, 2, 5, 6):
         ev = sorted((int(st[it, s]) - int(t0), names.get(s, str(s))) for s in range(48) if st[it, s])
@@ -66,7 +66,8 @@ def main():
     path = os.path.join(tmp, "m.onnx")
     _, arch = modelgen.make_voice(path, "medium", n_speakers=1, seed=1234)
     sess = B200Session(path, precision="bf16")
-    probe(sess)
+    if '--probe' in sys.argv:
+        probe(sess)
     timeline(sess, 3, arch)
     timeline(sess, 2, arch)
 
