@@ -68,7 +68,7 @@ struct Mrf3Cfg {
     int tmem_cols;
     int nmw;                     // MMA-issuing warps (2 when the M blocks split evenly)
     int nub, u_rows, u_bytes, upw_bytes;   // mode U: M blocks of the ups pass, rows / bytes of its input tile, bytes of both weight halves
-    int bias_off, postw_off;
+    int bias_off, postw_off, sp_off;   // sp: per-row per-tap partial sums of conv_post, [span + 8][MRF3_SP_PITCH] floats
     int smem_bytes;
 };
 
@@ -77,8 +77,17 @@ namespace tc {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
 }  // namespace tc
 
+#define MRF3_SP_PITCH 9
 #define MRF3_STAMP(it_, slot_) do { if (dbg_on && (it_) < MRF3_DBG_TILES) a.dbg[(it_) * 48 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
 template <int C>
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + MRF3_NBAR);
     float* sB = reinterpret_cast<float*>(smem + c.bias_off);  // bias1 of every resblock, then sum_r bias2_r, then the ups bias
     uint8_t* sWp = smem + c.postw_off;
+    float* sP = reinterpret_cast<float*>(smem + c.sp_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool post = a.post_w != nullptr;
@@ -136,11 +146,13 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         sB[(a.nrb + 1) * C + i] = modeU ? __ldg(a.up_b + i) : 0.f;
     }
     if (post) {
-        // conv_post filter as a K-major bf16 B operand [tap][C/8][16][8]: output column 0 holds w[tap][:], columns 1-15 zero
+        // conv_post as ONE tap-0 GEMM with the 7 filter taps as output columns: P[t][j] = sum_c w[j][c] * y[t][c]
+        // (K-major bf16 B operand [C/8][16][8], columns 7-15 zero); the epilogue then adds P[t + j - 3][j] over j.
+        // 8 MMAs per tile instead of 56 -- an N=16 MMA costs as much as an N=32 one (the A operand read bounds both)
         __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(sWp);
-        for (int i = tid; i < MRF3_POST_K * C * 16; i += MRF3_THREADS) {
-            const int e = i & 7, n = (i >> 3) & 15, kc = (i >> 7) % (C / 8), tap = i / (C * 16);
-            wp[i] = __float2bfloat16_rn(n == 0 ? __ldg(a.post_w + tap * C + kc * 8 + e) : 0.f);
+        for (int i = tid; i < C * 16; i += MRF3_THREADS) {
+            const int e = i & 7, n = (i >> 3) & 15, kc = i >> 7;
+            wp[i] = __float2bfloat16_rn(n < MRF3_POST_K ? __ldg(a.post_w + n * C + kc * 8 + e) : 0.f);
         }
         tc::fence_proxy_async();
     }
@@ -184,56 +196,75 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             tc::mbar_wait(bar_post_done, n_post & 1); n_post++;
             tc::tc_fence_after();
             if (active && cg == 0) {
-                const float v = tc::tmem_ld1(tmem_base + ((uint32_t)(32 * q) << 16) + accp_col + (uint32_t)(bb * 16));
-                const int t = p_o0 - c.hmax + wr;                 // stage row == audio sample of this thread
-                if (wr >= c.hmax + c.post_halo && wr < c.hmax + c.t_out - c.post_halo && t < p_len) a.audio[p_row0 + t] = tanhf(v);
+                float p8[8];
+                tc::tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + accp_col + (uint32_t)(bb * 16), p8);
+                float* dstp = sP + (wr + 3) * MRF3_SP_PITCH;      // row wr of the window at index wr + 3
+#pragma unroll
+                for (int j = 0; j < MRF3_POST_K; j++) dstp[j] = p8[j];
             }
             tc::tc_fence_before();
             tc::mbar_arrive(bar_post_free);
+            asm volatile("bar.sync 1, %0;" ::"n"(MRF3_EPI_THREADS) : "memory");      // the 16 epilogue warps only
+            if (active && cg == 0) {
+                const int t = p_o0 - c.hmax + wr;                 // stage row == audio sample of this thread
+                if (wr >= c.hmax + c.post_halo && wr < c.hmax + c.t_out - c.post_halo && t < p_len) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int j = 0; j < MRF3_POST_K; j++) v += sP[(wr + j) * MRF3_SP_PITCH + j];     // P[wr + j - 3][j]
+                    a.audio[p_row0 + t] = tanhf(v);
+                }
+            }
         };
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+        // ---- E0: ups accumulators -> + bias -> lrelu -> bf16 operand tile sX (zero outside the utterance).
+        // warp = (lane quadrant q, phase pp): input row qq of M block ub  ->  x row u*(qb + qq) + pp.  Runs one tile AHEAD
+        // (for the first tile before the loop, then right after E1(n_r - 1) of the previous tile, under its last conv2)
+        auto e0_stage = [&](int tile, int itn) {
             long row0; int len, o0;
             tile_geom(tile, row0, len, o0);
             const int tbase = o0 - lead;
-            MRF3_STAMP(it, 0);
-            if (modeU) {
-                // ---- E0: ups accumulators -> + bias -> lrelu -> bf16 operand tile sX (zero outside the utterance).
-                // warp = (lane quadrant q, phase pp): input row qq of M block ub  ->  x row u*(qb + qq) + pp
-                const int pp = warp >> 2;
-                const int qb = q_base(tbase);
-                tc::mbar_wait(bar_ups, n_ups & 1); n_ups++;
-                MRF3_STAMP(it, 1);
-                tc::tc_fence_after();
-                const float* ub_bias = sB + (a.nrb + 1) * C;
-                for (int ub = 0; ub < c.nub; ub++) {
-                    const int qq = ub * 128 + 32 * q + lane;
-                    const int t = ((qb + qq) << 2) + pp;              // time row inside the utterance
-                    const int r = t - tbase;                          // row of the operand tile
-                    const bool inu = (t >= 0) && (t < len);
-                    const bool inr = (r >= 0) && (r < c.rx);
-                    if (__all_sync(0xffffffffu, !inr)) continue;       // e.g. the tail of the last M block: nothing of this warp lands in the tile
-                    const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ub * a.up_u * C) + (uint32_t)(pp * C);
+            const int pp = warp >> 2;
+            const int qb = q_base(tbase);
+            tc::mbar_wait(bar_ups, n_ups & 1); n_ups++;
+            MRF3_STAMP(itn, 1);
+            tc::tc_fence_after();
+            const float* ub_bias = sB + (a.nrb + 1) * C;
+            for (int ub = 0; ub < c.nub; ub++) {
+                const int qq = ub * 128 + 32 * q + lane;
+                const int t = ((qb + qq) << 2) + pp;              // time row inside the utterance
+                const int r = t - tbase;                          // row of the operand tile
+                const bool inu = (t >= 0) && (t < len);
+                const bool inr = (r >= 0) && (r < c.rx);
+                if (__all_sync(0xffffffffu, !inr)) continue;       // e.g. the tail of the last M block: nothing of this warp lands in the tile
+                const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ub * a.up_u * C) + (uint32_t)(pp * C);
 #pragma unroll
-                    for (int n0 = 0; n0 < C; n0 += 16) {
-                        float v[16];
-                        tc::tmem_ld16(tl + (uint32_t)n0, v);
-                        uint32_t pk[8];
+                for (int n0 = 0; n0 < C; n0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(tl + (uint32_t)n0, v);
+                    uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float x0 = v[j] + ub_bias[n0 + j], x1v = v[j + 1] + ub_bias[n0 + j + 1];
-                            pk[j >> 1] = inu ? tc::pack_bf16(lrelu_max(x0, a.slope), lrelu_max(x1v, a.slope)) : 0u;
-                        }
-                        if (inr) {
-                            *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 0) * c.rx + r) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 1) * c.rx + r) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                        }
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(ub_bias + n0 + j);
+                        const float x0 = v[j] + bv.x, x1v = v[j + 1] + bv.y, x2 = v[j + 2] + bv.z, x3 = v[j + 3] + bv.w;
+                        pk[j >> 1] = inu ? tc::pack_bf16(lrelu_max(x0, a.slope), lrelu_max(x1v, a.slope)) : 0u;
+                        pk[(j >> 1) + 1] = inu ? tc::pack_bf16(lrelu_max(x2, a.slope), lrelu_max(x3, a.slope)) : 0u;
+                    }
+                    if (inr) {
+                        *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 0) * c.rx + r) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 1) * c.rx + r) * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
-                tc::fence_proxy_async();
-                tc::tc_fence_before();
-                tc::mbar_arrive(bar_x);
-                MRF3_STAMP(it, 2);
             }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_x);
+            MRF3_STAMP(itn, 2);
+        };
+        if (modeU && (int)blockIdx.x < a.ntiles) e0_stage(blockIdx.x, 0);
+        uint32_t n_x1e = 0;                                       // completions of bar_x1 seen so far (n_r per tile)
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            long row0; int len, o0;
+            tile_geom(tile, row0, len, o0);
+            MRF3_STAMP(it, 0);
             // the previous tile's conv_post accumulators drain here, under this tile's first conv1 MMAs; this also
             // guarantees its MMAs no longer read sX1 before E1(0) below overwrites it
             if (post && have_prev) post_epilogue();
@@ -298,6 +329,12 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 tc::tc_fence_before();
                 tc::mbar_arrive(bar_x1);
                 MRF3_STAMP(it, 7 + 4 * r);
+            }
+            n_x1e += (uint32_t)a.nrb;
+            if (modeU && tile + (int)gridDim.x < a.ntiles) {
+                // every epilogue thread has finished reading x out of sX (its arrival on bar_x1 follows its last read)
+                tc::mbar_wait(bar_x1, (n_x1e - 1u) & 1u);
+                e0_stage(tile + gridDim.x, it + 1);
             }
             // ---- final epilogue: out = (acc2 + sum_r(x1_r + b2_r)) / n_r on the central rows
             tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++;
@@ -408,29 +445,33 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             const uint32_t uw_tap16 = (uint32_t)(KCU * N2);          // 16-byte units per tap of one polyphase half
             uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
             const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && mw == 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-                MRF3_STAMP((int)it, 20);
-                tc::mbar_wait(bar_in, it & 1);
+            // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
+            auto issue_ups = [&](uint32_t itn) {
+                tc::mbar_wait(bar_in, itn & 1);
+                if (itn == 0) tc::mbar_wait(bar_upw, 0);
                 tc::tc_fence_after();
-                if (modeU) {
-                    // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
-                    if (it == 0) { tc::mbar_wait(bar_upw, 0); tc::tc_fence_after(); }
-                    for (int ub = ub_lo; ub < ub_hi; ub++)
-                        for (int half = 0; half < 2; half++) {
-                            const uint32_t dcol = tmem_base + (uint32_t)(ub * a.up_u * C) + (uint32_t)(half * N2);
-                            for (int tap = 0; tap < 2; tap++) {
-                                // operand row 0 of sU is input row qb - 1: half A reads rows q-1, q; half B rows q, q+1
-                                uint64_t ad = dhi_u | (uint64_t)((u16 + (uint32_t)(ub * 128 + half + tap)) & 0x3FFF);
-                                uint64_t bd = dhi_uw | (uint64_t)((uw16 + (uint32_t)(half * 2 + tap) * uw_tap16) & 0x3FFF);
-                                for (int k16 = 0; k16 < (a.up_cin >> 4); k16++) {
-                                    tc::umma_bf16(dcol, ad, bd, idesc_up, (tap > 0 || k16) ? 1u : 0u);
-                                    ad += ad_step_u; bd += bd_step_u;
-                                }
+                for (int ub = ub_lo; ub < ub_hi; ub++)
+                    for (int half = 0; half < 2; half++) {
+                        const uint32_t dcol = tmem_base + (uint32_t)(ub * a.up_u * C) + (uint32_t)(half * N2);
+                        for (int tap = 0; tap < 2; tap++) {
+                            // operand row 0 of sU is input row qb - 1: half A reads rows q-1, q; half B rows q, q+1
+                            uint64_t ad = dhi_u | (uint64_t)((u16 + (uint32_t)(ub * 128 + half + tap)) & 0x3FFF);
+                            uint64_t bd = dhi_uw | (uint64_t)((uw16 + (uint32_t)(half * 2 + tap) * uw_tap16) & 0x3FFF);
+                            for (int k16 = 0; k16 < (a.up_cin >> 4); k16++) {
+                                tc::umma_bf16(dcol, ad, bd, idesc_up, (tap > 0 || k16) ? 1u : 0u);
+                                ad += ad_step_u; bd += bd_step_u;
                             }
                         }
-                    tc::umma_commit(bar_in_free);             // the loader may overwrite sU
-                    tc::umma_commit(bar_ups);
-                    MRF3_STAMP((int)it, 21);
+                    }
+                tc::umma_commit(bar_in_free);             // the loader may overwrite sU
+                tc::umma_commit(bar_ups);
+                MRF3_STAMP((int)itn, 21);
+            };
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                MRF3_STAMP((int)it, 20);
+                if (!modeU) { tc::mbar_wait(bar_in, it & 1); tc::tc_fence_after(); }
+                if (modeU) {
+                    if (it == 0) issue_ups(0);                // later tiles: issued one tile ahead, between C2(n_r - 2) and C2(n_r - 1)
                     tc::mbar_wait(bar_x, it & 1);
                     tc::tc_fence_after();
                 }
@@ -438,6 +479,9 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 for (int cv = 0; cv < 2; cv++) {
                     for (int r = 0; r < a.nrb; r++) {
                         if (cv == 1) {
+                            // the next tile's ConvTranspose goes in before the last conv2: its accumulators (conv1 buffers 0..) were
+                            // drained when x1(n_r - 2) was staged, and E0 of the next tile then runs under conv2(n_r - 1)
+                            if (modeU && r == a.nrb - 1 && tile + (int)gridDim.x < a.ntiles) issue_ups(it + 1);
                             tc::mbar_wait(bar_x1, n_x1 & 1); n_x1++;                       // x1(r) staged, acc1[r] drained
                             if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
                             tc::tc_fence_after();
@@ -476,21 +520,17 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 }
                 if (c.resident) { s = 0; }
                 if (post) {
-                    // conv_post: 7 taps, dilation 1, over the stage output sitting in sX1; N = 16 (column 0 is the filter)
+                    // conv_post partial sums P[t][tap] over the stage output sitting in sX1 (tap offset 0, N = 16)
                     tc::mbar_wait(bar_post_rdy, it & 1);
                     MRF3_STAMP((int)it, 40);
                     tc::tc_fence_after();
-                    uint32_t arow16 = x116 - (uint32_t)((MRF3_POST_K - 1) >> 1);
-                    for (int tap = 0; tap < MRF3_POST_K; tap++, arow16++) {
-                        const uint64_t bd0 = dhi_wp | (uint64_t)((wp16 + (uint32_t)(tap * (C / 8) * 16)) & 0x3FFF);
-                        for (int bb = bb_lo; bb < bb_hi; bb++) {
-                            uint64_t ad = dhi_x1 | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
-                            uint64_t bd = bd0;
+                    for (int bb = bb_lo; bb < bb_hi; bb++) {
+                        uint64_t ad = dhi_x1 | (uint64_t)((x116 + 128u * (uint32_t)bb) & 0x3FFF);
+                        uint64_t bd = dhi_wp | (uint64_t)(wp16 & 0x3FFF);
 #pragma unroll
-                            for (int k16 = 0; k16 < C / 16; k16++) {
-                                tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, (tap > 0 || k16) ? 1u : 0u);
-                                ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
-                            }
+                        for (int k16 = 0; k16 < C / 16; k16++) {
+                            tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, k16 ? 1u : 0u);
+                            ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
                         }
                     }
                     tc::umma_commit(bar_post_done);
@@ -566,7 +606,7 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
     if (fuse_post && hmax < c.post_halo) return false;        // the conv_post taps must stay inside the x1 tile
     const int limit = 225 * 1024;
     const int ng = a.C / 32;
-    const int postw_bytes = fuse_post ? MRF3_POST_K * a.C * 16 * 2 : 0;
+    const int postw_bytes = fuse_post ? a.C * 16 * 2 : 0;
     for (int nb = nb_pref; nb >= 1; nb--) {
         if (nb == 3) continue;
         if (nb * ng > MRF3_EPI_WARPS / 4) continue;           // one (block, 32-channel group) item per epilogue warp
@@ -582,13 +622,16 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
         if (modeU) {
             // input rows floor(tbase/u) - 1 ... : the ups pass must cover rx + (u - 1) output rows
             c.nub = (c.rx + a.up_u - 1 + 128 * a.up_u - 1) / (128 * a.up_u);
-            if (c.nub * a.up_u * a.C > (fuse_post ? a.nrb - 1 : a.nrb) * nb * a.C) continue;   // ups accumulators live in the conv1 buffers (not the conv_post one)
+            // ups accumulators live in conv1 buffers 0 .. n_r - 2: those are drained when the next tile's ups pass is issued (before
+            // the last conv2), and the last buffer doubles as the conv_post accumulator
+            if (a.nrb < 2 || c.nub * a.up_u * a.C > (a.nrb - 1) * nb * a.C) continue;
             c.u_rows = ((c.nub * 128 + 2 + 7) / 8) * 8 + 1;
             c.u_bytes = ((a.up_cin / 8) * c.u_rows * 16 + 127) / 128 * 128;
             c.upw_bytes = 2 * 2 * a.up_cin * (a.up_u / 2) * a.C * 2;
         }
         const long fixed = (long)c.x_bytes + c.x1_bytes + c.u_bytes + c.upw_bytes;
-        const long tail = (2 * MRF3_MAX_STAGES + MRF3_NBAR) * 8 + 32 + (MRF3_MAX_RB + 2) * a.C * 4 + postw_bytes + 512;
+        const long tail = (2 * MRF3_MAX_STAGES + MRF3_NBAR) * 8 + 32 + (MRF3_MAX_RB + 2) * a.C * 4 + postw_bytes + 512 +
+                          (fuse_post ? (128 * nb + 8) * MRF3_SP_PITCH * 4 + 128 : 0);
         const long res_bytes = (long)npieces * c.slot_bytes;
         if (npieces <= MRF3_MAX_STAGES && fixed + res_bytes + tail <= limit) { c.resident = 1; c.nstages = npieces; }
         else {
@@ -602,7 +645,8 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
         }
         c.bias_off = (int)((fixed + (long)c.nstages * c.slot_bytes + (2 * c.nstages + MRF3_NBAR) * 8 + 32 + 15) / 16 * 16);
         c.postw_off = (c.bias_off + (MRF3_MAX_RB + 2) * a.C * 4 + 127) / 128 * 128;
-        c.smem_bytes = c.postw_off + postw_bytes;
+        c.sp_off = (c.postw_off + postw_bytes + 127) / 128 * 128;
+        c.smem_bytes = c.sp_off + (fuse_post ? (c.span + 8) * MRF3_SP_PITCH * 4 : 0);
         if (c.smem_bytes > limit) continue;
         int cols = 32; while (cols < (a.nrb + 1) * nb * a.C) cols <<= 1;
         c.tmem_cols = cols;
