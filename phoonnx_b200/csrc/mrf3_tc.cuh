@@ -77,6 +77,13 @@ namespace tc {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// tcgen05.mma with the two shared-memory descriptors given as (lo, hi) 32-bit halves: only `lo` (start address >> 4 | LBO << 16)
+// changes between the MMAs of a conv, by plain 32-bit adds; `hi` (SBO, version) is loop-invariant
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -444,6 +451,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             const uint32_t wp16 = tc::smem_u32(sWp) >> 4, u16 = tc::smem_u32(sU) >> 4, uw16 = tc::smem_u32(sUW) >> 4;
             const uint32_t uw_tap16 = (uint32_t)(KCU * N2);          // 16-byte units per tap of one polyphase half
             uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
+            const uint32_t slot16 = (uint32_t)c.slot_bytes >> 4;
+            const int nbw = bb_hi - bb_lo;                     // M blocks of this warp: 1 or 2
             const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && mw == 0;
             // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
             auto issue_ups = [&](uint32_t itn) {
@@ -491,25 +500,26 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                         }
                         MRF3_STAMP((int)it, 24 + 2 * (cv * 3 + r));
                         const int kr = a.k[r];
-                        const int dil = cv ? a.d2[r] : a.d1[r];
-                        const uint64_t dhi = cv ? dhi_x1 : dhi_x;
-                        const uint64_t ad_step = cv ? ad_step_x1 : ad_step_x;
-                        const uint32_t dcol0 = tmem_base + (cv ? acc2_col : (uint32_t)r * acc1_cols);
-                        uint32_t arow16 = (cv ? x116 : x16) - (uint32_t)(((kr - 1) >> 1) * dil);     // tap 0
-                        for (int tap = 0; tap < kr; tap++, arow16 += (uint32_t)dil) {
+                        const uint32_t dil = (uint32_t)(cv ? a.d2[r] : a.d1[r]);
+                        // descriptor low words: start address (16-byte units == rows) | LBO << 16; a tap advances the A start by `dil`
+                        // rows, an M block by 128 rows, a K=16 step by two chunk planes (2 * LBO)
+                        const uint32_t a_lbo16 = cv ? (lbo_x1 >> 4) : (lbo_x >> 4);
+                        const uint32_t a_k16 = 2u * a_lbo16, b_k16 = 2u * (lbo_w >> 4);
+                        const uint32_t ahi = (uint32_t)((cv ? dhi_x1 : dhi_x) >> 32), bhi = (uint32_t)(dhi_w >> 32);
+                        const uint32_t dcol0 = tmem_base + (cv ? acc2_col : (uint32_t)r * acc1_cols) + (uint32_t)(bb_lo * C);
+                        uint32_t alo = ((cv ? x116 : x16) - (uint32_t)((kr - 1) >> 1) * dil + 128u * (uint32_t)bb_lo) | (a_lbo16 << 16);   // tap 0
+                        const uint32_t acc_first = (cv && r > 0) ? 1u : 0u;      // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks
+                        for (int tap = 0; tap < kr; tap++, alo += dil) {
                             if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
-                            const uint64_t bd0 = dhi_w | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
-                            // conv1: fresh accumulator per resblock; conv2 accumulates across resblocks (and taps)
-                            const uint32_t acc0 = (tap > 0 || (cv && r > 0)) ? 1u : 0u;
-                            for (int bb = bb_lo; bb < bb_hi; bb++) {
-                                uint64_t ad = dhi | (uint64_t)((arow16 + 128u * (uint32_t)bb) & 0x3FFF);
-                                uint64_t bd = bd0;
-                                const uint32_t dcol = dcol0 + (uint32_t)(bb * C);
+                            const uint32_t blo = ((sW_u >> 4) + s * slot16) | ((lbo_w >> 4) << 16);
+                            const uint32_t acc0 = tap > 0 ? 1u : acc_first;
 #pragma unroll
-                                for (int k16 = 0; k16 < C / 16; k16++) {
-                                    tc::umma_bf16(dcol, ad, bd, idesc, k16 ? 1u : acc0);
-                                    ad += ad_step; bd += bd_step;
-                                }
+                            for (int k16 = 0; k16 < C / 16; k16++)
+                                tc::umma_bf16_lh(dcol0, alo + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0);
+                            if (nbw == 2) {
+#pragma unroll
+                                for (int k16 = 0; k16 < C / 16; k16++)
+                                    tc::umma_bf16_lh(dcol0 + (uint32_t)C, alo + 128u + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0);
                             }
                             if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
