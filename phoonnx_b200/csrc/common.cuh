@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define CONV_MAX_TAPS 16
+#define CONV_MAX_SLICES 8
 
 enum ConvEpi { EPI_STORE = 0, EPI_GATE = 1, EPI_SPLIT = 2, EPI_SUBFROM = 3 };
 enum OutAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
@@ -34,6 +35,9 @@ struct ConvArgs {
     // bf16(x - xh)).  The activation tile holds a hi and a lo plane; wtc then holds 3*cin input channels per tap
     // ([wh | wl | wh]).  Used for the text side, whose output feeds ceil(exp(logw)).
     int split3;
+    // K slices (tcgen05 path): the kernel loops over nks slices of `cin` input channels each (activation columns xcol + ks * cin,
+    // weights wtc_ks[ks]) and accumulates them in TMEM: one epilogue per tile, activation tiles double-buffered across slices
+    int nks;  const __nv_bfloat16* wtc_ks[CONV_MAX_SLICES];
     __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
     unsigned long long* dbg;   // test-only phase timeline of CTA (0,0): [tile][16] clock64 stamps, or null
 };

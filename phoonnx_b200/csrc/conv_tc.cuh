@@ -409,12 +409,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
             const long row0 = (long)cb0 * a.rate;
             const int len = (cb1 - cb0) * a.rate;
-            const uint32_t abuf = it % (uint32_t)c.nabuf, ause = it / (uint32_t)c.nabuf;
+            const int tlo = -(t0 + c.min_off), thi = len - (t0 + c.min_off);      // valid tile rows: tlo <= r < thi
+            for (int ks = 0; ks < a.nks; ks++) {
+            const uint32_t lit = it * (uint32_t)a.nks + (uint32_t)ks;         // activation tiles are counted per (tile, K slice)
+            const uint32_t abuf = lit % (uint32_t)c.nabuf, ause = lit / (uint32_t)c.nabuf;
             tc::mbar_wait(bar_aempty0 + 8u * abuf, (ause & 1u) ^ 1u);     // MMAs that read this buffer have retired
             TC_STAMP(it, 5);
             uint8_t* dstA = sA + (size_t)abuf * c.a_bytes;
-            const float* xbase = a.x + (row0 + t0 + c.min_off) * a.ldx + a.xcol;
-            const int tlo = -(t0 + c.min_off), thi = len - (t0 + c.min_off);      // valid tile rows: tlo <= r < thi
+            const float* xbase = a.x + (row0 + t0 + c.min_off) * a.ldx + a.xcol + ks * a.cin;
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
             // flight per thread before any conversion so the load latency is paid once per batch
             int r = lt / kc_total, kc = lt - r * kc_total;
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc::mbar_arrive(bar_afull0 + 8u * abuf);
             TC_STAMP(it, 6);
+            }
         }
     } else if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= weight producer (one thread, cp.async.bulk ring) =================
@@ -472,7 +475,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, itp++) {
                 if (c.resident && tile != (int)blockIdx.x) break;
                 TC_STAMP(itp, 7);
-                const __nv_bfloat16* src = a.wtc + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
+                for (int ks = 0; ks < a.nks; ks++) {
+                const __nv_bfloat16* src = a.wtc_ks[ks] + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
                 for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
                         const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s(dst, src, kc_bytes, fb);
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
+                }
                 }
                 TC_STAMP(itp, 8);
             }
@@ -499,14 +504,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             uint32_t abuf = 0, aph = 0, cbuf = 0, cph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
                 TC_STAMP((int)it, 9);
-                tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
-                TC_STAMP((int)it, 10);
                 tc::mbar_wait(bar_accempty0 + 8u * cbuf, cph ^ 1u);
                 TC_STAMP((int)it, 11);
-                tc::tc_fence_after();
                 const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
-                const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
                 uint32_t accum = 0;
+                for (int ks = 0; ks < a.nks; ks++) {
+                tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
+                TC_STAMP((int)it, 10);
+                tc::tc_fence_after();
+                const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
                 for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
                     const int tap = a.split3 ? tapseg / 3 : tapseg;
                     const int seg = tapseg - tap * nseg;
@@ -527,11 +533,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
                 }
-                if (c.resident) s = 0;
                 tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
+                if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
+                }
+                if (c.resident) s = 0;
                 tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
                 TC_STAMP((int)it, 12);
-                if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
                 if (++cbuf == (uint32_t)c.naccbuf) { cbuf = 0; cph ^= 1u; }
             }
         }
@@ -561,7 +568,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     c.a_bytes = (planes * (a.cin / 8) * rows * 16 + 127) / 128 * 128;
     c.piece_ch = a.cin < TC_PIECE_CH ? a.cin : TC_PIECE_CH;
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
-    c.npieces = a.ntaps * nseg * c.cpt;
+    c.npieces = a.ntaps * nseg * c.cpt * (a.nks > 0 ? a.nks : 1);
     const int limit = 222 * 1024;
     const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;
     int nt = a.npad16 <= 256 ? a.npad16 : 0;

@@ -32,7 +32,6 @@ namespace {
 
 struct DevBlob { void* p = nullptr; size_t bytes = 0; int dtype = 0; };
 
-#define CONV_MAX_SLICES 8
 struct ConvP {
     const float* w = nullptr; const __nv_bfloat16* wtc = nullptr; const float* b = nullptr;
     int cin = 0, n = 0, npad = 0, npad16 = 0, ntaps = 0; int toff[CONV_MAX_TAPS] = {0};
@@ -166,11 +165,12 @@ int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, co
     c.wtc = nullptr;
     if (t && t->dtype == 1 && cin % 16 == 0 && t->bytes >= (size_t)c.ntaps * cin * c.npad16 * 2)
         c.wtc = reinterpret_cast<const __nv_bfloat16*>(t->p);
-    // K slices of the bf16x3 form: largest divisor of cin that is a multiple of 16 and <= 192 (packing.split3_slice)
+    // K slices of the bf16x3 form: largest divisor of cin that is a multiple of 16 and <= 96 (packing.split3_slice): the hi + lo
+    // activation planes of one slice, double-buffered, fit one CTA's shared memory
     c.nsl = 0; c.slice_cin = 0;
     if (cin % 16 == 0 && n % 16 == 0) {
         int sl = 0;
-        for (int v = std::min(cin, 192); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
+        for (int v = std::min(cin, 96); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
         if (sl && cin / sl <= CONV_MAX_SLICES) {
             bool all = true;
             for (int j = 0; j < cin / sl; j++) {
@@ -232,7 +232,7 @@ ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out
 
 int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     a.cu = T.cu; a.B = T.B; a.rate = T.rate;
-    a.split3 = 0;
+    a.split3 = 0; a.nks = 1; a.wtc_ks[0] = a.wtc;
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
         a.tile_cu = T.t128; a.ntiles = T.n128;
         if (T.n128 == 0) return 0;
@@ -260,21 +260,19 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
 // Text-side convolution (encoder / duration predictor): in bf16 mode it runs on the tensor cores as an fp32-faithful
 // bf16x3 product, K-sliced so the hi+lo activation planes fit shared memory; slices after the first accumulate.
 int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T) {
-    const bool want = h->precision == 1 && h->text_tc && c.nsl > 0 && a.epi == EPI_STORE && a.ldx % 4 == 0 &&
-                      a.xcol % 4 == 0 && !(c.nsl > 1 && (a.out_act != ACT_NONE || a.out_div != 1.f));
+    const bool want = h->precision == 1 && h->text_tc && c.nsl > 0 && a.epi == EPI_STORE && a.ldx % 4 == 0 && a.xcol % 4 == 0;
     if (!want) return launch_conv(h, a, T, false);
     a.cu = T.cu; a.B = T.B; a.rate = T.rate;
     a.tile_cu = T.t128; a.ntiles = T.n128;
     if (T.n128 == 0) return 0;
-    const int xcol0 = a.xcol;
-    for (int j = 0; j < c.nsl; j++) {
-        ConvArgs s = a;
-        s.split3 = 1; s.wtc = c.wtc3[j]; s.cin = c.slice_cin; s.xcol = xcol0 + j * c.slice_cin;
-        if (j > 0) { s.bias = nullptr; s.utab = nullptr; s.res = nullptr; s.accumulate = 1; }
-        cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream);
-        if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc (bf16x3) launch: %s", cudaGetErrorString(e));
-        h->launches++;
-    }
+    // one launch: the kernel loops over the K slices and accumulates them in TMEM
+    ConvArgs s = a;
+    s.split3 = 1; s.cin = c.slice_cin; s.nks = c.nsl; s.wtc = c.wtc3[0];
+    for (int j = 0; j < c.nsl; j++) s.wtc_ks[j] = c.wtc3[j];
+    s.dbg = nullptr;
+    cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream);
+    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc (bf16x3) launch: %s", cudaGetErrorString(e));
+    h->launches++;
     return 0;
 }
 
@@ -410,6 +408,9 @@ int vits_set_option(vits_handle* h, const char* key, double value) {
         h->precision = (int)value;
     } else if (k == "text_tc") {
         h->text_tc = value != 0;
+    } else if (k == "num_sms") {
+        if (value < 1) return fail(h, VITS_E_INVALID, "num_sms must be >= 1");
+        h->num_sms = (int)value;                 // test hook: persistent grids use this many CTAs
     } else if (k == "max_chunk_frames") {
         if (value < 1) return fail(h, VITS_E_INVALID, "max_chunk_frames must be >= 1");
         h->max_chunk_frames = (int64_t)value;
@@ -1105,7 +1106,14 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     CK(h, cudaMemcpy(dmeta, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice));
     const Tiles T = tb.get(dmeta, 1);
     ConvP c; c.w = dw; c.wtc = (const __nv_bfloat16*)dwtc; c.b = db; c.cin = cin; c.n = n; c.npad = npad; c.npad16 = npad16; c.ntaps = ntaps;
-    if (use_tc == 2) { c.nsl = 1; c.slice_cin = cin; c.wtc3[0] = (const __nv_bfloat16*)dwtc; }
+    if (use_tc == 2) {
+        // `wtc` holds the K slices back to back ("<n>.wtc3.0", ".1", ...), slice width as in mkconv
+        int sl = 0;
+        for (int v = std::min(cin, 96); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
+        if (!sl || cin / sl > CONV_MAX_SLICES) { cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dmeta); return fail(h, VITS_E_INVALID, "bf16x3: unsupported cin %d", cin); }
+        c.nsl = cin / sl; c.slice_cin = sl;
+        for (int j = 0; j < c.nsl; j++) c.wtc3[j] = (const __nv_bfloat16*)dwtc + (size_t)j * ntaps * 3 * sl * npad16;
+    }
     for (int i = 0; i < ntaps; i++) c.toff[i] = taps[i];
     ConvArgs a = base_args(c, dx, cin, 0, dout, out_cols, 0);
     a.in_act = in_act; a.in_slope = in_slope; a.epi = epi; a.res = dres; a.ldres = n; a.accumulate = accumulate;

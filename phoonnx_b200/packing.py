@@ -42,7 +42,7 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return (f32_to_bf16_bits(x).astype(np.uint32) << 16).view(np.float32)
 
 
-SPLIT3_MAX_CIN = 192   # widest K slice whose hi+lo activation planes fit one CTA's shared memory
+SPLIT3_MAX_CIN = 96    # widest K slice whose hi+lo activation planes, double-buffered, fit one CTA's shared memory
 
 
 def split3_slice(cin: int) -> int:

@@ -55,7 +55,7 @@ def test_bf16x3_operands_reproduce_fp32_products():
     blobs = {}
     packing.pack_conv(blobs, "c", w, None, tc3=True)
     sl = packing.split3_slice(cin)
-    assert sl == 192 and "c.wtc3.1" in blobs and "c.wtc3.2" not in blobs
+    assert sl == 96 and "c.wtc3.3" in blobs and "c.wtc3.4" not in blobs
     x = rs.randn(50, cin).astype(np.float32)
     xh = packing.bf16_round(x)
     xl = packing.bf16_round(x - xh)

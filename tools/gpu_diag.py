@@ -40,9 +40,12 @@ def run_conv(eng, use_tc, x, w_tcn, bias, taps, in_slope=None, epi=0, res=None, 
     p = lambda a_: None if a_ is None else a_.ctypes.data_as(C.c_void_p)
     wtc = blobs.get("c.wtc")
     if use_tc == 2:
-        if "c.wtc3.1" in blobs or "c.wtc3.0" not in blobs:
-            raise ValueError("test hook runs single-slice bf16x3 convolutions only")
-        wtc = blobs["c.wtc3.0"]
+        if "c.wtc3.0" not in blobs:
+            raise ValueError("shape has no bf16x3 operands")
+        parts, j = [], 0
+        while f"c.wtc3.{j}" in blobs:
+            parts.append(blobs[f"c.wtc3.{j}"].reshape(-1)); j += 1
+        wtc = np.ascontiguousarray(np.concatenate(parts))
     xb = np.ascontiguousarray(x, np.float32)
     rc = lib.vits_test_conv(eng._h, int(use_tc), p(xb), L, cin, p(taps_a), len(taps), p(blobs["c.w"]), p(wtc),
                             p(blobs.get("c.b")), n, 0 if in_slope is None else 1, float(in_slope or 1.0), epi,

@@ -21,6 +21,8 @@ def main():
     _, arch = modelgen.make_voice(path, "medium", n_speakers=1, seed=1234)
     sess = B200Session(path, precision="bf16", max_chunk_frames=int(sys.argv[1]) if len(sys.argv) > 1 else 131072)
     eng = sess.engine
+    if len(sys.argv) > 2:
+        eng.set_option("num_sms", int(sys.argv[2]))
     rs = np.random.RandomState(0)
     B = 96
     lens = rs.randint(150, 257, size=(B,)).astype(np.int64)
