@@ -128,7 +128,8 @@ def main():
     ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--preset", default="medium")
-    ap.add_argument("--max-ids", type=int, default=32768, help="phoneme ids per device batch")
+    ap.add_argument("--max-ids", type=int, default=131072, help="phoneme ids per device batch")
+    ap.add_argument("--max-utts", type=int, default=2048, help="utterances per device batch")
     ap.add_argument("--chunk-frames", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=24, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -179,7 +180,7 @@ def main():
     from phoonnx_b200.session import B200Session
     sess = B200Session(path, device=local, precision=args.precision, max_chunk_frames=args.chunk_frames, seed=1000 * rank)
     eng = sess.engine
-    batches = scheduler.plan(lengths, 1, 0, max_ids=args.max_ids)
+    batches = scheduler.plan(lengths, 1, 0, max_ids=args.max_ids, max_utts=args.max_utts)
     feeds = []
     for bidx in batches:
         x, lens = scheduler.pad_batch([utts[i] for i in bidx])

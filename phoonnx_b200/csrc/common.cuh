@@ -38,7 +38,9 @@ struct ConvArgs {
     // K slices (tcgen05 path): the kernel loops over nks slices of `cin` input channels each (activation columns xcol + ks * cin,
     // weights wtc_ks[ks]) and accumulates them in TMEM: one epilogue per tile, activation tiles double-buffered across slices
     int nks;  const __nv_bfloat16* wtc_ks[CONV_MAX_SLICES];
-    __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
+    const __nv_bfloat16* xb;  int ldxb;       // tcgen05 path: the input as bf16 MMA-operand rows [rows, ldxb] (already activated) instead of fp32 `x`;
+                                            // cp.async'd straight into the operand tile (xcol applies)
+    __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE / EPI_GATE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
     unsigned long long* dbg;   // test-only phase timeline of CTA (0,0): [tile][16] clock64 stamps, or null
 };
 

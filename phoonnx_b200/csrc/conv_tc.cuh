@@ -284,7 +284,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                                 if (a.out_div != 1.f) { v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div; }
                                 if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
                             }
-                            if (EPI == EPI_STORE && a.outb) {
+                            if ((EPI == EPI_STORE || EPI == EPI_GATE) && a.outb) {
                                 // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
                                 const float sl = a.outb_slope;
                                 const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(v4.x, v4.x * sl), fmaxf(v4.y, v4.y * sl)),
@@ -417,6 +417,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             TC_STAMP(it, 5);
             uint8_t* dstA = sA + (size_t)abuf * c.a_bytes;
             const float* xbase = a.x + (row0 + t0 + c.min_off) * a.ldx + a.xcol + ks * a.cin;
+            if (a.xb) {
+                // the producer already wrote MMA-operand rows (bf16, activated): 16-byte cp.async straight into the K-major
+                // tile, zero-filled outside the utterance; no registers, no conversion
+                const __nv_bfloat16* xbb = a.xb + (row0 + t0 + c.min_off) * (long)a.ldxb + a.xcol + ks * a.cin;
+                const uint32_t dA = tc::smem_u32(dstA);
+                for (int i = lt; i < items; i += TC_LOAD_THREADS) {
+                    const int r2 = i / kc_total, kc2 = i - r2 * kc_total;
+                    const bool okr = (r2 >= tlo) && (r2 < thi);
+                    const __nv_bfloat16* src = xbb + (okr ? (long)r2 * a.ldxb : 0) + kc2 * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dA + (uint32_t)(kc2 * c.rows_a + r2) * 16u), "l"(okr ? src : a.xb), "r"(okr ? 16u : 0u) : "memory");
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                tc::fence_proxy_async();
+                tc::mbar_arrive(bar_afull0 + 8u * abuf);
+                TC_STAMP(it, 6);
+                continue;
+            }
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
             // flight per thread before any conversion so the load latency is paid once per batch
             int r = lt / kc_total, kc = lt - r * kc_total;
@@ -552,7 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
 static inline bool conv_tc_supported(const ConvArgs& a) {
     if (!a.wtc) return false;
     if (a.cin % 16 || a.n % 16 || a.cin < 16 || a.n < 16) return false;
-    if (a.ldx % 4 || a.xcol % 4) return false;
+    if (a.xb ? (a.ldxb % 8 || a.xcol % 8 || a.split3) : (a.ldx % 4 || a.xcol % 4)) return false;
     if (a.epi == EPI_SPLIT && (a.split % 16)) return false;
     return true;
 }

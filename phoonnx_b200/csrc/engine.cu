@@ -75,7 +75,8 @@ struct vits_handle {
     std::vector<CFlow> cflows;
     float ea_m = 0.f, ea_logs = 0.f;
     ConvP dpd_c1, dpd_c2, dpd_proj; LnP dpd_n1, dpd_n2;
-    struct FlowS { ConvP pre, post; std::vector<ConvP> in, rs; std::vector<const float*> cond_tab; int xcol, ocol; };
+    struct FlowS { ConvP pre, post; std::vector<ConvP> in, rs; std::vector<const float*> cond_tab; int xcol, ocol;
+                   std::vector<ConvP> rsr, mskip; const float* mskip_b = nullptr; bool v2 = false; };   // tensor-core tail (packing.py "mskip")
     std::vector<FlowS> flows;
     ConvP dec_pre; const float* dec_cond_tab = nullptr;
     struct UpS { ConvP A, B; int rate, cout; };
@@ -104,7 +105,7 @@ struct vits_handle {
     cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
-    Buf audio_alt;
+    Buf audio_alt, facts_b;
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
     float stage_ms[3] = {0, 0, 0};
@@ -232,7 +233,8 @@ ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out
 
 int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     a.cu = T.cu; a.B = T.B; a.rate = T.rate;
-    a.split3 = 0; a.nks = 1; a.wtc_ks[0] = a.wtc;
+    a.split3 = 0;
+    if (a.nks <= 1) { a.nks = 1; a.wtc_ks[0] = a.wtc; }
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
         a.tile_cu = T.t128; a.ntiles = T.n128;
         if (T.n128 == 0) return 0;
@@ -248,6 +250,7 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
         h->launches++;
         return 0;
     }
+    if (a.xb || a.outb) return fail(h, VITS_E_STATE, "bf16 operand rows need the tcgen05 conv path (cin %d, n %d)", a.cin, a.n);
     a.tile_cu = T.t64; a.ntiles = T.n64;
     if (T.n64 == 0) return 0;
     dim3 grid(T.n64, (a.n + CF_TN - 1) / CF_TN);
@@ -495,6 +498,17 @@ int vits_finalize(vits_handle* h) {
             dil *= A.wn_dilation_rate;
         }
         if ((rc = mkconv(h, f.post, p + ".post", H, half, {0}, true))) return rc;
+        // optional tensor-core tail: residual-only res_skip convs + one composed GEMM for m (packing.py)
+        f.v2 = find_blob(h, p + ".mskip.b") != nullptr && H % 16 == 0 && half % 16 == 0;
+        if (f.v2) {
+            f.rsr.resize(A.wn_layers); f.mskip.resize(A.wn_layers);
+            for (int i = 0; i < A.wn_layers && f.v2; i++) {
+                if (i < A.wn_layers - 1 && (mkconv(h, f.rsr[i], p + ".rsr." + std::to_string(i), H, H, {0}, true) || !f.rsr[i].wtc)) f.v2 = false;
+                if (f.v2 && (mkconv(h, f.mskip[i], p + ".mskip." + std::to_string(i), H, half, {0}, false) || !f.mskip[i].wtc)) f.v2 = false;
+            }
+            if (f.v2 && need_f32(h, p + ".mskip.b", &f.mskip_b, half)) f.v2 = false;
+            if (A.wn_layers > CONV_MAX_SLICES) f.v2 = false;
+        }
     }
     // decoder
     if ((rc = mkconv(h, h->dec_pre, "dec.pre", C, A.up_init, sym_taps(7, 1), true))) return rc;
@@ -845,10 +859,34 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         // ---- coupling flow, reverse (models.py:247-254, modules.py:447-466, 184-209)
         const bool tc_flow = true;
+        const bool flow_v2 = h->precision == 1 && h->opts["no_flow_v2"] == 0;
         for (int s = 0; s < A.n_flow; s++) {
             auto& f = h->flows[s];
             ConvArgs a = base_args(f.pre, P, C, f.xcol, fh, H, 0);
             if ((rc = launch_conv(h, a, T1, tc_flow))) return rc;
+            if (flow_v2 && f.v2) {
+                // bf16 tail: gate outputs of all layers side by side as MMA-operand rows [Fr, layers * H]; res_skip keeps its
+                // residual half; m = one GEMM over all of them (K slices = layers), subtracted from the coupled half in place
+                const int L = A.wn_layers;
+                if ((rc = ensure(h, h->facts_b, (size_t)Fr * L * H * 2))) return rc;
+                __nv_bfloat16* fb = ptr<__nv_bfloat16>(h->facts_b);
+                for (int i = 0; i < L; i++) {
+                    a = base_args(f.in[i], fh, H, 0, facts, L * H, i * H); a.epi = EPI_GATE;
+                    a.outb = fb; a.outb_slope = 1.f;
+                    if (A.n_speakers > 1) { a.utab = f.cond_tab[i]; a.uidx = d_sid; a.utab_ld = 2 * H; }
+                    if ((rc = launch_conv(h, a, T1, true))) return rc;
+                    if (i < L - 1) {
+                        a = base_args(f.rsr[i], nullptr, 0, i * H, fh, H, 0); a.accumulate = 1;
+                        a.xb = fb; a.ldxb = L * H;
+                        if ((rc = launch_conv(h, a, T1, true))) return rc;
+                    }
+                }
+                a = base_args(f.mskip[0], nullptr, 0, 0, P, C, f.ocol); a.epi = EPI_SUBFROM; a.res = P; a.ldres = C; a.rescol = f.ocol;
+                a.bias = f.mskip_b; a.xb = fb; a.ldxb = L * H;
+                a.nks = L; for (int i = 0; i < L; i++) a.wtc_ks[i] = f.mskip[i].wtc;
+                if ((rc = launch_conv(h, a, T1, true))) return rc;
+                continue;
+            }
             for (int i = 0; i < A.wn_layers; i++) {
                 a = base_args(f.in[i], fh, H, 0, facts, H, 0); a.epi = EPI_GATE;
                 if (A.n_speakers > 1) { a.utab = f.cond_tab[i]; a.uidx = d_sid; a.utab_ld = 2 * H; }
@@ -1190,7 +1228,7 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }

@@ -181,6 +181,24 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
         if flipped:
             w, b = w[:, :, ::-1], b[::-1]
         pack_conv(o, f"flow.{s}.post", np.ascontiguousarray(w), np.ascontiguousarray(b), tc=tc)
+        if tc:
+            # tensor-core form of the WN tail (modules.py:196-209 + 447-466): the skip path is linear, so
+            #   m = post(sum_l skip_l(acts_l)) = sum_l (W_skip_l @ W_post) acts_l + (sum_l b_skip_l) @ W_post + b_post
+            # is ONE GEMM over the concatenated gate outputs of all layers -- no skip accumulator in HBM, no separate
+            # post conv; the res_skip convs keep their residual half only
+            wp = np.asarray(w[0], np.float64)                                   # [H, half]
+            bsum = np.zeros((H,), np.float64)
+            for i in range(a.wn_layers):
+                wr, br = _conv_std(W, f"{p}.enc.res_skip_layers.{i}")          # [1, H, 2H] (last layer: [1, H, H])
+                if i < a.wn_layers - 1:
+                    pack_conv(o, f"flow.{s}.rsr.{i}", np.ascontiguousarray(wr[:, :, :H]), np.ascontiguousarray(br[:H]), tc=True)
+                    wsk, bsk = wr[0][:, H:], br[H:]
+                else:
+                    wsk, bsk = wr[0], br
+                pack_conv(o, f"flow.{s}.mskip.{i}", (np.asarray(wsk, np.float64) @ wp).astype(np.float32)[None],
+                          None, tc=True)
+                bsum += np.asarray(bsk, np.float64)
+            o[f"flow.{s}.mskip.b"] = (bsum @ wp + np.asarray(b, np.float64)).astype(np.float32)
 
     pack_conv(o, "dec.pre", *_conv_std(W, "dec.conv_pre"), tc=tc)
     nk = len(a.rb_kernels)

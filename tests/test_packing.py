@@ -69,3 +69,36 @@ def test_bf16x3_operands_reproduce_fp32_products():
     assert np.abs(acc - want).max() < 2e-5 * np.abs(want).max() + 1e-6
     plain = xh.astype(np.float64) @ packing.bf16_round(w[1]).astype(np.float64)
     assert np.abs(plain - want).max() > 50 * np.abs(acc - want).max()   # the split really buys ~2^8
+
+
+def test_flow_tail_composition_matches_skip_then_post():
+    """packing.py "mskip": m = post(sum_l skip_l(acts_l)) folded into one GEMM over the concatenated gate outputs,
+    res_skip reduced to its residual half (modules.py:196-209, 447-466).  Checked against the unfused blobs."""
+    import tempfile, os
+    from phoonnx_b200 import modelgen
+    from phoonnx_b200.weights import load_model
+    from phoonnx_b200.packing import pack_model
+    import emulate as E
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "v.onnx")
+        modelgen.make_voice(path, "x_low", n_speakers=1, seed=3)
+        W, a, _ = load_model(path)
+    blobs, _ = pack_model(W, a)
+    H, half, L = a.hidden, a.inter // 2, a.wn_layers
+    rs = np.random.RandomState(0)
+    acts = [rs.randn(40, H).astype(np.float32) for _ in range(L)]
+    for s in range(len(a.flow_layers)):
+        skip = np.zeros((40, H), np.float64)
+        for i in range(L):
+            w, b = blobs[f"flow.{s}.rs.{i}.w"], blobs[f"flow.{s}.rs.{i}.b"]
+            full = E.conv_cl(acts[i], w, b, [0], w.shape[2])
+            if i < L - 1:
+                skip += full[:, H:2 * H]
+                res = E.conv_cl(acts[i], blobs[f"flow.{s}.rsr.{i}.w"], blobs[f"flow.{s}.rsr.{i}.b"], [0], H)
+                assert np.array_equal(res, full[:, :H])
+            else:
+                skip += full[:, :H]
+        want = E.conv_cl(skip.astype(np.float32), blobs[f"flow.{s}.post.w"], blobs[f"flow.{s}.post.b"], [0], half)
+        got = sum(acts[i].astype(np.float64) @ blobs[f"flow.{s}.mskip.{i}.w"][0, :, :half].astype(np.float64) for i in range(L))
+        got = got + blobs[f"flow.{s}.mskip.b"][:half]
+        assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max()), np.abs(got - want).max()
