@@ -40,6 +40,7 @@ struct ConvArgs {
     int nks;  const __nv_bfloat16* wtc_ks[CONV_MAX_SLICES];
     const __nv_bfloat16* xb;  int ldxb;       // tcgen05 path: the input as bf16 MMA-operand rows [rows, ldxb] (already activated) instead of fp32 `x`;
                                             // cp.async'd straight into the operand tile (xcol applies)
+    const __nv_bfloat16* resb;  int ldresb;  float resb_slope;   // residual given as bf16 lrelu_{slope} rows: res = min(v, v / slope) (rescol applies)
     __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE / EPI_GATE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
     unsigned long long* dbg;   // test-only phase timeline of CTA (0,0): [tile][16] clock64 stamps, or null
 };

@@ -25,7 +25,7 @@
 
 #define TC_M 128
 #define TC_EPI_WARPS 8
-#define TC_LOAD_WARPS 8
+#define TC_LOAD_WARPS 6
 #define TC_THREADS ((TC_EPI_WARPS + TC_LOAD_WARPS + 2) * 32)
 #define TC_LOAD_THREADS (TC_LOAD_WARPS * 32)
 #define TC_EPI_PITCH 36            // floats per staged row: 16 B aligned, conflict-free for 8-lane phases
@@ -159,12 +159,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
-// Warp-specialised persistent kernel (TC_THREADS = 576):
+// Warp-specialised persistent kernel (TC_THREADS = 512 = 16 warps: the register file is handed out to groups of 4 warps, so 18
+// warps would be charged as 20 and cap the kernel at 96 registers per thread; 16 warps leave 128 for the epilogue's prefetch):
 //   warps 0-7   epilogue  (TMEM -> registers -> smem transpose -> coalesced global), TMEM lane quadrant = warp % 4,
 //               the two warps of a quadrant alternate over the 32-column groups of the accumulator
-//   warps 8-15  activation loaders (global fp32 -> lrelu -> bf16 -> smem operand tile)
-//   warp  16    weight producer (elected lane) + TMEM allocator
-//   warp  17    MMA issuer (elected lane)
+//   warps 8-13  activation loaders (global fp32 -> lrelu -> bf16 -> smem operand tile, or cp.async of bf16 operand rows)
+//   warp  14    weight producer (elected lane) + TMEM allocator
+//   warp  15    MMA issuer (elected lane)
 // Activation tiles and TMEM accumulators are double-buffered when they fit, so the load of tile i+1, the MMAs of
 // tile i and the epilogue of tile i-1 overlap inside one CTA.
 // r01 timeline (profiles/r01c_conv_timeline.log): with 4 epilogue warps and one generic, branchy epilogue the
@@ -174,7 +175,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 #define TC_DBG_TILES 16
 #define TC_STAMP(it_, slot_) do { if (dbg_on && (it_) < TC_DBG_TILES) a.dbg[(it_) * 16 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
-template <int EPI>
+// RESK: residual operand kind (0 none, 1 fp32 rows, 2 bf16 lrelu rows); ACC: the destination may be accumulated into.  Compile-time so
+// that the prefetch registers exist only for operands the launch really has.
+template <int EPI, int RESK, int ACC>
 __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, uint8_t* smem, uint32_t tmem_base,
                                             uint32_t bar_accfull0, uint32_t bar_accempty0, int warp, int lane, bool dbg_on) {
     const int q = warp & 3, hh = warp >> 2, ny = blockIdx.y;
@@ -182,7 +185,8 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     float* srow = sE + lane * TC_EPI_PITCH;
     const int ngroups = (c.ntile + 31) >> 5;
     const float inv_div = 1.f / a.out_div;
-    const bool has_res = a.res != nullptr;
+    constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2);
+    const float resb_inv = has_resb ? 1.f / a.resb_slope : 1.f;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
         TC_STAMP(it, 0);
@@ -207,6 +211,35 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 const int n0 = g * 32;
                 const int ng = ny * c.ntile + n0;         // global accumulator column of this 32-wide group
                 const int ncols = min(32, c.ntile - n0);  // 16 or 32
+                // phase-2 mapping: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction
+                const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
+                const int og = (EPI == EPI_GATE) ? (ng >> 1) : ng;               // first output column
+                const int lsh = ocols == 32 ? 3 : (ocols == 16 ? 2 : 1);
+                const int lpr = 1 << lsh, rpi = 32 >> lsh;                       // lanes per row, rows per instruction; iterations = lpr
+                const int cq = (lane & (lpr - 1)) * 4, rsub = lane >> lsh;
+                const int n = og + cq;
+                float* dst0; long ldd; int acc;
+                if (EPI == EPI_SPLIT && n >= a.split) { dst0 = a.out2 + a.ocol2 + (n - a.split); ldd = a.ldo2; acc = a.accumulate2; }
+                else { dst0 = a.out + a.ocol + n; ldd = a.ldo; acc = a.accumulate; }
+                dst0 += (row0 + trow0 + rsub) * ldd;
+                const float* res0 = has_res ? (a.res + (row0 + trow0 + rsub) * a.ldres + a.rescol + n) : nullptr;
+                const __nv_bfloat16* resb0 = has_resb ? (a.resb + (row0 + trow0 + rsub) * (long)a.ldresb + a.rescol + n) : nullptr;
+                __nv_bfloat16* outb0 = a.outb ? (a.outb + (row0 + trow0 + rsub) * (long)a.ldo + a.ocol + n) : nullptr;
+                (void)res0; (void)resb0; (void)outb0;
+                const float* st0 = sE + rsub * TC_EPI_PITCH + cq;
+                // ---- prefetch: every global operand of this group's phase-2 iterations is independent of the accumulator; issuing the
+                // loads HERE puts their latency under phase 1 (r01 timeline: with the loads inside phase 2 a 128 x 128 tile spent
+                // 12-15k cycles in four serial load -> use rounds, against 2k for a store-only epilogue)
+                float4 rr[has_res ? 8 : 1], pp[ACC ? 8 : 1];
+                uint2 rb[has_resb ? 8 : 1];
+#pragma unroll
+                for (int itr = 0; itr < 8; itr++) {
+                    const int rl = itr * rpi + rsub;
+                    const bool okp = (itr < lpr) && (rl < nrows);
+                    if (has_res) { rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp) rr[itr] = *reinterpret_cast<const float4*>(res0 + (long)(itr * rpi) * a.ldres); }
+                    if (has_resb) { rb[itr] = make_uint2(0u, 0u); if (okp) rb[itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb); }
+                    if (ACC) { pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp && acc) pp[itr] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd); }
+                }
                 // ---- phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias / gate -> transpose buffer
 #pragma unroll
                 for (int hcol = 0; hcol < 32; hcol += 16) {
@@ -239,60 +272,47 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 }
                 __syncwarp();
                 if (dbg_on) { const long long t2 = clock64(); ph1 += t2 - tq; tq = t2; }
-                // ---- phase 2: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction; all global
-                // loads of 4 iterations are issued before their first use
-                const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
-                const int og = (EPI == EPI_GATE) ? (ng >> 1) : ng;               // first output column
-                const int lsh = ocols == 32 ? 3 : (ocols == 16 ? 2 : 1);
-                const int lpr = 1 << lsh, rpi = 32 >> lsh;                       // lanes per row, rows per instruction; iterations = lpr
-                const int cq = (lane & (lpr - 1)) * 4, rsub = lane >> lsh;
-                const int n = og + cq;
-                float* dst0; long ldd; int acc;
-                if (EPI == EPI_SPLIT && n >= a.split) { dst0 = a.out2 + a.ocol2 + (n - a.split); ldd = a.ldo2; acc = a.accumulate2; }
-                else { dst0 = a.out + a.ocol + n; ldd = a.ldo; acc = a.accumulate; }
-                dst0 += (row0 + trow0 + rsub) * ldd;
-                const float* res0 = has_res ? (a.res + (row0 + trow0 + rsub) * a.ldres + a.rescol + n) : nullptr;
-                const float* st0 = sE + rsub * TC_EPI_PITCH + cq;
+                // ---- phase 2: staged rows + prefetched residual / accumulate operands -> global
+                // branch-free per iteration (predicated stores only): the 8 iterations are independent and must overlap -- with an
+                // early `continue` per iteration each LDS -> math -> STG chain ran alone (270 cycles per iteration, measured)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; h2++) {
-                    if (h2 * 4 < lpr) {
-                        float4 o[4], rr[4], pp[4];
-                        bool ok[4];
+                    float4 o[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int itr = h2 * 4 + u;
-                            const int rl = itr * rpi + rsub;
-                            ok[u] = (itr < lpr) && (rl < nrows);
-                            rr[u] = make_float4(0.f, 0.f, 0.f, 0.f); pp[u] = rr[u];
-                            if (ok[u]) {
-                                if (has_res) rr[u] = *reinterpret_cast<const float4*>(res0 + (long)(itr * rpi) * a.ldres);
-                                if (EPI != EPI_GATE && EPI != EPI_SUBFROM && acc) pp[u] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd);
-                                o[u] = *reinterpret_cast<const float4*>(st0 + itr * rpi * TC_EPI_PITCH);
-                            }
+                    for (int u = 0; u < 4; u++) {
+                        const int itr = h2 * 4 + u;
+                        o[u] = *reinterpret_cast<const float4*>(st0 + min(itr, lpr - 1) * rpi * TC_EPI_PITCH);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int itr = h2 * 4 + u;
+                        const bool okp = (itr < lpr) && (itr * rpi + rsub < nrows);
+                        float4 v4 = o[u];
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_res) r4 = rr[itr];
+                        if (has_resb) {
+                            // the residual is the conv's own input, stored as the bf16 lrelu operand: invert the (monotone) lrelu
+                            const uint32_t bx = rb[itr].x, by = rb[itr].y;
+                            const float r0 = tc::bf16_lo_f(bx), r1 = tc::bf16_hi_f(bx), r2 = tc::bf16_lo_f(by), r3 = tc::bf16_hi_f(by);
+                            r4 = make_float4(fminf(r0, r0 * resb_inv), fminf(r1, r1 * resb_inv), fminf(r2, r2 * resb_inv), fminf(r3, r3 * resb_inv));
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            if (!ok[u]) continue;
-                            const int itr = h2 * 4 + u;
-                            float4 v4 = o[u];
-                            if (EPI == EPI_SUBFROM) {
-                                v4 = make_float4(rr[u].x - v4.x, rr[u].y - v4.y, rr[u].z - v4.z, rr[u].w - v4.w);
-                            } else if (EPI != EPI_GATE) {
-                                v4.x += rr[u].x; v4.y += rr[u].y; v4.z += rr[u].z; v4.w += rr[u].w;
-                                if (a.out_act == ACT_RELU) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
-                                v4.x += pp[u].x; v4.y += pp[u].y; v4.z += pp[u].z; v4.w += pp[u].w;
-                                if (a.out_div != 1.f) { v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div; }
-                                if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
-                            }
-                            if ((EPI == EPI_STORE || EPI == EPI_GATE) && a.outb) {
-                                // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
-                                const float sl = a.outb_slope;
-                                const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(v4.x, v4.x * sl), fmaxf(v4.y, v4.y * sl)),
-                                                             tc::pack_bf16(fmaxf(v4.z, v4.z * sl), fmaxf(v4.w, v4.w * sl)));
-                                *reinterpret_cast<uint2*>(a.outb + (row0 + trow0 + rsub + itr * rpi) * (long)a.ldo + a.ocol + n) = pk2;
-                            } else
+                        if (EPI == EPI_SUBFROM) {
+                            v4 = make_float4(r4.x - v4.x, r4.y - v4.y, r4.z - v4.z, r4.w - v4.w);
+                        } else if (EPI != EPI_GATE) {
+                            v4.x += r4.x; v4.y += r4.y; v4.z += r4.z; v4.w += r4.w;
+                            if (a.out_act == ACT_RELU) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+                            if (ACC) { v4.x += pp[itr].x; v4.y += pp[itr].y; v4.z += pp[itr].z; v4.w += pp[itr].w; }
+                            v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div;
+                            if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
+                        }
+                        if ((EPI == EPI_STORE || EPI == EPI_GATE) && a.outb) {
+                            // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
+                            const float sl = a.outb_slope;
+                            const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(v4.x, v4.x * sl), fmaxf(v4.y, v4.y * sl)),
+                                                         tc::pack_bf16(fmaxf(v4.z, v4.z * sl), fmaxf(v4.w, v4.w * sl)));
+                            if (okp) *reinterpret_cast<uint2*>(outb0 + (long)(itr * rpi) * a.ldo) = pk2;
+                        } else if (okp)
                             *reinterpret_cast<float4*>(dst0 + (long)(itr * rpi) * ldd) = v4;
-                        }
                     }
                 }
                 __syncwarp();
@@ -391,13 +411,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
 
     if (warp < TC_EPI_WARPS) {
         // ================= epilogue (256 threads) =================
+        const bool anyacc = a.accumulate || (a.epi == EPI_SPLIT && a.accumulate2);
+#define TC_EPI_CALL(E_, R_, A_) tc_epilogue<E_, R_, A_>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on)
         if (!c.vec) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
-        else if (a.epi == EPI_GATE) tc_epilogue<EPI_GATE>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
-        else if (a.epi == EPI_SPLIT) tc_epilogue<EPI_SPLIT>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
-        else if (a.epi == EPI_SUBFROM) tc_epilogue<EPI_SUBFROM>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
-        else tc_epilogue<EPI_STORE>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
+        else if (a.epi == EPI_GATE) TC_EPI_CALL(EPI_GATE, 0, 0);
+        else if (a.epi == EPI_SUBFROM) TC_EPI_CALL(EPI_SUBFROM, 1, 0);
+        else if (a.epi == EPI_SPLIT) { if (a.res) TC_EPI_CALL(EPI_SPLIT, 1, 1); else TC_EPI_CALL(EPI_SPLIT, 0, 1); }
+        else if (a.resb) { if (anyacc) TC_EPI_CALL(EPI_STORE, 2, 1); else TC_EPI_CALL(EPI_STORE, 2, 0); }
+        else if (a.res) { if (anyacc) TC_EPI_CALL(EPI_STORE, 1, 1); else TC_EPI_CALL(EPI_STORE, 1, 0); }
+        else { if (anyacc) TC_EPI_CALL(EPI_STORE, 0, 1); else TC_EPI_CALL(EPI_STORE, 0, 0); }
+#undef TC_EPI_CALL
     } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
-        // ================= activation loaders (256 threads) =================
+        // ================= activation loaders (192 threads) =================
         const int lt = tid - TC_EPI_WARPS * 32;
         uint32_t it = 0;
         const int items = c.rows_a * kc_total;

@@ -824,6 +824,16 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             }
             if (!mrf_on[i + 1] && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
         }
+        // unfused ResBlock2 stages (e.g. the 128-channel first stage) in bf16 mode: bf16 operand rows between the convs
+        std::vector<int> rb_bf16(A.n_ups + 2, 0);
+        for (int i = 0; i < A.n_ups; i++) {
+            const int co = chans[i + 1];
+            bool ok = h->precision == 1 && A.resblock_type == 2 && mrf_on[i + 1] == 0 && h->opts["no_stage_bf16"] == 0 && co % 16 == 0 &&
+                      h->ups[i].A.wtc && h->ups[i].B.wtc && (h->ups[i].rate * co) % 8 == 0;
+            for (int j = 0; j < A.n_rbk && ok; j++)
+                for (int c2 = 0; c2 < A.rb_ndil[j]; c2++) if (!h->rb_c1[i * A.n_rbk + j][c2].wtc) ok = false;
+            rb_bf16[i + 1] = ok;
+        }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
         for (int i = 0; i <= A.n_ups; i++)
             tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0)));
@@ -927,10 +937,10 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(X);          // v3: the stage input as bf16 lrelu rows
             if (!up_fused[i + 1]) {
                 a = base_args(U.A, cur, cur_c, 0, X, u * co, 0); a.in_act = 1; a.in_slope = 0.1f;
-                if (mrf_on[i + 1] == 3) { a.outb = Xb; a.outb_slope = 0.1f; }
+                if (mrf_on[i + 1] == 3 || rb_bf16[i + 1]) { a.outb = Xb; a.outb_slope = 0.1f; }
                 if ((rc = launch_conv(h, a, Tin, true))) return rc;
                 a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
-                if (mrf_on[i + 1] == 3) { a.outb = Xb; a.outb_slope = 0.1f; }
+                if (mrf_on[i + 1] == 3 || rb_bf16[i + 1]) { a.outb = Xb; a.outb_slope = 0.1f; }
                 if ((rc = launch_conv(h, a, Tin, true))) return rc;
             }
             if (mrf_on[i + 1] == 3) {
@@ -989,7 +999,18 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 const float* in = X;
                 for (int c = 0; c < nd; c++) {
                     const bool fin = (c == nd - 1);
-                    if (A.resblock_type == 2) {
+                    if (A.resblock_type == 2 && rb_bf16[i + 1]) {
+                        // modules.py:355-364 with bf16 operand rows between the convs: the input, the residual (recovered from
+                        // the operand, lrelu is invertible) and the intermediate x1 are 2 bytes per value; the per-resblock
+                        // results still accumulate in fp32
+                        __nv_bfloat16* inb = (c == 0) ? Xb : reinterpret_cast<__nv_bfloat16*>((c & 1) ? T1b : Ya);
+                        float* dstf = (c & 1) ? Ya : T1b;
+                        a = base_args(h->rb_c1[n][c], nullptr, 0, 0, fin ? XS : dstf, co, 0);
+                        a.xb = inb; a.ldxb = co; a.resb = inb; a.ldresb = co; a.resb_slope = 0.1f;
+                        if (fin) { a.accumulate = !first; if (last) a.out_div = (float)A.n_rbk; }
+                        else { a.outb = reinterpret_cast<__nv_bfloat16*>(dstf); a.outb_slope = 0.1f; }
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                    } else if (A.resblock_type == 2) {
                         // modules.py:355-364: x = conv_d(lrelu(x)) + x
                         float* dst = fin ? XS : ((c & 1) ? Ya : T1b);
                         a = base_args(h->rb_c1[n][c], in, co, 0, dst, co, 0); a.in_act = 1; a.in_slope = 0.1f;

@@ -32,9 +32,10 @@ def main():
     feed = {"input": x, "input_lengths": lens, "scales": np.asarray((0.667, 1.0, 0.8), np.float32)}
     sess.synthesize_packed(feed, out="none")
     print("frames", int(sess.last_lengths.sum()) // 256)
-    for idx, what in ((1, "flow pre 1x1 96->192"), (2, "flow in-layer k5 192->384 gate"), (3, "flow res-skip 1x1 192->384 split+acc"),
-                      (10, "flow post 192->96 subfrom"), (41, "dec conv_pre k7 192->256"), (42, "ups0 A"), (44, "stage1 rb k3 d1 128->128"),
-                      (49, "stage1 rb k7 d12 accumulate /3"), (50, "ups1 A 128->4*64"), (52, "ups2 A 64->2*32")):
+    for idx, what in ((2, "flow in-layer k5 192->384 gate -> bf16 acts"), (3, "flow rsr 1x1 192->192 bf16 in, fh accumulate"),
+                      (9, "flow mskip K=4x192 -> 96 subfrom"), (37, "dec conv_pre k7 192->256"), (38, "ups0 A -> bf16"),
+                      (40, "stage1 rb0 c0 k3 d1 bf16 in/res/out"), (41, "stage1 rb0 c1 k3 d2 bf16 in/res, fp32 out"),
+                      (44, "stage1 rb2 c0 k7 d3"), (45, "stage1 rb2 c1 k7 d12 accumulate /3"), (46, "ups1 A 128->4*64 -> bf16")):
         eng.set_option("conv_dbg", idx)
         sess.synthesize_packed(feed, out="none")
         buf = np.zeros((16 * 16 * 2,), np.float32)
