@@ -623,7 +623,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
             return (nabuf * c.a_bytes + nstages * c.slot_bytes + (2 * nstages + 8) * 8 + 16 + 127) / 128 * 128 + epi_bytes;
         };
         bool ok = false;
-        if (c.npieces <= TC_MAX_STAGES && res_bytes <= 72 * 1024 && total(2, c.npieces) <= limit) {
+        if (c.npieces <= TC_MAX_STAGES && total(2, c.npieces) <= limit) {     // (res_bytes up to ~120 KB: weights read once per CTA, not per tile)
             c.resident = 1; c.nstages = c.npieces; c.nabuf = 2; ok = true;
         } else {
             // widest N tile first (the activation tile is re-read once per N tile), then double-buffered
