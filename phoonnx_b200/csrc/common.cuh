@@ -31,6 +31,7 @@ struct ConvArgs {
     float* out;  int ldo;  int ocol;
     float* out2;  int ldo2;  int ocol2;  int split;  int accumulate2;   // EPI_SPLIT: n >= split -> out2[n - split]
     const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
+    const int4* tdesc;          // tcgen05 path: per 128-row tile {utterance's first row, its rows, tile's first row in it, utterance} (k_tile_desc)
     // split3 (tcgen05 path only): fp32-faithful bf16x3 product  x*w ~= xh*wh + xh*wl + xl*wh  (xh = bf16(x), xl =
     // bf16(x - xh)).  The activation tile holds a hi and a lo plane; wtc then holds 3*cin input channels per tap
     // ([wh | wl | wh]).  Used for the text side, whose output feeds ceil(exp(logw)).

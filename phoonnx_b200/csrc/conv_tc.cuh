@@ -16,6 +16,7 @@
 //   * epilogue: tcgen05.ld 32x32b (SASS LDTM) -> bias / speaker bias / residual / gate /
 //     split-accumulate / tanh -> fp32 stores.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "kernels_f32.cuh"
 
@@ -135,6 +136,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// 32 consecutive accumulator columns of this thread's TMEM lane: one instruction, one wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
 // one lane of a converged warp; ptxas knows the predicate is single-lane, so UTCHMMA / UBLKCP / UTCBAR inside the
 // elected region take their uniform-register operands directly (a plain `lane == 0` test makes it wrap EVERY such
 // instruction in an ELECT / BRA.U.ANY waterfall loop plus R2UR moves: ~100 cycles per MMA issued, measured)
@@ -172,6 +187,18 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // TMEM -> HBM drain of one 128 x 192 tile took 40-80k cycles (2100 warp-instructions per 32 x 32 sub-tile at one warp
 // per scheduler) against 6-12k for the loaders and 1-9k for the MMAs -- hence 8 + 8 warps, a lean epilogue
 // specialised per mode at compile time, and batched (independent) residual / accumulate loads.
+// one thread per 128-row tile: {first row of the utterance, its rows, first row of the tile inside it, utterance}.  The
+// kernel's roles read ONE 16-byte descriptor per tile, a tile ahead, instead of a binary search of dependent global loads
+// per role per tile (r01d ncu: 18 % of all stall samples sat on that search and the geometry loads behind it)
+__global__ void k_tile_desc(const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int rate, int ntiles, int tm,
+                            int4* __restrict__ out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    const int b = find_segment(tile_cu, B, tile);
+    const int cb0 = __ldg(cu + b), cb1 = __ldg(cu + b + 1);
+    out[tile] = make_int4(cb0 * rate, (cb1 - cb0) * rate, (tile - __ldg(tile_cu + b)) * tm, b);
+}
+
 #define TC_DBG_TILES 16
 #define TC_STAMP(it_, slot_) do { if (dbg_on && (it_) < TC_DBG_TILES) a.dbg[(it_) * 16 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
@@ -187,14 +214,17 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     const float inv_div = 1.f / a.out_div;
     constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2);
     const float resb_inv = has_resb ? 1.f / a.resb_slope : 1.f;
+    const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);   // this N tile's bias
     uint32_t it = 0;
+    int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
         TC_STAMP(it, 0);
-        const int b = find_segment(a.tile_cu, a.B, tile);
-        const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
-        const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
-        const long row0 = (long)cb0 * a.rate;
-        const int len = (cb1 - cb0) * a.rate;
+        // tile geometry: one 16-byte descriptor, fetched a tile ahead (k_tile_desc)
+        const int4 dsc = dnext;
+        if (tile + (int)gridDim.x < a.ntiles) dnext = __ldg(a.tdesc + tile + gridDim.x);
+        const int b = dsc.w, t0 = dsc.z, len = dsc.y;
+        const long row0 = (long)dsc.x;
+        const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
         TC_STAMP(it, 1);
         const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
         tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
@@ -203,8 +233,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
         const int trow0 = t0 + q * 32;                    // first time row of this warp
         const int nrows = len - trow0;                    // rows of this warp inside the utterance (<= 0: nothing to store)
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
-        const float* ur = a.utab ? (a.utab + (long)__ldg(a.uidx + b) * a.utab_ld) : nullptr;
-        long long ph1 = 0, ph2 = 0, tq = 0;
+        long long ph1 = 0, ph2 = 0, tq = 0, ph1a = 0, ph1b = 0;
         if (nrows > 0) {                                  // warp-uniform
             for (int g = hh; g < ngroups; g += 2) {
                 if (dbg_on) tq = clock64();
@@ -214,8 +243,11 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 // phase-2 mapping: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction
                 const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
                 const int og = (EPI == EPI_GATE) ? (ng >> 1) : ng;               // first output column
-                const int lsh = ocols == 32 ? 3 : (ocols == 16 ? 2 : 1);
-                const int lpr = 1 << lsh, rpi = 32 >> lsh;                       // lanes per row, rows per instruction; iterations = lpr
+                // the body is instantiated per lanes-per-row shift so that every loop bound, predicate and row stride below is a
+                // compile-time constant (r01d: ~18k warp-instructions per 128 x 128 tile with the shift as a run-time value)
+                auto group_body = [&](auto lsh_c) {
+                constexpr int lsh = decltype(lsh_c)::value;
+                constexpr int lpr = 1 << lsh, rpi = 32 >> lsh;                   // lanes per row, rows per instruction; iterations = lpr
                 const int cq = (lane & (lpr - 1)) * 4, rsub = lane >> lsh;
                 const int n = og + cq;
                 float* dst0; long ldd; int acc;
@@ -234,22 +266,33 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 uint2 rb[has_resb ? 8 : 1];
 #pragma unroll
                 for (int itr = 0; itr < 8; itr++) {
+                    if (itr >= lpr) continue;                  // compile-time
                     const int rl = itr * rpi + rsub;
-                    const bool okp = (itr < lpr) && (rl < nrows);
+                    const bool okp = rl < nrows;
                     if (has_res) { rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp) rr[itr] = *reinterpret_cast<const float4*>(res0 + (long)(itr * rpi) * a.ldres); }
                     if (has_resb) { rb[itr] = make_uint2(0u, 0u); if (okp) rb[itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb); }
                     if (ACC) { pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp && acc) pp[itr] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd); }
                 }
                 // ---- phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias / gate -> transpose buffer
+                // one 32-column TMEM load per group where the registers allow (fp32 residual + accumulate operands already
+                // hold 64 prefetch registers: those variants load 16 columns at a time)
+                if (dbg_on) { const long long t2 = clock64(); ph1a += t2 - tq; }
+                constexpr bool WIDE = !ACC;
+                float vv[WIDE ? 32 : 16];
+                if (WIDE) {
+                    if (ncols == 32) tc::tmem_ld32(trow + (uint32_t)n0, vv);      // warp-uniform
+                    else tc::tmem_ld16(trow + (uint32_t)n0, vv);
+                }
+                if (dbg_on) { const long long t2 = clock64(); ph1b += t2 - tq; }
 #pragma unroll
                 for (int hcol = 0; hcol < 32; hcol += 16) {
                     if (hcol < ncols) {
-                        float v[16];
-                        tc::tmem_ld16(trow + (uint32_t)(n0 + hcol), v);
+                        float* v = WIDE ? vv + hcol : vv;
+                        if (!WIDE) tc::tmem_ld16(trow + (uint32_t)(n0 + hcol), vv);
                         const int nc = ng + hcol;
-                        if (a.bias) {
+                        {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) { const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + nc) + k); v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w; }
+                            for (int k = 0; k < 4; k++) { const float4 bb = *reinterpret_cast<const float4*>(sBias + n0 + hcol + 4 * k); v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w; }
                         }
                         if (ur) {
 #pragma unroll
@@ -277,16 +320,18 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 // early `continue` per iteration each LDS -> math -> STG chain ran alone (270 cycles per iteration, measured)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; h2++) {
+                    if (h2 * 4 >= lpr) continue;               // compile-time
                     float4 o[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int itr = h2 * 4 + u;
-                        o[u] = *reinterpret_cast<const float4*>(st0 + min(itr, lpr - 1) * rpi * TC_EPI_PITCH);
+                        if (itr < lpr) o[u] = *reinterpret_cast<const float4*>(st0 + itr * rpi * TC_EPI_PITCH);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int itr = h2 * 4 + u;
-                        const bool okp = (itr < lpr) && (itr * rpi + rsub < nrows);
+                        if (itr >= lpr) continue;              // compile-time
+                        const bool okp = itr * rpi + rsub < nrows;
                         float4 v4 = o[u];
                         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (has_res) r4 = rr[itr];
@@ -303,7 +348,6 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                             if (a.out_act == ACT_RELU) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
                             if (ACC) { v4.x += pp[itr].x; v4.y += pp[itr].y; v4.z += pp[itr].z; v4.w += pp[itr].w; }
                             v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div;
-                            if (a.out_act == ACT_TANH) { v4.x = tanhf(v4.x); v4.y = tanhf(v4.y); v4.z = tanhf(v4.z); v4.w = tanhf(v4.w); }
                         }
                         if ((EPI == EPI_STORE || EPI == EPI_GATE) && a.outb) {
                             // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
@@ -316,10 +360,14 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                     }
                 }
                 __syncwarp();
+                };
+                if (ocols == 32) group_body(std::integral_constant<int, 3>{});
+                else if (ocols == 16) group_body(std::integral_constant<int, 2>{});
+                else group_body(std::integral_constant<int, 1>{});
                 if (dbg_on) ph2 += clock64() - tq;
             }
         }
-        if (dbg_on && it < TC_DBG_TILES) { a.dbg[it * 16 + 13] = (unsigned long long)ph1; a.dbg[it * 16 + 14] = (unsigned long long)ph2; }
+        if (dbg_on && it < TC_DBG_TILES) { a.dbg[it * 16 + 13] = (unsigned long long)ph1 | ((unsigned long long)ph1a << 20) | ((unsigned long long)ph1b << 40); a.dbg[it * 16 + 14] = (unsigned long long)ph2; }
         tc::tc_fence_before();                       // TMEM reads retired before the accumulator is handed back
         tc::mbar_arrive(bar_accempty0 + 8u * cbuf);
         TC_STAMP(it, 3);
@@ -333,11 +381,9 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
     const int ngroups = (c.ntile + 15) >> 4;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
-        const int b = find_segment(a.tile_cu, a.B, tile);
-        const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
-        const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
-        const long row0 = (long)cb0 * a.rate;
-        const int len = (cb1 - cb0) * a.rate;
+        const int4 dsc = __ldg(a.tdesc + tile);
+        const int b = dsc.w, t0 = dsc.z, len = dsc.y;
+        const long row0 = (long)dsc.x;
         const uint32_t cbuf = it % (uint32_t)c.naccbuf, cuse = it / (uint32_t)c.naccbuf;
         tc::mbar_wait(bar_accfull0 + 8u * cbuf, cuse & 1u);
         tc::tc_fence_after();
@@ -368,6 +414,10 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
     }
 }
 
+// One instantiation per epilogue variant (EPI < 0: the scalar epilogue): each gets its own register allocation and a hot loop
+// that fits the instruction cache (as ONE kernel with a run-time dispatch this was 18k SASS instructions, spilling for the
+// heaviest variant's sake and stalling on instruction fetch -- r01d ncu `no_inst`)
+template <int EPI, int RESK, int ACC>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
@@ -398,6 +448,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
         }
         tc::fence_mbar_init();
     }
+    {
+        float* sBias = reinterpret_cast<float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);
+        for (int i = tid; i < c.ntile; i += TC_THREADS) sBias[i] = a.bias ? __ldg(a.bias + ny * c.ntile + i) : 0.f;
+    }
     if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
@@ -411,29 +465,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
 
     if (warp < TC_EPI_WARPS) {
         // ================= epilogue (256 threads) =================
-        const bool anyacc = a.accumulate || (a.epi == EPI_SPLIT && a.accumulate2);
-#define TC_EPI_CALL(E_, R_, A_) tc_epilogue<E_, R_, A_>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on)
-        if (!c.vec) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
-        else if (a.epi == EPI_GATE) TC_EPI_CALL(EPI_GATE, 0, 0);
-        else if (a.epi == EPI_SUBFROM) TC_EPI_CALL(EPI_SUBFROM, 1, 0);
-        else if (a.epi == EPI_SPLIT) { if (a.res) TC_EPI_CALL(EPI_SPLIT, 1, 1); else TC_EPI_CALL(EPI_SPLIT, 0, 1); }
-        else if (a.resb) { if (anyacc) TC_EPI_CALL(EPI_STORE, 2, 1); else TC_EPI_CALL(EPI_STORE, 2, 0); }
-        else if (a.res) { if (anyacc) TC_EPI_CALL(EPI_STORE, 1, 1); else TC_EPI_CALL(EPI_STORE, 1, 0); }
-        else { if (anyacc) TC_EPI_CALL(EPI_STORE, 0, 1); else TC_EPI_CALL(EPI_STORE, 0, 0); }
-#undef TC_EPI_CALL
+        if constexpr (EPI < 0) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
+        else tc_epilogue<EPI, RESK, ACC>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
     } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= activation loaders (192 threads) =================
         const int lt = tid - TC_EPI_WARPS * 32;
         uint32_t it = 0;
         const int items = c.rows_a * kc_total;
         const int dr = TC_LOAD_THREADS / kc_total, dk = TC_LOAD_THREADS - dr * kc_total;   // advance of (r, kc) per TC_LOAD_THREADS items
+        int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
+        const int lr0 = lt / kc_total, lk0 = lt - lr0 * kc_total;          // this thread's first (row, chunk) item
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
             TC_STAMP(it, 4);
-            const int b = find_segment(a.tile_cu, a.B, tile);
-            const int t0 = (tile - __ldg(a.tile_cu + b)) * TC_M;
-            const int cb0 = __ldg(a.cu + b), cb1 = __ldg(a.cu + b + 1);
-            const long row0 = (long)cb0 * a.rate;
-            const int len = (cb1 - cb0) * a.rate;
+            const int4 dsc = dnext;
+            if (tile + (int)gridDim.x < a.ntiles) dnext = __ldg(a.tdesc + tile + gridDim.x);
+            const int t0 = dsc.z, len = dsc.y;
+            const long row0 = (long)dsc.x;
             const int tlo = -(t0 + c.min_off), thi = len - (t0 + c.min_off);      // valid tile rows: tlo <= r < thi
             for (int ks = 0; ks < a.nks; ks++) {
             const uint32_t lit = it * (uint32_t)a.nks + (uint32_t)ks;         // activation tiles are counted per (tile, K slice)
@@ -447,11 +494,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                 // tile, zero-filled outside the utterance; no registers, no conversion
                 const __nv_bfloat16* xbb = a.xb + (row0 + t0 + c.min_off) * (long)a.ldxb + a.xcol + ks * a.cin;
                 const uint32_t dA = tc::smem_u32(dstA);
+                int r2 = lr0, kc2 = lk0;
                 for (int i = lt; i < items; i += TC_LOAD_THREADS) {
-                    const int r2 = i / kc_total, kc2 = i - r2 * kc_total;
                     const bool okr = (r2 >= tlo) && (r2 < thi);
                     const __nv_bfloat16* src = xbb + (okr ? (long)r2 * a.ldxb : 0) + kc2 * 8;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dA + (uint32_t)(kc2 * c.rows_a + r2) * 16u), "l"(okr ? src : a.xb), "r"(okr ? 16u : 0u) : "memory");
+                    r2 += dr; kc2 += dk;
+                    if (kc2 >= kc_total) { kc2 -= kc_total; r2++; }
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 tc::fence_proxy_async();
@@ -461,7 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             }
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
             // flight per thread before any conversion so the load latency is paid once per batch
-            int r = lt / kc_total, kc = lt - r * kc_total;
+            int r = lr0, kc = lk0;
             for (int base = lt; base < items; base += 4 * TC_LOAD_THREADS) {
                 float4 v0[4], v1[4];
                 int rr[4], kk[4];
@@ -596,6 +645,7 @@ static inline bool conv_tc_supported(const ConvArgs& a) {
     if (a.cin % 16 || a.n % 16 || a.cin < 16 || a.n < 16) return false;
     if (a.xb ? (a.ldxb % 8 || a.xcol % 8 || a.split3) : (a.ldx % 4 || a.xcol % 4)) return false;
     if (a.epi == EPI_SPLIT && (a.split % 16)) return false;
+    if (a.out_act == ACT_TANH) return false;          // no tanh epilogue on this path (conv_post has its own kernels)
     return true;
 }
 
@@ -612,7 +662,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
     c.npieces = a.ntaps * nseg * c.cpt * (a.nks > 0 ? a.nks : 1);
     const int limit = 222 * 1024;
-    const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4;
+    const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4 + 256 * 4;      // transpose buffers + this N tile's bias
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
     if (!nt) for (int cand = 256; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { nt = cand; break; }
     for (;;) {
@@ -657,23 +707,30 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
 static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStream_t st) {
     TcCfg c;
     if (!conv_tc_plan(a, c)) return cudaErrorInvalidConfiguration;
-    static bool attr_set[64] = {false};
+    // epilogue variant (compile-time in the kernel)
+    typedef void (*KFn)(const ConvArgs, const TcCfg);
+    const bool anyacc = a.accumulate || (a.epi == EPI_SPLIT && a.accumulate2);
+    KFn fn; int vid;
+    if (!c.vec) { fn = k_conv_tc<-1, 0, 0>; vid = 0; }
+    else if (a.epi == EPI_GATE) { fn = k_conv_tc<EPI_GATE, 0, 0>; vid = 1; }
+    else if (a.epi == EPI_SUBFROM) { fn = k_conv_tc<EPI_SUBFROM, 1, 0>; vid = 2; }
+    else if (a.epi == EPI_SPLIT) { if (a.res) { fn = k_conv_tc<EPI_SPLIT, 1, 1>; vid = 3; } else { fn = k_conv_tc<EPI_SPLIT, 0, 1>; vid = 4; } }
+    else if (a.resb) { if (anyacc) { fn = k_conv_tc<EPI_STORE, 2, 1>; vid = 5; } else { fn = k_conv_tc<EPI_STORE, 2, 0>; vid = 6; } }
+    else if (a.res) { if (anyacc) { fn = k_conv_tc<EPI_STORE, 1, 1>; vid = 7; } else { fn = k_conv_tc<EPI_STORE, 1, 0>; vid = 8; } }
+    else { if (anyacc) { fn = k_conv_tc<EPI_STORE, 0, 1>; vid = 9; } else { fn = k_conv_tc<EPI_STORE, 0, 0>; vid = 10; } }
+    static bool attr_set[64][11] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (dev >= 0 && dev < 64 && !attr_set[dev][vid]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
+        attr_set[dev][vid] = true;
     }
     // resident CTAs per SM: shared memory (228 KB/SM, 1 KB reserved per CTA), registers (64K / (regs * threads)),
     // TMEM columns (512 / tmem_cols)
-    static int regs_per_thread = 0;
-    if (!regs_per_thread) {
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, k_conv_tc) == cudaSuccess && fa.numRegs > 0) regs_per_thread = fa.numRegs; else regs_per_thread = 96;
-    }
+    const int regs_per_thread = 128;            // __launch_bounds__(TC_THREADS, 1): 16 warps x 128 registers is the whole file
     int occ = (228 * 1024) / (c.smem_bytes + 1024);
     const int reg_occ = 65536 / (((regs_per_thread + 7) / 8 * 8) * TC_THREADS);
     if (occ > reg_occ) occ = reg_occ;
@@ -686,6 +743,6 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, ny);
-    k_conv_tc<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c);
+    fn<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c);
     return cudaGetLastError();
 }

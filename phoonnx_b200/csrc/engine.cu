@@ -105,7 +105,7 @@ struct vits_handle {
     cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
-    Buf audio_alt, facts_b;
+    Buf audio_alt, facts_b, tdesc_t, tdesc_c;
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
     float stage_ms[3] = {0, 0, 0};
@@ -218,7 +218,8 @@ int mkdds(vits_handle* h, std::vector<DdsP>& v, const std::string& name, int C) 
 // ------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------
-struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; const int* tx; int n64, n128, n256, nx, tmx; int B; int rate; };
+struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; const int* tx; int n64, n128, n256, nx, tmx; int B; int rate;
+               const int4* d128; };   // d128: per-128-row-tile descriptors for the tcgen05 conv kernel (make_d128)
 
 ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out, int ldo, int ocol) {
     ConvArgs a;
@@ -236,8 +237,9 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     a.split3 = 0;
     if (a.nks <= 1) { a.nks = 1; a.wtc_ks[0] = a.wtc; }
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
-        a.tile_cu = T.t128; a.ntiles = T.n128;
+        a.tile_cu = T.t128; a.ntiles = T.n128; a.tdesc = T.d128;
         if (T.n128 == 0) return 0;
+        if (!T.d128) return fail(h, VITS_E_STATE, "conv_tc: tile descriptors missing for rate %d", T.rate);
         a.dbg = nullptr;
         if (h->opts.count("conv_dbg") && (int)h->opts["conv_dbg"] == ++h->conv_counter) {
             int rc = ensure(h, h->conv_dbg, (size_t)TC_DBG_TILES * 16 * 8);
@@ -266,8 +268,9 @@ int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T
     const bool want = h->precision == 1 && h->text_tc && c.nsl > 0 && a.epi == EPI_STORE && a.ldx % 4 == 0 && a.xcol % 4 == 0;
     if (!want) return launch_conv(h, a, T, false);
     a.cu = T.cu; a.B = T.B; a.rate = T.rate;
-    a.tile_cu = T.t128; a.ntiles = T.n128;
+    a.tile_cu = T.t128; a.ntiles = T.n128; a.tdesc = T.d128;
     if (T.n128 == 0) return 0;
+    if (!T.d128) return fail(h, VITS_E_STATE, "conv_tc: tile descriptors missing for rate %d", T.rate);
     // one launch: the kernel loops over the K slices and accumulates them in TMEM
     ConvArgs s = a;
     s.split3 = 1; s.cin = c.slice_cin; s.nks = c.nsl; s.wtc = c.wtc3[0];
@@ -353,11 +356,21 @@ struct TileBuilder {
         for (auto& e : ents) if (e.rate == rate) {
             Tiles t; t.cu = dev + cu_off; t.t64 = dev + e.o64; t.t128 = dev + e.o128; t.t256 = dev + e.o256;
             t.n64 = e.n64; t.n128 = e.n128; t.n256 = e.n256; t.B = B; t.rate = rate;
-            t.tx = dev + e.ox; t.nx = e.nx; t.tmx = e.tmx; return t;
+            t.tx = dev + e.ox; t.nx = e.nx; t.tmx = e.tmx; t.d128 = nullptr; return t;
         }
         Tiles t; memset(&t, 0, sizeof t); return t;
     }
 };
+
+// expand T's 128-row tile table into per-tile descriptors at `dst` (device, T.n128 entries) on the handle's stream
+int make_d128(vits_handle* h, Tiles& T, int4* dst) {
+    T.d128 = dst;
+    if (T.n128 <= 0) return 0;
+    k_tile_desc<<<(T.n128 + 255) / 256, 256, 0, h->stream>>>(T.cu, T.t128, T.B, T.rate, T.n128, TC_M, dst);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
 
 }  // namespace
 
@@ -606,7 +619,8 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         CK(h, cudaMemcpyAsync(h->inj_dp.p, noise_dp, nb, cudaMemcpyHostToDevice, st));
         d_inj = ptr<float>(h->inj_dp);
     }
-    const Tiles T = tb.get(ptr<int>(h->tile_t), 1);
+    Tiles T = tb.get(ptr<int>(h->tile_t), 1);
+    if ((rc = ensure(h, h->tdesc_t, (size_t)std::max(T.n128, 1) * sizeof(int4))) || (rc = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc;
     const int* d_sid = ptr<int>(h->sid);
     float *x = ptr<float>(h->x), *y = ptr<float>(h->y), *qkv = ptr<float>(h->qkv), *att = ptr<float>(h->att),
           *ffn = ptr<float>(h->ffn), *stats = ptr<float>(h->stats);
@@ -849,7 +863,16 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             if ((rc = ensure(h, h->sYb, Fr * stage_elems_per_frame * 4))) return rc;
         CK(h, cudaMemcpyAsync(h->chunk_meta.p, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice, st));
         const int* meta = ptr<int>(h->chunk_meta);
-        const Tiles T1 = tb.get(meta, 1);
+        // per-rate tile descriptors for the tcgen05 conv kernel
+        std::vector<Tiles> TR(A.n_ups + 1);
+        {
+            size_t ntl = 0;
+            for (int i = 0; i <= A.n_ups; i++) { TR[i] = tb.get(meta, rates[i]); ntl += (size_t)TR[i].n128; }
+            if ((rc = ensure(h, h->tdesc_c, std::max<size_t>(ntl, 1) * sizeof(int4)))) return rc;
+            int4* dp = ptr<int4>(h->tdesc_c);
+            for (int i = 0; i <= A.n_ups; i++) { if ((rc = make_d128(h, TR[i], dp))) return rc; dp += TR[i].n128; }
+        }
+        const Tiles T1 = TR[0];
         const int* d_sid = ptr<int>(h->sid) + b_lo;
         float *P = ptr<float>(h->P), *fh = ptr<float>(h->fh), *facts = ptr<float>(h->facts), *fskip = ptr<float>(h->fskip);
         // ---- prior expansion + sampling (models.py:705-718)
@@ -927,8 +950,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         const __nv_bfloat16* cur_b = nullptr;          // previous stage's output as bf16 lrelu rows (feeds a fused ConvTranspose)
         for (int i = 0; i < A.n_ups; i++) {
             auto& U = h->ups[i];
-            const Tiles Tin = tb.get(meta, rates[i]);
-            const Tiles Tout = tb.get(meta, rates[i + 1]);
+            const Tiles Tin = TR[i];
+            const Tiles Tout = TR[i + 1];
             const int co = U.cout, u = U.rate;
             float* XS = XSab[i & 1];      // stage output; the next stage reads it while writing the other one
             // polyphase ConvTranspose1d (models.py:320-332): output row-block q holds u*co contiguous floats
@@ -1035,7 +1058,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         // ---- lrelu(0.01) -> conv_post -> tanh (models.py:364-366)
         {
-            const Tiles Tl = tb.get(meta, rates[A.n_ups]);
+            const Tiles Tl = TR[A.n_ups];
             if (Tl.n256 > 0 && !post_fused) {
                 size_t smem = (size_t)(CP_TILE + 6) * (h->post_c + 1) * sizeof(float);
                 k_conv_post<<<Tl.n256, 256, smem, st>>>(cur, h->post_c, h->post_w, Tl.cu, Tl.t256, nB, Tl.rate, 0.01f,
@@ -1163,7 +1186,8 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     int cu[2] = {0, L};
     TileBuilder tb; tb.begin(cu, 1); tb.add(1);
     CK(h, cudaMemcpy(dmeta, tb.host.data(), tb.host.size() * 4, cudaMemcpyHostToDevice));
-    const Tiles T = tb.get(dmeta, 1);
+    Tiles T = tb.get(dmeta, 1);
+    { int rc0; if ((rc0 = ensure(h, h->tdesc_t, (size_t)std::max(T.n128, 1) * sizeof(int4))) || (rc0 = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc0; }
     ConvP c; c.w = dw; c.wtc = (const __nv_bfloat16*)dwtc; c.b = db; c.cin = cin; c.n = n; c.npad = npad; c.npad16 = npad16; c.ntaps = ntaps;
     if (use_tc == 2) {
         // `wtc` holds the K slices back to back ("<n>.wtc3.0", ".1", ...), slice width as in mkconv

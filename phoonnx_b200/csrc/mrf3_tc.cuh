@@ -476,6 +476,26 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 tc::umma_commit(bar_ups);
                 MRF3_STAMP((int)itn, 21);
             };
+            // conv_post partial sums P[t][tap] of tile `itp` over its stage output sitting in sX1 (tap offset 0, N = 16).  Issued
+            // one tile LATE, between C1(0) and C1(1) of the next tile: waiting here for the final epilogue (which stages the
+            // operand) used to leave the tensor pipe idle for ~3.5k of a 19k-cycle tile (r01d timeline); now conv1(0) of the next
+            // tile runs under it.  The post accumulators alias conv1 buffer n_r - 1, whose MMAs wait for bar_post_free below.
+            auto issue_post = [&](uint32_t itp) {
+                tc::mbar_wait(bar_post_rdy, itp & 1);
+                MRF3_STAMP((int)itp, 40);
+                tc::tc_fence_after();
+                for (int bb = bb_lo; bb < bb_hi; bb++) {
+                    uint64_t ad = dhi_x1 | (uint64_t)((x116 + 128u * (uint32_t)bb) & 0x3FFF);
+                    uint64_t bd = dhi_wp | (uint64_t)(wp16 & 0x3FFF);
+#pragma unroll
+                    for (int k16 = 0; k16 < C / 16; k16++) {
+                        tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, k16 ? 1u : 0u);
+                        ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
+                    }
+                }
+                tc::umma_commit(bar_post_done);
+                MRF3_STAMP((int)itp, 41);
+            };
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
                 MRF3_STAMP((int)it, 20);
                 if (!modeU) { tc::mbar_wait(bar_in, it & 1); tc::tc_fence_after(); }
@@ -494,9 +514,12 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                             tc::mbar_wait(bar_x1, n_x1 & 1); n_x1++;                       // x1(r) staged, acc1[r] drained
                             if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
                             tc::tc_fence_after();
-                        } else if (post && r == a.nrb - 1 && it > 0) {
-                            tc::mbar_wait(bar_post_free, (it - 1) & 1);                    // conv_post accumulators (same columns) drained
-                            tc::tc_fence_after();
+                        } else if (post && it > 0) {
+                            if (r == (a.nrb > 1 ? 1 : 0)) issue_post(it - 1);              // previous tile's conv_post, behind this tile's C1(0)
+                            if (r == a.nrb - 1) {
+                                tc::mbar_wait(bar_post_free, (it - 1) & 1);                // conv_post accumulators (same columns) drained
+                                tc::tc_fence_after();
+                            }
                         }
                         MRF3_STAMP((int)it, 24 + 2 * (cv * 3 + r));
                         const int kr = a.k[r];
@@ -529,24 +552,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     }
                 }
                 if (c.resident) { s = 0; }
-                if (post) {
-                    // conv_post partial sums P[t][tap] over the stage output sitting in sX1 (tap offset 0, N = 16)
-                    tc::mbar_wait(bar_post_rdy, it & 1);
-                    MRF3_STAMP((int)it, 40);
-                    tc::tc_fence_after();
-                    for (int bb = bb_lo; bb < bb_hi; bb++) {
-                        uint64_t ad = dhi_x1 | (uint64_t)((x116 + 128u * (uint32_t)bb) & 0x3FFF);
-                        uint64_t bd = dhi_wp | (uint64_t)(wp16 & 0x3FFF);
-#pragma unroll
-                        for (int k16 = 0; k16 < C / 16; k16++) {
-                            tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, k16 ? 1u : 0u);
-                            ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
-                        }
-                    }
-                    tc::umma_commit(bar_post_done);
-                    MRF3_STAMP((int)it, 41);
-                }
             }
+            if (post && it > 0) issue_post(it - 1);          // the last tile's conv_post
         }
     } else {
         // ===================== input-row loader (warp 18): cp.async, 16 B per lane, zero fill outside the utterance =====================

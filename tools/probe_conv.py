@@ -47,7 +47,7 @@ def main():
             ev = sorted((int(st[it, s]) - t0, NAMES.get(s, str(s))) for s in range(13) if st[it, s])
             if not ev:
                 break
-            print(f" tile {it}: " + "  ".join(f"{nm}@{t}" for t, nm in ev) + f"  | epi phase1 {int(st[it, 13])} phase2 {int(st[it, 14])}")
+            print(f" tile {it}: " + "  ".join(f"{nm}@{t}" for t, nm in ev) + f"  | epi phase1 {int(st[it, 13]) & 0xFFFFF} (prefetch issued +{(int(st[it, 13]) >> 20) & 0xFFFFF}, tmem loaded +{(int(st[it, 13]) >> 40) & 0xFFFFF}, cumulative over the warp's groups) phase2 {int(st[it, 14])}")
     eng.set_option("conv_dbg", 0)
 
 
