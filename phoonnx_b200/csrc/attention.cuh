@@ -223,3 +223,273 @@ static inline bool attention_tiled_launch(const float* qkv, const float* Ek, con
     *err = cudaGetLastError();
     return true;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant (bf16 mode): the same flash-style schedule with both contractions on mma.sync.m16n8k16 as an
+// fp32-faithful bf16x3 product (the text side's precision policy):
+//     q.k^T ~= qh.kh + qh.kl + ql.kh          p.v ~= ph.vh + ph.vl + pl.vh          (xh = bf16(x), xl = bf16(x - xh))
+// with fp32 accumulation, fp32 softmax (expf), and the 9-wide relative-position band (q.Ek logits, p.Ev values) on CUDA
+// cores in fp32 exactly as above.  One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows; keys / values
+// stream through shared memory 64 at a time, split into hi / lo planes while being staged.  The accumulator fragment
+// of the score MMA is the A fragment of the value MMA, so P never leaves registers.
+// r01d: the fp32 CUDA-core kernel above ran at 13 TFLOP/s and was 9.5 % of the whole path.
+// ------------------------------------------------------------------------------------------------------------------
+#define AT2_THREADS 128
+#define AT2_PBP 12        // floats per row of the per-warp band buffer
+
+namespace at2 {
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed bf16 hi pair and the packed bf16 of the remainders
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// stage a [64 x DK] fp32 tile (rows r0.. of a [*, ld] matrix, zero beyond nvalid rows) as bf16 hi / lo planes [64][DK + 8]
+template <int DK>
+__device__ __forceinline__ void stage_split(const float* __restrict__ base, long ld, int nvalid, float scale,
+                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int tid) {
+    constexpr int P = DK + 8, D4 = DK / 4;
+    for (int idx = tid; idx < 64 * D4; idx += AT2_THREADS) {
+        const int r = idx / D4, d4 = idx - r * D4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nvalid) v = __ldg(reinterpret_cast<const float4*>(base + (long)r * ld) + d4);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        uint2 h, l;
+        split2(v.x, v.y, h.x, l.x); split2(v.z, v.w, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi + r * P + 4 * d4) = h;
+        *reinterpret_cast<uint2*>(lo + r * P + 4 * d4) = l;
+    }
+}
+}  // namespace at2
+
+static inline size_t attention_mma_smem_bytes(int dk, int nrel) {
+    return (size_t)6 * 64 * (dk + 8) * 2 + sizeof(float) * ((size_t)64 * AT_MAXREL + 2 * (size_t)nrel * dk + 4 * 16 * AT2_PBP);
+}
+
+template <int DK>
+__global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
+    const float* __restrict__ qkv, const float* __restrict__ Ek, const float* __restrict__ Ev,
+    float* __restrict__ out, const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int H, int window) {
+    constexpr int P = DK + 8;                 // bf16 elements per staged row: 16-byte segments of 8 consecutive rows hit 8 distinct bank groups
+    constexpr int NTO = DK / 8;               // output n-tiles (8 channels each)
+    extern __shared__ __align__(16) uint8_t sm_at2[];
+    __nv_bfloat16* sQh = reinterpret_cast<__nv_bfloat16*>(sm_at2);
+    __nv_bfloat16* sQl = sQh + 64 * P;
+    __nv_bfloat16* sKh = sQl + 64 * P;
+    __nv_bfloat16* sKl = sKh + 64 * P;
+    __nv_bfloat16* sVh = sKl + 64 * P;
+    __nv_bfloat16* sVl = sVh + 64 * P;
+    float* qe = reinterpret_cast<float*>(sVl + 64 * P);     // [64][AT_MAXREL]
+    const int nrel = 2 * window + 1;
+    float* Eks = qe + 64 * AT_MAXREL;                        // [nrel][DK]
+    float* Evs = Eks + nrel * DK;
+    float* sPB = Evs + nrel * DK;                            // [4 warps][16][AT2_PBP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y, tile = blockIdx.x;
+    const int b = find_segment(tile_cu, B, tile);
+    const int q0 = (tile - __ldg(tile_cu + b)) * 64;
+    const int r0 = __ldg(cu + b), T = __ldg(cu + b + 1) - r0;
+    const int ld = 3 * H;
+    const float* qbase = qkv + (long)r0 * ld + head * DK;
+    const float* kbase = qbase + H;
+    const float* vbase = qbase + 2 * H;
+    const float scale = 1.f / sqrtf((float)DK);      // attentions.py:232
+
+    at2::stage_split<DK>(qbase + (long)q0 * ld, ld, T - q0, scale, sQh, sQl, tid);
+    for (int idx = tid; idx < nrel * DK; idx += AT2_THREADS) { Eks[idx] = __ldg(Ek + idx); Evs[idx] = __ldg(Ev + idx); }
+    __syncthreads();
+    // relative-key logits of this q tile: qe[i][r] = (q_i / sqrt(dk)) . Ek[r], fp32 on the hi + lo reconstruction of q
+    for (int idx = tid; idx < 64 * nrel; idx += AT2_THREADS) {
+        const int i = idx & 63, r = idx >> 6;
+        float s = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < DK; d++) s = fmaf(__bfloat162float(sQh[i * P + d]) + __bfloat162float(sQl[i * P + d]), Eks[r * DK + d], s);
+        qe[i * AT_MAXREL + r] = s;
+    }
+
+    float o[NTO][4];
+#pragma unroll
+    for (int n = 0; n < NTO; n++) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
+    float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
+    const int mi = lane >> 3, l7 = lane & 7;
+    // ldmatrix lane addresses (bytes, relative to the plane): A = this warp's 16 query rows; B(K) = key row l7 of n-tile (mi >> 1),
+    // k half (mi & 1); B(V, transposed) = key row (mi & 1) * 8 + l7, channel block (mi >> 1)
+    const uint32_t a_off = (uint32_t)(((warp * 16 + l7 + (mi & 1) * 8) * P + (mi >> 1) * 8) * 2);
+    const uint32_t k_off = (uint32_t)((((mi >> 1) * 8 + l7) * P + (mi & 1) * 8) * 2);
+    const uint32_t v_off = (uint32_t)((((mi & 1) * 8 + l7) * P + (mi >> 1) * 8) * 2);
+    const uint32_t uQh = at2::s_u32(sQh), uQl = at2::s_u32(sQl), uKh = at2::s_u32(sKh), uKl = at2::s_u32(sKl),
+                   uVh = at2::s_u32(sVh), uVl = at2::s_u32(sVl);
+    float* pb = sPB + warp * 16 * AT2_PBP;
+
+    for (int k0 = 0; k0 < T; k0 += 64) {
+        __syncthreads();                        // the previous tile's K / V reads are done (first pass: qe is complete)
+        at2::stage_split<DK>(kbase + (long)k0 * ld, ld, T - k0, 1.f, sKh, sKl, tid);
+        at2::stage_split<DK>(vbase + (long)k0 * ld, ld, T - k0, 1.f, sVh, sVl, tid);
+        __syncthreads();
+        // ---- scores: 16 rows x 64 keys per warp
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; n++) { s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ks++) {
+            uint32_t ah[4], al[4];
+            at2::ldsm_x4(uQh + a_off + ks * 32, ah[0], ah[1], ah[2], ah[3]);
+            at2::ldsm_x4(uQl + a_off + ks * 32, al[0], al[1], al[2], al[3]);
+#pragma unroll
+            for (int np = 0; np < 4; np++) {
+                uint32_t bh[4], bl[4];
+                const uint32_t off = k_off + (uint32_t)(np * 16 * P * 2 + ks * 32);
+                at2::ldsm_x4(uKh + off, bh[0], bh[1], bh[2], bh[3]);
+                at2::ldsm_x4(uKl + off, bl[0], bl[1], bl[2], bl[3]);
+                at2::mma16816(s[2 * np], al, bh[0], bh[1]);
+                at2::mma16816(s[2 * np], ah, bl[0], bl[1]);
+                at2::mma16816(s[2 * np], ah, bh[0], bh[1]);
+                at2::mma16816(s[2 * np + 1], al, bh[2], bh[3]);
+                at2::mma16816(s[2 * np + 1], ah, bl[2], bl[3]);
+                at2::mma16816(s[2 * np + 1], ah, bh[2], bh[3]);
+            }
+        }
+        // ---- relative-key band, key mask, online softmax (fp32); thread: rows g and g + 8, keys nt * 8 + 2t + {0, 1}
+        const bool near_diag = (k0 <= q0 + 63 + window) && (k0 + 63 >= q0 - window);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int il = warp * 16 + g + 8 * h, qi = q0 + il;
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < 8; n++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = k0 + n * 8 + 2 * t + e;
+                    float v = s[n][2 * h + e];
+                    if (near_diag) {
+                        const int rel = j - qi + window;
+                        if (rel >= 0 && rel < nrel) v += qe[il * AT_MAXREL + rel];
+                    }
+                    if (j >= T) v = -INFINITY;
+                    s[n][2 * h + e] = v;
+                    tmax = fmaxf(tmax, v);
+                }
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+            const float mnew = fmaxf(mrun[h], tmax);          // finite: every key tile holds >= 1 valid key
+            const float corr = expf(mrun[h] - mnew);          // exp(-inf) = 0 on the first tile
+            float psum = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; n++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) { const float p = expf(s[n][2 * h + e] - mnew); s[n][2 * h + e] = p; psum += p; }
+            psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+            psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+            lrun[h] = lrun[h] * corr + psum;
+            mrun[h] = mnew;
+#pragma unroll
+            for (int n = 0; n < NTO; n++) { o[n][2 * h] *= corr; o[n][2 * h + 1] *= corr; }
+        }
+        // ---- relative-value band: out_i += sum_{|j-i|<=w} p_ij Ev[j-i+w]; the band entries change hands through a per-warp buffer
+        if (near_diag) {
+            for (int idx = lane; idx < 16 * AT2_PBP; idx += 32) pb[idx] = 0.f;
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int qi = q0 + warp * 16 + g + 8 * h;
+#pragma unroll
+                for (int n = 0; n < 8; n++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int rel = k0 + n * 8 + 2 * t + e - qi + window;
+                        if (rel >= 0 && rel < nrel) pb[(g + 8 * h) * AT2_PBP + rel] = s[n][2 * h + e];
+                    }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                for (int r = 0; r < nrel; r++) {
+                    const float p = pb[(g + 8 * h) * AT2_PBP + r];
+                    if (p != 0.f) {
+#pragma unroll
+                        for (int n = 0; n < NTO; n++) {
+                            const float2 ev = *reinterpret_cast<const float2*>(Evs + r * DK + n * 8 + 2 * t);
+                            o[n][2 * h] = fmaf(p, ev.x, o[n][2 * h]);
+                            o[n][2 * h + 1] = fmaf(p, ev.y, o[n][2 * h + 1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- out += p . v: the score accumulators of key n-tiles (2kk, 2kk + 1) are the A fragment of key step kk
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            uint32_t ph[4], pl[4];
+            at2::split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+            at2::split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+            at2::split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+            at2::split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int np = 0; np < NTO / 2; np++) {
+                uint32_t vh[4], vl[4];
+                const uint32_t off = v_off + (uint32_t)(kk * 16 * P * 2 + np * 32);
+                at2::ldsm_x4_t(uVh + off, vh[0], vh[1], vh[2], vh[3]);
+                at2::ldsm_x4_t(uVl + off, vl[0], vl[1], vl[2], vl[3]);
+                at2::mma16816(o[2 * np], pl, vh[0], vh[1]);
+                at2::mma16816(o[2 * np], ph, vl[0], vl[1]);
+                at2::mma16816(o[2 * np], ph, vh[0], vh[1]);
+                at2::mma16816(o[2 * np + 1], pl, vh[2], vh[3]);
+                at2::mma16816(o[2 * np + 1], ph, vl[2], vl[3]);
+                at2::mma16816(o[2 * np + 1], ph, vh[2], vh[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int qi = q0 + warp * 16 + g + 8 * h;
+        if (qi >= T) continue;
+        const float inv = 1.f / lrun[h];
+        float* orow = out + (long)(r0 + qi) * H + head * DK + 2 * t;
+#pragma unroll
+        for (int n = 0; n < NTO; n++) *reinterpret_cast<float2*>(orow + n * 8) = make_float2(o[n][2 * h] * inv, o[n][2 * h + 1] * inv);
+    }
+}
+
+// returns false when the shape is outside this kernel (caller falls back to the fp32 kernels)
+static inline bool attention_mma_launch(const float* qkv, const float* Ek, const float* Ev, float* out, const int* cu,
+                                        const int* tile_cu64, int ntiles64, int B, int H, int n_heads, int dk, int window,
+                                        cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    if ((dk != 96 && dk != 48 && dk != 64 && dk != 32) || 2 * window + 1 > AT2_PBP || 2 * window + 1 > AT_MAXREL || (3 * H) % 4 || H % 2) return false;
+    if (ntiles64 <= 0) return true;
+    const size_t smem = attention_mma_smem_bytes(dk, 2 * window + 1);
+    const dim3 grid(ntiles64, n_heads);
+#define AT2_CASE(DKV)                                                                                                 \
+    case DKV: {                                                                                                       \
+        static bool attr_done[64] = {false};                                                                          \
+        int dev = 0; cudaGetDevice(&dev);                                                                             \
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {                                                                \
+            *err = cudaFuncSetAttribute(k_rel_attention_mma<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); \
+            if (*err != cudaSuccess) return true;                                                                     \
+            attr_done[dev] = true;                                                                                    \
+        }                                                                                                             \
+        k_rel_attention_mma<DKV><<<grid, AT2_THREADS, smem, st>>>(qkv, Ek, Ev, out, cu, tile_cu64, B, H, window);     \
+        break;                                                                                                        \
+    }
+    switch (dk) {
+        AT2_CASE(96) AT2_CASE(48) AT2_CASE(64) AT2_CASE(32)
+        default: return false;
+    }
+#undef AT2_CASE
+    *err = cudaGetLastError();
+    return true;
+}

@@ -39,8 +39,12 @@ struct ConvArgs {
     // K slices (tcgen05 path): the kernel loops over nks slices of `cin` input channels each (activation columns xcol + ks * cin,
     // weights wtc_ks[ks]) and accumulates them in TMEM: one epilogue per tile, activation tiles double-buffered across slices
     int nks;  const __nv_bfloat16* wtc_ks[CONV_MAX_SLICES];
+    // per-slice tap lists (tcgen05 path, optional): slice ks uses taps toff[tap0_ks[ks] .. + ntaps_ks[ks]) (`ntaps` = the flattened
+    // total); all zero = every slice uses toff[0 .. ntaps).  Lets ONE launch sum convolutions with different kernels / dilations.
+    int ntaps_ks[CONV_MAX_SLICES];  int tap0_ks[CONV_MAX_SLICES];
     const __nv_bfloat16* xb;  int ldxb;       // tcgen05 path: the input as bf16 MMA-operand rows [rows, ldxb] (already activated) instead of fp32 `x`;
                                             // cp.async'd straight into the operand tile (xcol applies)
+    int nresb;  int resb_stride;            // > 1: the residual is the SUM of nresb such row groups, resb_stride columns apart (<= 3)
     const __nv_bfloat16* resb;  int ldresb;  float resb_slope;   // residual given as bf16 lrelu_{slope} rows: res = min(v, v / slope) (rescol applies)
     __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE / EPI_GATE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`
     unsigned long long* dbg;   // test-only phase timeline of CTA (0,0): [tile][16] clock64 stamps, or null

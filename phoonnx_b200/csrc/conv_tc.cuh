@@ -212,7 +212,8 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     float* srow = sE + lane * TC_EPI_PITCH;
     const int ngroups = (c.ntile + 31) >> 5;
     const float inv_div = 1.f / a.out_div;
-    constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2);
+    constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2 || RESK == 3);
+    constexpr int NRB = (RESK == 3) ? 3 : 1;          // bf16 residual row groups summed (RESK 3: up to three, a.nresb)
     const float resb_inv = has_resb ? 1.f / a.resb_slope : 1.f;
     const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);   // this N tile's bias
     uint32_t it = 0;
@@ -263,21 +264,27 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                 // loads HERE puts their latency under phase 1 (r01 timeline: with the loads inside phase 2 a 128 x 128 tile spent
                 // 12-15k cycles in four serial load -> use rounds, against 2k for a store-only epilogue)
                 float4 rr[has_res ? 8 : 1], pp[ACC ? 8 : 1];
-                uint2 rb[has_resb ? 8 : 1];
+                uint2 rb[NRB][has_resb ? 8 : 1];
 #pragma unroll
                 for (int itr = 0; itr < 8; itr++) {
                     if (itr >= lpr) continue;                  // compile-time
                     const int rl = itr * rpi + rsub;
                     const bool okp = rl < nrows;
                     if (has_res) { rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp) rr[itr] = *reinterpret_cast<const float4*>(res0 + (long)(itr * rpi) * a.ldres); }
-                    if (has_resb) { rb[itr] = make_uint2(0u, 0u); if (okp) rb[itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb); }
+                    if (has_resb) {
+#pragma unroll
+                        for (int j = 0; j < NRB; j++) {
+                            rb[j][itr] = make_uint2(0u, 0u);
+                            if (okp && (NRB == 1 || j < a.nresb)) rb[j][itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb + j * a.resb_stride);
+                        }
+                    }
                     if (ACC) { pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp && acc) pp[itr] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd); }
                 }
                 // ---- phase 1 (thread = TMEM lane = time row): TMEM -> registers, bias / speaker bias / gate -> transpose buffer
                 // one 32-column TMEM load per group where the registers allow (fp32 residual + accumulate operands already
                 // hold 64 prefetch registers: those variants load 16 columns at a time)
                 if (dbg_on) { const long long t2 = clock64(); ph1a += t2 - tq; }
-                constexpr bool WIDE = !ACC;
+                constexpr bool WIDE = !ACC && RESK != 3;
                 float vv[WIDE ? 32 : 16];
                 if (WIDE) {
                     if (ncols == 32) tc::tmem_ld32(trow + (uint32_t)n0, vv);      // warp-uniform
@@ -337,9 +344,12 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                         if (has_res) r4 = rr[itr];
                         if (has_resb) {
                             // the residual is the conv's own input, stored as the bf16 lrelu operand: invert the (monotone) lrelu
-                            const uint32_t bx = rb[itr].x, by = rb[itr].y;
-                            const float r0 = tc::bf16_lo_f(bx), r1 = tc::bf16_hi_f(bx), r2 = tc::bf16_lo_f(by), r3 = tc::bf16_hi_f(by);
-                            r4 = make_float4(fminf(r0, r0 * resb_inv), fminf(r1, r1 * resb_inv), fminf(r2, r2 * resb_inv), fminf(r3, r3 * resb_inv));
+#pragma unroll
+                            for (int j = 0; j < NRB; j++) {
+                                const uint32_t bx = rb[j][itr].x, by = rb[j][itr].y;
+                                const float r0 = tc::bf16_lo_f(bx), r1 = tc::bf16_hi_f(bx), r2 = tc::bf16_lo_f(by), r3 = tc::bf16_hi_f(by);
+                                r4.x += fminf(r0, r0 * resb_inv); r4.y += fminf(r1, r1 * resb_inv); r4.z += fminf(r2, r2 * resb_inv); r4.w += fminf(r3, r3 * resb_inv);
+                            }
                         }
                         if (EPI == EPI_SUBFROM) {
                             v4 = make_float4(r4.x - v4.x, r4.y - v4.y, r4.z - v4.z, r4.w - v4.w);
@@ -568,7 +578,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                 TC_STAMP(itp, 7);
                 for (int ks = 0; ks < a.nks; ks++) {
                 const __nv_bfloat16* src = a.wtc_ks[ks] + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
-                for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
+                const int nt_ks = a.ntaps_ks[0] ? a.ntaps_ks[ks] : a.ntaps;
+                for (int tapseg = 0; tapseg < nt_ks * nseg; tapseg++) {
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
                         const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
                         if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
@@ -604,11 +615,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                 TC_STAMP((int)it, 10);
                 tc::tc_fence_after();
                 const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
-                for (int tapseg = 0; tapseg < a.ntaps * nseg; tapseg++) {
+                const int nt_ks = a.ntaps_ks[0] ? a.ntaps_ks[ks] : a.ntaps;
+                const int tap0 = a.ntaps_ks[0] ? a.tap0_ks[ks] : 0;
+                for (int tapseg = 0; tapseg < nt_ks * nseg; tapseg++) {
                     const int tap = a.split3 ? tapseg / 3 : tapseg;
                     const int seg = tapseg - tap * nseg;
                     // segment 2 multiplies the lo plane, which sits kc_total chunks behind the hi plane
-                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap] + (seg == 2 ? (((uint32_t)kc_total * lbo_a) >> 4) : 0u);
+                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap0 + tap] + (seg == 2 ? (((uint32_t)kc_total * lbo_a) >> 4) : 0u);
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch, arow16 += piece_a16) {
                         const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
                         if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
@@ -660,7 +673,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     c.a_bytes = (planes * (a.cin / 8) * rows * 16 + 127) / 128 * 128;
     c.piece_ch = a.cin < TC_PIECE_CH ? a.cin : TC_PIECE_CH;
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
-    c.npieces = a.ntaps * nseg * c.cpt * (a.nks > 0 ? a.nks : 1);
+    c.npieces = (a.ntaps_ks[0] ? a.ntaps : a.ntaps * (a.nks > 0 ? a.nks : 1)) * nseg * c.cpt;
     const int limit = 222 * 1024;
     const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4 + 256 * 4;      // transpose buffers + this N tile's bias
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
@@ -715,10 +728,11 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
     else if (a.epi == EPI_GATE) { fn = k_conv_tc<EPI_GATE, 0, 0>; vid = 1; }
     else if (a.epi == EPI_SUBFROM) { fn = k_conv_tc<EPI_SUBFROM, 1, 0>; vid = 2; }
     else if (a.epi == EPI_SPLIT) { if (a.res) { fn = k_conv_tc<EPI_SPLIT, 1, 1>; vid = 3; } else { fn = k_conv_tc<EPI_SPLIT, 0, 1>; vid = 4; } }
+    else if (a.resb && a.nresb > 1) { if (anyacc || a.nresb > 3) return cudaErrorInvalidConfiguration; fn = k_conv_tc<EPI_STORE, 3, 0>; vid = 11; }
     else if (a.resb) { if (anyacc) { fn = k_conv_tc<EPI_STORE, 2, 1>; vid = 5; } else { fn = k_conv_tc<EPI_STORE, 2, 0>; vid = 6; } }
     else if (a.res) { if (anyacc) { fn = k_conv_tc<EPI_STORE, 1, 1>; vid = 7; } else { fn = k_conv_tc<EPI_STORE, 1, 0>; vid = 8; } }
     else { if (anyacc) { fn = k_conv_tc<EPI_STORE, 0, 1>; vid = 9; } else { fn = k_conv_tc<EPI_STORE, 0, 0>; vid = 10; } }
-    static bool attr_set[64][11] = {{false}};
+    static bool attr_set[64][12] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev][vid]) {

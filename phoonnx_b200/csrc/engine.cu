@@ -105,7 +105,8 @@ struct vits_handle {
     cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
-    Buf audio_alt, facts_b, tdesc_t, tdesc_c;
+    Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b;
+    std::vector<float*> rb_b2sum;     // per stage: sum over resblocks of the second conv's bias (ResBlock2; fused conv2 launch)
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
     float stage_ms[3] = {0, 0, 0};
@@ -636,7 +637,11 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
             ConvArgs a = base_args(L.qkv, x, H, 0, qkv, 3 * H, 0);
             if ((rc = launch_conv_text(h, L.qkv, a, T))) return rc;
             cudaError_t ae = cudaSuccess;
-            if (h->opts["attention_v1"] == 0 &&
+            // bf16 mode: both contractions on the tensor cores as fp32-faithful bf16x3 products; fp32 mode: CUDA cores
+            if (h->precision == 1 && h->text_tc && h->opts["attention_v1"] == 0 && h->opts["attention_fp32"] == 0 &&
+                attention_mma_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {
+                if (ae != cudaSuccess) return fail(h, VITS_E_CUDA, "attention (mma) launch: %s", cudaGetErrorString(ae));
+            } else if (h->opts["attention_v1"] == 0 &&
                 attention_tiled_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {
                 if (ae != cudaSuccess) return fail(h, VITS_E_CUDA, "attention launch: %s", cudaGetErrorString(ae));
             } else {
@@ -1273,7 +1278,7 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }

@@ -436,3 +436,32 @@ def test_synthesize_many_equals_serial_calls(lib, tmp_path_factory):
         # the session is back in blocking mode afterwards and page-locked blocks are recycled
         again, alen = b.synthesize_packed(feeds[0])              # (a new call number => new noise, new durations)
         assert again.dtype == np.float32 and again.shape == (int(alen.sum()),) and np.isfinite(again).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["x_low", "medium"])
+def test_tensor_core_attention_matches_fp32_kernel(lib, tmp_path_factory, preset):
+    """attention.cuh: the mma.sync bf16x3 kernel (bf16 mode) vs the fp32 CUDA-core kernel on the same qkv --
+    every key-tile count (T = 1 .. 256), ragged q tiles, utterances shorter than the relative window
+    (attentions.py:295-305); logw agrees to fp32 noise, so durations are identical (or exact ceil ties)."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, preset, 1)
+    rs = np.random.RandomState(33)
+    lens = np.array([256, 193, 129, 128, 65, 64, 63, 6, 5, 3, 1], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd}
+    res = {}
+    for name, opt in (("mma", 0), ("fp32", 1)):
+        sess = B200Session(p, precision="bf16")
+        sess.engine.set_option("attention_fp32", opt)
+        n0 = sess.engine.launch_count()
+        sess.synthesize_packed(feed, out="none")
+        assert sess.engine.launch_count() > n0
+        res[name] = (sess.engine.fetch("logw").copy(), sess.engine.fetch("durations").copy())
+    d = np.abs(res["mma"][0] - res["fp32"][0]).max()
+    assert d < 3e-5, d
+    bad = np.nonzero(res["mma"][1] != res["fp32"][1])[0]
+    w = np.exp(res["fp32"][0].astype(np.float64))
+    assert all(abs(w[i] - round(w[i])) < 1e-4 for i in bad), "duration mismatch that is not a ceil tie"
