@@ -554,6 +554,26 @@ int vits_finalize(vits_handle* h) {
             h->rb_c1.push_back(c1); h->rb_c2.push_back(c2);
         }
     }
+    // per stage: sum over the resblocks of the second conv's bias (ResBlock2): ONE launch sums the second convs of a stage
+    for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
+    h->rb_b2sum.assign(A.n_ups, nullptr);
+    if (A.resblock_type == 2) {
+        int chs = A.up_init;
+        for (int i = 0; i < A.n_ups; i++) {
+            chs /= 2;
+            bool ok = true;
+            for (int j = 0; j < A.n_rbk; j++) if (A.rb_ndil[j] != 2 || !h->rb_c1[i * A.n_rbk + j][1].b) ok = false;
+            if (!ok) continue;
+            const int np4 = rup(chs, 4), np16 = rup(chs, 16);
+            std::vector<float> sum(np16, 0.f), tmp(np4);
+            for (int j = 0; j < A.n_rbk; j++) {
+                CK(h, cudaMemcpy(tmp.data(), h->rb_c1[i * A.n_rbk + j][1].b, (size_t)np4 * 4, cudaMemcpyDeviceToHost));
+                for (int q = 0; q < chs; q++) sum[q] += tmp[q];
+            }
+            CK(h, cudaMalloc(&h->rb_b2sum[i], (size_t)np16 * 4));
+            CK(h, cudaMemcpy(h->rb_b2sum[i], sum.data(), (size_t)np16 * 4, cudaMemcpyHostToDevice));
+        }
+    }
     h->post_c = ch;
     if (ch > 64) return fail(h, VITS_E_INVALID, "conv_post input width %d > 64 unsupported", ch);
     if ((rc = need_f32(h, "dec.post_w", &h->post_w, (size_t)7 * ch))) return rc;
@@ -853,6 +873,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 for (int c2 = 0; c2 < A.rb_ndil[j]; c2++) if (!h->rb_c1[i * A.n_rbk + j][c2].wtc) ok = false;
             rb_bf16[i + 1] = ok;
         }
+        // ... of which: stages whose second convs run as one summed launch (needs a consumer that takes bf16 rows or fp32)
+        std::vector<int> stage_sum2(A.n_ups + 2, 0);
+        for (int i = 0; i < A.n_ups; i++) {
+            int tt = 0; bool ok = rb_bf16[i + 1] && h->opts["no_stage_sum2"] == 0 && A.n_rbk <= 3 && A.n_rbk <= CONV_MAX_SLICES && h->rb_b2sum[i] != nullptr;
+            for (int j = 0; j < A.n_rbk && ok; j++) { if (A.rb_ndil[j] != 2) ok = false; tt += A.rb_kernels[j]; }
+            // the consumer of bf16 rows is the next stage's ConvTranspose launch; a fused-ups v3 kernel also reads them; the last stage stays fp32
+            stage_sum2[i + 1] = ok && tt <= CONV_MAX_TAPS;
+        }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
         for (int i = 0; i <= A.n_ups; i++)
             tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0)));
@@ -953,6 +981,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         const float* cur = dpre; int cur_c = A.up_init;
         const __nv_bfloat16* cur_b = nullptr;          // previous stage's output as bf16 lrelu rows (feeds a fused ConvTranspose)
+        bool cur_is_b = false;                         // ... and ONLY in that form (`cur` is not valid)
         for (int i = 0; i < A.n_ups; i++) {
             auto& U = h->ups[i];
             const Tiles Tin = TR[i];
@@ -964,13 +993,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             ConvArgs a;
             __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(X);          // v3: the stage input as bf16 lrelu rows
             if (!up_fused[i + 1]) {
-                a = base_args(U.A, cur, cur_c, 0, X, u * co, 0); a.in_act = 1; a.in_slope = 0.1f;
-                if (mrf_on[i + 1] == 3 || rb_bf16[i + 1]) { a.outb = Xb; a.outb_slope = 0.1f; }
-                if ((rc = launch_conv(h, a, Tin, true))) return rc;
-                a = base_args(U.B, cur, cur_c, 0, X, u * co, (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
-                if (mrf_on[i + 1] == 3 || rb_bf16[i + 1]) { a.outb = Xb; a.outb_slope = 0.1f; }
-                if ((rc = launch_conv(h, a, Tin, true))) return rc;
+                for (int half = 0; half < 2; half++) {
+                    a = base_args(half ? U.B : U.A, cur, cur_c, 0, X, u * co, half * (u / 2) * co); a.in_act = 1; a.in_slope = 0.1f;
+                    if (cur_is_b) { a.x = nullptr; a.ldx = 0; a.in_act = 0; a.xb = cur_b; a.ldxb = cur_c; }   // already lrelu'd bf16 operand rows
+                    if (mrf_on[i + 1] == 3 || rb_bf16[i + 1]) { a.outb = Xb; a.outb_slope = 0.1f; }
+                    if ((rc = launch_conv(h, a, Tin, true))) return rc;
+                }
             }
+            bool out_is_b = false;
             if (mrf_on[i + 1] == 3) {
                 Mrf3Args& m = mrf3_args[i + 1];
                 m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
@@ -1019,6 +1049,32 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf_tc launch: %s", cudaGetErrorString(e));
                     h->launches++;
                 }
+            } else if (stage_sum2[i + 1]) {
+                // ResBlock2 stage (modules.py:355-364) in n_r + 1 launches: x1_r = x + conv_{k_r,d_r1}(lrelu x) for every resblock, written
+                // side by side as bf16 lrelu rows [rows, n_r * C]; then ONE launch sums the second convs of all resblocks in TMEM
+                // (K slices = resblocks, each with its own taps), adds sum_r x1_r recovered from the same rows and divides by n_r.
+                // No fp32 read-modify-write of the stage output, 4 epilogues instead of 6.
+                const int nr = A.n_rbk;
+                const size_t rows = (size_t)Fr * rates[i + 1];
+                if ((rc = ensure(h, h->sX1b, rows * nr * co * 2))) return rc;
+                __nv_bfloat16* X1 = ptr<__nv_bfloat16>(h->sX1b);
+                for (int j = 0; j < nr; j++) {
+                    a = base_args(h->rb_c1[i * nr + j][0], nullptr, 0, 0, T1b, nr * co, j * co);
+                    a.xb = Xb; a.ldxb = co; a.resb = Xb; a.ldresb = co; a.resb_slope = 0.1f;
+                    a.outb = X1; a.outb_slope = 0.1f;
+                    if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                }
+                a = base_args(h->rb_c1[i * nr][1], nullptr, 0, 0, XS, co, 0);
+                a.ntaps = 0;
+                for (int j = 0; j < nr; j++) {
+                    const ConvP& cv = h->rb_c1[i * nr + j][1];
+                    a.tap0_ks[j] = a.ntaps; a.ntaps_ks[j] = cv.ntaps; a.wtc_ks[j] = cv.wtc;
+                    for (int q = 0; q < cv.ntaps; q++) a.toff[a.ntaps++] = cv.toff[q];
+                }
+                a.nks = nr; a.bias = h->rb_b2sum[i]; a.out_div = (float)nr;
+                a.xb = X1; a.ldxb = nr * co; a.resb = X1; a.ldresb = nr * co; a.resb_slope = 0.1f; a.nresb = nr; a.resb_stride = co;
+                if (i + 1 < A.n_ups) { a.outb = reinterpret_cast<__nv_bfloat16*>(XS); a.outb_slope = 0.1f; out_is_b = true; }
+                if ((rc = launch_conv(h, a, Tout, true))) return rc;
             } else
             for (int j = 0; j < A.n_rbk; j++) {
                 const int n = i * A.n_rbk + j;
@@ -1060,6 +1116,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 }
             }
             cur = XS; cur_c = co; cur_b = reinterpret_cast<const __nv_bfloat16*>(XS);
+            cur_is_b = out_is_b;
         }
         // ---- lrelu(0.01) -> conv_post -> tanh (models.py:364-366)
         {
@@ -1280,6 +1337,7 @@ void vits_destroy(vits_handle* h) {
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
                    &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
+    for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);

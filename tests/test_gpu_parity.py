@@ -465,3 +465,29 @@ def test_tensor_core_attention_matches_fp32_kernel(lib, tmp_path_factory, preset
     bad = np.nonzero(res["mma"][1] != res["fp32"][1])[0]
     w = np.exp(res["fp32"][0].astype(np.float64))
     assert all(abs(w[i] - round(w[i])) < 1e-4 for i in bad), "duration mismatch that is not a ceil tie"
+
+
+@pytest.mark.parametrize("preset", ["x_low", "medium"])
+def test_summed_second_convs_equal_per_conv_launches(lib, tmp_path_factory, preset):
+    """Unfused ResBlock2 stage (the 128-channel first stage): one launch that sums the second convs of all resblocks in TMEM
+    (K slices with per-slice taps, residual = sum of the bf16 x1 rows) vs one launch per conv with fp32 accumulation of the
+    stage output -- same operand rounding, so they agree to fp32 re-association noise; ragged utterance edges included."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, preset, 1)
+    rs = np.random.RandomState(5)
+    lens = np.array([97, 3, 160, 41, 1], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
+    outs = []
+    for opt in (0, 1):
+        sess = B200Session(p, precision="bf16")
+        sess.engine.set_option("no_stage_sum2", opt)
+        n0 = sess.engine.launch_count()
+        a, alen = sess.synthesize_packed(feed)
+        outs.append((a, alen, sess.engine.launch_count() - n0))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] < outs[1][2]               # fewer launches: the summed path really ran
+    assert snr_db(outs[1][0], outs[0][0]) > 55.0, snr_db(outs[1][0], outs[0][0])
