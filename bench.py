@@ -33,6 +33,18 @@ sys.path.insert(0, ROOT)
 
 SCALES = (0.667, 1.0, 0.8)
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`, one launch over a 131072-frame chunk of this workload)
+# -- constants copied from the committed captures, not measured by this script (a number taken under a profiler is never a
+# bench value; these only say whether the kernels re-read more than the algorithm needs)
+KERNEL_TRAFFIC = {
+    "k_mrf3_tc<32>": {"bytes_per_launch": 1.074467e9 + 0.129114e9, "algorithmic_bytes_per_launch": 131072 * (64 * 64 * 2 + 256 * 4),
+                      "source": "profiles/r01d_ncu_mrf3.txt"},
+    "k_mrf3_tc<64>": {"bytes_per_launch": 1.073970e9 + 1.027093e9, "algorithmic_bytes_per_launch": 131072 * (64 * 64 * 2) * 2,
+                      "source": "profiles/r01d_ncu_mrf3.txt"},
+}
+DEC_TRAFFIC = {"bytes": None, "note": "per-kernel DRAM traffic of the two fused kernels is under roofline.kernels[].traffic; the decoder as a "
+                                      "whole is a launch family, see profiles/README.md for the per-launch dram bytes of every member"}
+
 
 def make_workload(n_utts: int, seed: int, n_vocab: int = 256):
     rs = np.random.RandomState(seed)
@@ -133,6 +145,7 @@ def main():
     ap.add_argument("--chunk-frames", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=24, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="engine option (A/B experiments), repeatable")
     args = ap.parse_args()
 
     rank, world, local = dist_env()
@@ -180,6 +193,9 @@ def main():
     from phoonnx_b200.session import B200Session
     sess = B200Session(path, device=local, precision=args.precision, max_chunk_frames=args.chunk_frames, seed=1000 * rank)
     eng = sess.engine
+    for kv in args.opt:
+        k, v = kv.split("=", 1)
+        eng.set_option(k, float(v))
     batches = scheduler.plan(lengths, 1, 0, max_ids=args.max_ids, max_utts=args.max_utts)
     feeds = []
     for bidx in batches:
@@ -216,6 +232,7 @@ def main():
     barrier()
     launches = eng.launch_count() - launches0
     stage = eng.stage_ms()
+    kern = [eng.kernel_ms(0), eng.kernel_ms(1)]       # (ms, launches, algorithmic MACs) of the two fused decoder kernels
     clocks = sampler.stop()
     # end-to-end: host ids -> host float32 audio through the session's batch call (B200Session.synthesize_many: the
     # device->host transfer of batch k overlaps the kernels of batch k+1; every result is complete when it is yielded)
@@ -263,6 +280,15 @@ def main():
     dec_flops = 2.0 * arch.dec_mac_per_frame() * frames            # this rank
     dec_tflops = dec_flops / (stage["dec"] * 1e-3) / 1e12 if stage["dec"] > 0 else 0.0
     value = audio_s / (dev_ms * 1e-3)
+    # the two fused decoder kernels on their own (events around each launch; algorithmic FLOPs = no halo, no padding)
+    kernels = []
+    for (ms, n, mac), nm in zip(kern, ("k_mrf3_tc<32>: last stage = ConvTranspose1d + 3 ResBlock2 + lrelu/conv_post/tanh in one kernel (dominant kernel)",
+                                       "k_mrf3_tc<64>: other fused multi-receptive-field stages")):
+        if n > 0 and ms > 0:
+            tf = 2.0 * mac / (ms * 1e-3) / 1e12
+            kernels.append({"name": nm, "launches": n, "ms_per_launch": ms / n, "achieved": tf, "frac": tf / peak_tf,
+                            "algorithmic_flops_per_launch": 2.0 * mac / n,
+                            "traffic": KERNEL_TRAFFIC.get(nm[:13])})
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -275,10 +301,13 @@ def main():
         "e2e": {"value": e_audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // args.steps},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": dec_tflops / peak_tf, "traffic": None,
-                     "kernel": "HiFi-GAN decoder (k_conv_tc launches + conv_post), rank 0",
+                     "frac": dec_tflops / peak_tf, "traffic": DEC_TRAFFIC["bytes"],
+                     "traffic_note": DEC_TRAFFIC["note"],
+                     "kernel": "HiFi-GAN decoder = BASELINE.json's 'decoder % of tensor-core peak': every launch between conv_pre and the "
+                               "tanh output (k_conv_tc<...> + k_mrf3_tc<64> + k_mrf3_tc<32>), rank 0, CUDA events on the engine's stream",
                      "algorithmic_flops_per_frame": 2 * arch.dec_mac_per_frame(), "dec_ms": stage["dec"],
-                     "flow_ms": stage["flow"], "text_ms": stage["text"], "peak_source": peak_src},
+                     "flow_ms": stage["flow"], "text_ms": stage["text"], "peak_source": peak_src,
+                     "kernels": kernels},
     }
     if not args.no_cpu_baseline and world == 1:
         a_s, dt, _ = cpu_baseline(path, utts, sample_idx, n_threads)

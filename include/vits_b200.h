@@ -139,6 +139,12 @@ int64_t vits_launch_count(vits_handle* h);
  * calls since the last vits_timer_start, for the roofline of the dominant kernel family. */
 int vits_stage_ms(vits_handle* h, float* text_ms, float* flow_ms, float* dec_ms);
 
+/* Device time (ms, CUDA events around the kernel launches alone), launch count and ALGORITHMIC multiply-accumulates (halo recompute
+ * and padding excluded) of one fused decoder kernel since the last vits_timer_start: which = 0 the last generator stage
+ * (ConvTranspose1d + multi-receptive-field ResBlocks + lrelu / conv_post / tanh, models.py:352-366, one kernel), 1 the other fused
+ * multi-receptive-field stages.  The measurement behind bench.py's per-kernel roofline. */
+int vits_kernel_ms(vits_handle* h, int which, float* ms, int64_t* launches, double* macs);
+
 /* Test hook: one convolution (single utterance of L rows, channel-last) through the production
  * launch path -- use_tc = 0: fp32 CUDA-core kernel, 1: tcgen05 kernel.  `out` is [L, out_cols]
  * and is read first when `accumulate` is set.  epi: 0 store, 1 gate (out_cols = n/2),

@@ -105,11 +105,14 @@ struct vits_handle {
     cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
-    Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b;
+    Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b, rowpos;
     std::vector<float*> rb_b2sum;     // per stage: sum over resblocks of the second conv's bias (ResBlock2; fused conv2 launch)
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
-    float stage_ms[3] = {0, 0, 0};
+    float stage_ms[5] = {0, 0, 0, 0, 0};      // text, flow, decoder; [3] the fused last-stage kernel alone, [4] the other fused MRF stage kernels
+    size_t open_stage = 0;
+    int64_t kern_launches[2] = {0, 0};        // launches / algorithmic MACs behind stage_ms[3], [4] (vits_kernel_ms)
+    double kern_macs[2] = {0, 0};
 };
 
 namespace {
@@ -287,9 +290,11 @@ int launch_ln(vits_handle* h, const float* in, float* out, const LnP& ln, int ro
               const DdsP* dw, const Tiles& T) {
     if (C % 32 || C > 32 * LN_MAXV) return fail(h, VITS_E_INVALID, "LayerNorm width %d unsupported (multiple of 32, <= %d)", C, 32 * LN_MAXV);
     if (rows == 0) return 0;
-    k_layernorm<<<(rows + 3) / 4, 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, C, mode,
-                                                         dw ? dw->dw_w : nullptr, dw ? dw->dw_b : nullptr,
-                                                         h->A.dp_kernel, dw ? dw->dil : 1, T.cu, T.B);
+    const int rpw = h->opts.count("ln_rpw") ? (int)h->opts["ln_rpw"] : 1;
+#define LN_LAUNCH(R_) k_layernorm<R_><<<(rows + 4 * R_ - 1) / (4 * R_), 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, C, mode, \
+                          dw ? dw->dw_w : nullptr, dw ? dw->dw_b : nullptr, h->A.dp_kernel, dw ? dw->dil : 1, ptr<int2>(h->rowpos))
+    if (rpw >= 4) LN_LAUNCH(4); else if (rpw == 2) LN_LAUNCH(2); else LN_LAUNCH(1);
+#undef LN_LAUNCH
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -315,8 +320,17 @@ void stage_begin(vits_handle* h, int stage) {
     StagePair sp; sp.a = get_event(h); sp.b = get_event(h); sp.stage = stage;
     cudaEventRecord(sp.a, h->stream);
     h->stage_events.push_back(sp);
+    h->open_stage = h->stage_events.size() - 1;
 }
-void stage_end(vits_handle* h) { cudaEventRecord(h->stage_events.back().b, h->stream); }
+void stage_end(vits_handle* h) { cudaEventRecord(h->stage_events[h->open_stage].b, h->stream); }
+// a timed span nested inside a stage (one kernel): returns its slot for sub_end
+size_t sub_begin(vits_handle* h, int stage) {
+    StagePair sp; sp.a = get_event(h); sp.b = get_event(h); sp.stage = stage;
+    cudaEventRecord(sp.a, h->stream);
+    h->stage_events.push_back(sp);
+    return h->stage_events.size() - 1;
+}
+void sub_end(vits_handle* h, size_t slot) { cudaEventRecord(h->stage_events[slot].b, h->stream); }
 void resolve_stage_events(vits_handle* h) {
     for (auto& sp : h->stage_events) {
         float ms = 0.f;
@@ -362,6 +376,16 @@ struct TileBuilder {
         Tiles t; memset(&t, 0, sizeof t); return t;
     }
 };
+
+// the fused MRF kernel with CUDA events around the kernel proper (the tile-descriptor helper launch stays outside)
+cudaError_t mrf3_launch_timed(vits_handle* h, const Mrf3Args& m, const Mrf3Cfg& c, int stage) {
+    cudaError_t e = mrf3_tiles_launch(m, c, h->stream);
+    if (e != cudaSuccess) return e;
+    const size_t slot = sub_begin(h, stage);
+    e = mrf3_kernel_launch(m, c, h->num_sms, h->stream);
+    sub_end(h, slot);
+    return e;
+}
 
 // expand T's 128-row tile table into per-tile descriptors at `dst` (device, T.n128 entries) on the handle's stream
 int make_d128(vits_handle* h, Tiles& T, int4* dst) {
@@ -642,6 +666,9 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
     }
     Tiles T = tb.get(ptr<int>(h->tile_t), 1);
     if ((rc = ensure(h, h->tdesc_t, (size_t)std::max(T.n128, 1) * sizeof(int4))) || (rc = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc;
+    if ((rc = ensure(h, h->rowpos, (size_t)R * sizeof(int2)))) return rc;
+    k_row_pos<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(T.cu, B, (int)R, ptr<int2>(h->rowpos));
+    h->launches++;
     const int* d_sid = ptr<int>(h->sid);
     float *x = ptr<float>(h->x), *y = ptr<float>(h->y), *qkv = ptr<float>(h->qkv), *att = ptr<float>(h->att),
           *ffn = ptr<float>(h->ffn), *stats = ptr<float>(h->stats);
@@ -1020,7 +1047,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 if (m.ntiles > 0) {
                     if ((rc = ensure(h, h->tdesc, (size_t)m.ntiles * sizeof(int4)))) return rc;
                     m.tdesc = ptr<int4>(h->tdesc);
-                    cudaError_t e = mrf3_launch(m, mrf3_cfg[i + 1], h->num_sms, st);
+                    const int kw = (i == A.n_ups - 1) ? 0 : 1;
+                    double mac = 0.0;
+                    for (int j = 0; j < A.n_rbk; j++) mac += 2.0 * A.rb_kernels[j] * co * co;
+                    mac *= rates[i + 1];
+                    if (up_fused[i + 1]) mac += (double)rates[i] * U.A.cin * co * (2 * u);
+                    if (m.post_w) mac += (double)rates[i + 1] * co * 7;
+                    h->kern_macs[kw] += mac * Fr; h->kern_launches[kw]++;
+                    cudaError_t e = mrf3_launch_timed(h, m, mrf3_cfg[i + 1], 3 + kw);
                     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf3 launch: %s", cudaGetErrorString(e));
                     h->launches += 2;
                 }
@@ -1196,7 +1230,8 @@ int vits_timer_start(vits_handle* h) {
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->stream));
     resolve_stage_events(h);
-    h->stage_ms[0] = h->stage_ms[1] = h->stage_ms[2] = 0.f;
+    for (float& v : h->stage_ms) v = 0.f;
+    h->kern_launches[0] = h->kern_launches[1] = 0; h->kern_macs[0] = h->kern_macs[1] = 0.0;
     CK(h, cudaEventRecord(h->ev_t0, h->stream));
     return VITS_OK;
 }
@@ -1221,6 +1256,18 @@ int vits_stage_ms(vits_handle* h, float* text_ms, float* flow_ms, float* dec_ms)
     if (text_ms) *text_ms = h->stage_ms[0];
     if (flow_ms) *flow_ms = h->stage_ms[1];
     if (dec_ms) *dec_ms = h->stage_ms[2];
+    return VITS_OK;
+}
+
+int vits_kernel_ms(vits_handle* h, int which, float* ms, int64_t* launches, double* macs) {
+    if (!h || which < 0 || which > 1) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    resolve_stage_events(h);
+    if (ms) *ms = h->stage_ms[3 + which];
+    if (launches) *launches = h->kern_launches[which];
+    if (macs) *macs = h->kern_macs[which];
     return VITS_OK;
 }
 
@@ -1335,7 +1382,7 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
     for (auto e : h->event_pool) cudaEventDestroy(e);

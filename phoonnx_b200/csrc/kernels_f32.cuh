@@ -234,55 +234,99 @@ __global__ void __launch_bounds__(128) k_rel_attention(const float* __restrict__
 #define LN_MAXV 8
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
+// per row of the packed batch: {position inside its utterance, utterance length}; built once per vits_prepare so that the
+// per-row kernels below need no binary search over the utterance table (10 dependent L2 loads per warp, r01e profile)
+__global__ void k_row_pos(const int* __restrict__ cu, int B, int rows, int2* __restrict__ out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int b = find_segment(cu, B, row);
+    const int r0 = __ldg(cu + b);
+    out[row] = make_int2(row - r0, __ldg(cu + b + 1) - r0);
+}
+
+// LN_RPW rows per warp: that many independent load -> reduce -> store chains in flight
+template <int LN_RPW>
 __global__ void __launch_bounds__(128) k_layernorm(const float* __restrict__ in, float* __restrict__ out,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                    int rows, int C, int mode,
                                                    const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                   int dw_k, int dw_dil, const int* __restrict__ cu, int B) {
+                                                   int dw_k, int dw_dil, const int2* __restrict__ rowpos) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + warp;
-    if (row >= rows) return;
+    const int row0 = (blockIdx.x * 4 + warp) * LN_RPW;
+    if (row0 >= rows) return;
     const int nv = C >> 5;
-    float v[LN_MAXV];
+    float v[LN_RPW][LN_MAXV], prev[LN_RPW][LN_MAXV];
     if (mode == 1) {
-        const int b = find_segment(cu, B, row);
-        const int r0 = __ldg(cu + b), T = __ldg(cu + b + 1) - r0;
-        const int t = row - r0;
 #pragma unroll
-        for (int m = 0; m < LN_MAXV; m++) {
-            if (m < nv) {
-                const int c = lane + 32 * m;
-                float acc = __ldg(dw_b + c);
-                for (int k = 0; k < dw_k; k++) {
-                    const int tt = t + (k - dw_k / 2) * dw_dil;
-                    if (tt >= 0 && tt < T) acc = fmaf(__ldg(dw_w + k * C + c), in[(long)(r0 + tt) * C + c], acc);
+        for (int r = 0; r < LN_RPW; r++) {
+            const int row = min(row0 + r, rows - 1);
+            const int2 rp = __ldg(rowpos + row);
+            const int t = rp.x, T = rp.y;
+#pragma unroll
+            for (int m = 0; m < LN_MAXV; m++) {
+                if (m < nv) {
+                    const int c = lane + 32 * m;
+                    float acc = __ldg(dw_b + c);
+                    for (int k = 0; k < dw_k; k++) {
+                        const int off = (k - dw_k / 2) * dw_dil, tt = t + off;
+                        if (tt >= 0 && tt < T) acc = fmaf(__ldg(dw_w + k * C + c), in[(long)(row + off) * C + c], acc);
+                    }
+                    v[r][m] = acc;
                 }
-                v[m] = acc;
             }
         }
     } else {
 #pragma unroll
-        for (int m = 0; m < LN_MAXV; m++)
-            if (m < nv) v[m] = in[(long)row * C + lane + 32 * m];
+        for (int r = 0; r < LN_RPW; r++) {
+            const int row = min(row0 + r, rows - 1);
+#pragma unroll
+            for (int m = 0; m < LN_MAXV; m++)
+                if (m < nv) {
+                    v[r][m] = in[(long)row * C + lane + 32 * m];
+                    if (mode == 2) prev[r][m] = out[(long)row * C + lane + 32 * m];
+                }
+        }
     }
-    float s = 0.f;
+    float mean[LN_RPW], rstd[LN_RPW];
 #pragma unroll
-    for (int m = 0; m < LN_MAXV; m++) if (m < nv) s += v[m];
-    const float mean = warp_sum(s) / (float)C;
-    float q = 0.f;
+    for (int r = 0; r < LN_RPW; r++) {
+        float s = 0.f;
 #pragma unroll
-    for (int m = 0; m < LN_MAXV; m++) if (m < nv) { const float d = v[m] - mean; q = fmaf(d, d, q); }
-    const float var = warp_sum(q) / (float)C;
-    const float rstd = 1.f / sqrtf(var + 1e-5f);
+        for (int m = 0; m < LN_MAXV; m++) if (m < nv) s += v[r][m];
+        mean[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < LN_RPW; r++) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+    for (int r = 0; r < LN_RPW; r++) {
+        mean[r] /= (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int m = 0; m < LN_MAXV; m++) if (m < nv) { const float d = v[r][m] - mean[r]; q = fmaf(d, d, q); }
+        rstd[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < LN_RPW; r++) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < LN_RPW; r++) rstd[r] = 1.f / sqrtf(rstd[r] / (float)C + 1e-5f);
 #pragma unroll
     for (int m = 0; m < LN_MAXV; m++) {
         if (m < nv) {
             const int c = lane + 32 * m;
-            float y = (v[m] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-            if (mode != 0) y = gelu_erf(y);
-            float* dst = out + (long)row * C + c;
-            if (mode == 2) y += *dst;
-            *dst = y;
+            const float gm = __ldg(gamma + c), bt = __ldg(beta + c);
+#pragma unroll
+            for (int r = 0; r < LN_RPW; r++) {
+                if (row0 + r < rows) {
+                    float y = (v[r][m] - mean[r]) * rstd[r] * gm + bt;
+                    if (mode != 0) y = gelu_erf(y);
+                    if (mode == 2) y += prev[r][m];
+                    out[(long)(row0 + r) * C + c] = y;
+                }
+            }
         }
     }
 }

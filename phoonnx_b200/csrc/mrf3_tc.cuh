@@ -687,14 +687,26 @@ static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int
     int gx = num_sms;                       // one persistent CTA per SM (TMEM: 512 columns each)
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) return cudaSuccess;
-    k_mrf2_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
-                                                         const_cast<int4*>(a.tdesc));
     k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c);
     return cudaGetLastError();
 }
 
-static inline cudaError_t mrf3_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+// the per-tile descriptors the kernel reads (launched separately so that the kernel proper can be timed alone)
+static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c, cudaStream_t st) {
+    if (a.ntiles < 1) return cudaSuccess;
+    k_mrf2_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
+                                                         const_cast<int4*>(a.tdesc));
+    return cudaGetLastError();
+}
+
+static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
     if (a.C == 32) return mrf3_launch_t<32>(a, c, num_sms, st);
     if (a.C == 64) return mrf3_launch_t<64>(a, c, num_sms, st);
     return cudaErrorInvalidConfiguration;
+}
+
+static inline cudaError_t mrf3_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+    cudaError_t e = mrf3_tiles_launch(a, c, st);
+    if (e != cudaSuccess) return e;
+    return mrf3_kernel_launch(a, c, num_sms, st);
 }

@@ -96,6 +96,7 @@ def load_library(path: Optional[str] = None):
     lib.vits_timer_start.argtypes = [H]
     lib.vits_timer_stop.argtypes = [H, C.POINTER(C.c_float)]
     lib.vits_stage_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.vits_kernel_ms.argtypes = [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     lib.vits_launch_count.argtypes = [H]
     lib.vits_launch_count.restype = C.c_int64
     lib.vits_last_error.argtypes = [H]
@@ -106,7 +107,7 @@ def load_library(path: Optional[str] = None):
     lib.vits_host_free.argtypes = [C.c_void_p]
     lib.vits_wait_output.argtypes = [H, C.c_int]
     for fn in ("vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare", "vits_decode",
-               "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_host_alloc", "vits_host_free", "vits_wait_output"):
+               "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_host_alloc", "vits_host_free", "vits_wait_output"):
         getattr(lib, fn).restype = C.c_int
     if path is None:
         _lib = lib
@@ -115,7 +116,7 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = (
     "vits_abi_version", "vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare",
-    "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_launch_count",
+    "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_launch_count",
     "vits_last_error", "vits_destroy", "vits_host_alloc", "vits_host_free", "vits_wait_output",
 )
 
@@ -306,6 +307,12 @@ class Engine:
         a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
         self._check(self.lib.vits_stage_ms(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"text": a.value, "flow": b.value, "dec": c.value}
+
+    def kernel_ms(self, which: int):
+        """(device ms, launches, algorithmic MACs) of one fused decoder kernel since timer_start(): 0 = last stage, 1 = the others."""
+        ms, n, mac = C.c_float(), C.c_int64(), C.c_double()
+        self._check(self.lib.vits_kernel_ms(self._h, which, C.byref(ms), C.byref(n), C.byref(mac)))
+        return float(ms.value), int(n.value), float(mac.value)
 
     def launch_count(self) -> int:
         return int(self.lib.vits_launch_count(self._h))
