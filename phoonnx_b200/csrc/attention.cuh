@@ -283,16 +283,47 @@ __device__ __forceinline__ void stage_split(const float* __restrict__ base, long
         *reinterpret_cast<uint2*>(lo + r * P + 4 * d4) = l;
     }
 }
+// two tiles (K and V) with every load of both in flight before the first conversion: one memory round trip per key tile
+template <int DK>
+__device__ __forceinline__ void stage_split2(const float* __restrict__ base_a, const float* __restrict__ base_b, long ld, int nvalid,
+                                             __nv_bfloat16* __restrict__ hi_a, __nv_bfloat16* __restrict__ lo_a,
+                                             __nv_bfloat16* __restrict__ hi_b, __nv_bfloat16* __restrict__ lo_b, int tid) {
+    constexpr int P = DK + 8, D4 = DK / 4;
+    constexpr int NIT = 64 * D4 / AT2_THREADS;
+    float4 va[NIT], vb[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int idx = tid + it * AT2_THREADS;
+        const int r = idx / D4, d4 = idx - r * D4;
+        va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
+        if (r < nvalid) {
+            va[it] = __ldg(reinterpret_cast<const float4*>(base_a + (long)r * ld) + d4);
+            vb[it] = __ldg(reinterpret_cast<const float4*>(base_b + (long)r * ld) + d4);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int idx = tid + it * AT2_THREADS;
+        const int r = idx / D4, d4 = idx - r * D4;
+        uint2 h, l;
+        split2(va[it].x, va[it].y, h.x, l.x); split2(va[it].z, va[it].w, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi_a + r * P + 4 * d4) = h;
+        *reinterpret_cast<uint2*>(lo_a + r * P + 4 * d4) = l;
+        split2(vb[it].x, vb[it].y, h.x, l.x); split2(vb[it].z, vb[it].w, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi_b + r * P + 4 * d4) = h;
+        *reinterpret_cast<uint2*>(lo_b + r * P + 4 * d4) = l;
+    }
+}
 }  // namespace at2
 
 static inline size_t attention_mma_smem_bytes(int dk, int nrel) {
-    return (size_t)6 * 64 * (dk + 8) * 2 + sizeof(float) * ((size_t)64 * AT_MAXREL + 2 * (size_t)nrel * dk + 4 * 16 * AT2_PBP);
+    return (size_t)(6 * 64 + 2 * 16) * (dk + 8) * 2 + sizeof(float) * ((size_t)64 * AT_MAXREL + (size_t)nrel * dk + 4 * 16 * AT2_PBP);
 }
 
 template <int DK>
 __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
     const float* __restrict__ qkv, const float* __restrict__ Ek, const float* __restrict__ Ev,
-    float* __restrict__ out, const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int H, int window) {
+    float* __restrict__ out, const int4* __restrict__ tdesc64, int H, int window) {
     constexpr int P = DK + 8;                 // bf16 elements per staged row: 16-byte segments of 8 consecutive rows hit 8 distinct bank groups
     constexpr int NTO = DK / 8;               // output n-tiles (8 channels each)
     extern __shared__ __align__(16) uint8_t sm_at2[];
@@ -302,17 +333,17 @@ __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
     __nv_bfloat16* sKl = sKh + 64 * P;
     __nv_bfloat16* sVh = sKl + 64 * P;
     __nv_bfloat16* sVl = sVh + 64 * P;
-    float* qe = reinterpret_cast<float*>(sVl + 64 * P);     // [64][AT_MAXREL]
+    __nv_bfloat16* sEh = sVl + 64 * P;                       // relative-key embeddings, bf16 hi / lo planes [16][P] (rows >= nrel zero)
+    __nv_bfloat16* sEl = sEh + 16 * P;
+    float* qe = reinterpret_cast<float*>(sEl + 16 * P);      // [64][AT_MAXREL]
     const int nrel = 2 * window + 1;
-    float* Eks = qe + 64 * AT_MAXREL;                        // [nrel][DK]
-    float* Evs = Eks + nrel * DK;
+    float* Evs = qe + 64 * AT_MAXREL;                        // [nrel][DK]
     float* sPB = Evs + nrel * DK;                            // [4 warps][16][AT2_PBP]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int head = blockIdx.y, tile = blockIdx.x;
-    const int b = find_segment(tile_cu, B, tile);
-    const int q0 = (tile - __ldg(tile_cu + b)) * 64;
-    const int r0 = __ldg(cu + b), T = __ldg(cu + b + 1) - r0;
+    const int4 dsc = __ldg(tdesc64 + tile);          // {utterance's first row, its rows, tile's first row in it, utterance} (k_tile_desc)
+    const int q0 = dsc.z, r0 = dsc.x, T = dsc.y;
     const int ld = 3 * H;
     const float* qbase = qkv + (long)r0 * ld + head * DK;
     const float* kbase = qbase + H;
@@ -320,16 +351,17 @@ __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
     const float scale = 1.f / sqrtf((float)DK);      // attentions.py:232
 
     at2::stage_split<DK>(qbase + (long)q0 * ld, ld, T - q0, scale, sQh, sQl, tid);
-    for (int idx = tid; idx < nrel * DK; idx += AT2_THREADS) { Eks[idx] = __ldg(Ek + idx); Evs[idx] = __ldg(Ev + idx); }
-    __syncthreads();
-    // relative-key logits of this q tile: qe[i][r] = (q_i / sqrt(dk)) . Ek[r], fp32 on the hi + lo reconstruction of q
-    for (int idx = tid; idx < 64 * nrel; idx += AT2_THREADS) {
-        const int i = idx & 63, r = idx >> 6;
-        float s = 0.f;
-#pragma unroll 8
-        for (int d = 0; d < DK; d++) s = fmaf(__bfloat162float(sQh[i * P + d]) + __bfloat162float(sQl[i * P + d]), Eks[r * DK + d], s);
-        qe[i * AT_MAXREL + r] = s;
+    for (int idx = tid; idx < nrel * DK; idx += AT2_THREADS) Evs[idx] = __ldg(Ev + idx);
+    for (int idx = tid; idx < 16 * (DK / 2); idx += AT2_THREADS) {
+        const int r = idx / (DK / 2), d2 = idx - r * (DK / 2);
+        float2 e = make_float2(0.f, 0.f);
+        if (r < nrel) e = __ldg(reinterpret_cast<const float2*>(Ek + r * DK) + d2);
+        uint32_t eh, el;
+        at2::split2(e.x, e.y, eh, el);
+        *reinterpret_cast<uint32_t*>(sEh + r * P + 2 * d2) = eh;
+        *reinterpret_cast<uint32_t*>(sEl + r * P + 2 * d2) = el;
     }
+    __syncthreads();
 
     float o[NTO][4];
 #pragma unroll
@@ -344,11 +376,32 @@ __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
     const uint32_t uQh = at2::s_u32(sQh), uQl = at2::s_u32(sQl), uKh = at2::s_u32(sKh), uKl = at2::s_u32(sKl),
                    uVh = at2::s_u32(sVh), uVl = at2::s_u32(sVl);
     float* pb = sPB + warp * 16 * AT2_PBP;
+    // relative-key logits of this warp's 16 query rows: qe[i][r] = (q_i / sqrt(dk)) . Ek[r] -- one more bf16x3 product (the 16 padded
+    // "keys" are the relative embeddings); rows of qe are only ever read by the warp that wrote them
+    {
+        float c2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const uint32_t uEh = at2::s_u32(sEh), uEl = at2::s_u32(sEl);
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ks++) {
+            uint32_t ah[4], al[4], bh[4], bl[4];
+            at2::ldsm_x4(uQh + a_off + ks * 32, ah[0], ah[1], ah[2], ah[3]);
+            at2::ldsm_x4(uQl + a_off + ks * 32, al[0], al[1], al[2], al[3]);
+            at2::ldsm_x4(uEh + k_off + ks * 32, bh[0], bh[1], bh[2], bh[3]);
+            at2::ldsm_x4(uEl + k_off + ks * 32, bl[0], bl[1], bl[2], bl[3]);
+            at2::mma16816(c2[0], al, bh[0], bh[1]); at2::mma16816(c2[0], ah, bl[0], bl[1]); at2::mma16816(c2[0], ah, bh[0], bh[1]);
+            at2::mma16816(c2[1], al, bh[2], bh[3]); at2::mma16816(c2[1], ah, bl[2], bl[3]); at2::mma16816(c2[1], ah, bh[2], bh[3]);
+        }
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                *reinterpret_cast<float2*>(qe + (warp * 16 + g + 8 * h) * AT_MAXREL + n * 8 + 2 * t) = make_float2(c2[n][2 * h], c2[n][2 * h + 1]);
+        __syncwarp();
+    }
 
     for (int k0 = 0; k0 < T; k0 += 64) {
         __syncthreads();                        // the previous tile's K / V reads are done (first pass: qe is complete)
-        at2::stage_split<DK>(kbase + (long)k0 * ld, ld, T - k0, 1.f, sKh, sKl, tid);
-        at2::stage_split<DK>(vbase + (long)k0 * ld, ld, T - k0, 1.f, sVh, sVl, tid);
+        at2::stage_split2<DK>(kbase + (long)k0 * ld, vbase + (long)k0 * ld, ld, T - k0, sKh, sKl, sVh, sVl, tid);
         __syncthreads();
         // ---- scores: 16 rows x 64 keys per warp
         float s[8][4];
@@ -476,9 +529,8 @@ __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
 }
 
 // returns false when the shape is outside this kernel (caller falls back to the fp32 kernels)
-static inline bool attention_mma_launch(const float* qkv, const float* Ek, const float* Ev, float* out, const int* cu,
-                                        const int* tile_cu64, int ntiles64, int B, int H, int n_heads, int dk, int window,
-                                        cudaStream_t st, cudaError_t* err) {
+static inline bool attention_mma_launch(const float* qkv, const float* Ek, const float* Ev, float* out, const int4* tdesc64,
+                                        int ntiles64, int H, int n_heads, int dk, int window, cudaStream_t st, cudaError_t* err) {
     *err = cudaSuccess;
     if ((dk != 96 && dk != 48 && dk != 64 && dk != 32) || 2 * window + 1 > AT2_PBP || 2 * window + 1 > AT_MAXREL || (3 * H) % 4 || H % 2) return false;
     if (ntiles64 <= 0) return true;
@@ -493,7 +545,7 @@ static inline bool attention_mma_launch(const float* qkv, const float* Ek, const
             if (*err != cudaSuccess) return true;                                                                     \
             attr_done[dev] = true;                                                                                    \
         }                                                                                                             \
-        k_rel_attention_mma<DKV><<<grid, AT2_THREADS, smem, st>>>(qkv, Ek, Ev, out, cu, tile_cu64, B, H, window);     \
+        k_rel_attention_mma<DKV><<<grid, AT2_THREADS, smem, st>>>(qkv, Ek, Ev, out, tdesc64, H, window);              \
         break;                                                                                                        \
     }
     switch (dk) {

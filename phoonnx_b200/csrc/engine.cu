@@ -665,7 +665,11 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         d_inj = ptr<float>(h->inj_dp);
     }
     Tiles T = tb.get(ptr<int>(h->tile_t), 1);
-    if ((rc = ensure(h, h->tdesc_t, (size_t)std::max(T.n128, 1) * sizeof(int4))) || (rc = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc;
+    if ((rc = ensure(h, h->tdesc_t, (size_t)std::max(T.n128 + T.n64, 1) * sizeof(int4))) || (rc = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc;
+    if (T.n64 > 0) {     // 64-row tile descriptors (attention q tiles) behind the 128-row ones
+        k_tile_desc<<<(T.n64 + 255) / 256, 256, 0, st>>>(T.cu, T.t64, T.B, 1, T.n64, 64, ptr<int4>(h->tdesc_t) + T.n128);
+        h->launches++;
+    }
     if ((rc = ensure(h, h->rowpos, (size_t)R * sizeof(int2)))) return rc;
     k_row_pos<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(T.cu, B, (int)R, ptr<int2>(h->rowpos));
     h->launches++;
@@ -686,7 +690,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
             cudaError_t ae = cudaSuccess;
             // bf16 mode: both contractions on the tensor cores as fp32-faithful bf16x3 products; fp32 mode: CUDA cores
             if (h->precision == 1 && h->text_tc && h->opts["attention_v1"] == 0 && h->opts["attention_fp32"] == 0 &&
-                attention_mma_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {
+                attention_mma_launch(qkv, L.rel_k, L.rel_v, att, ptr<int4>(h->tdesc_t) + T.n128, T.n64, H, A.n_heads, dk, A.window, st, &ae)) {
                 if (ae != cudaSuccess) return fail(h, VITS_E_CUDA, "attention (mma) launch: %s", cudaGetErrorString(ae));
             } else if (h->opts["attention_v1"] == 0 &&
                 attention_tiled_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {

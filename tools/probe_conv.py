@@ -34,8 +34,9 @@ def main():
     print("frames", int(sess.last_lengths.sum()) // 256)
     for idx, what in ((2, "flow in-layer k5 192->384 gate -> bf16 acts"), (3, "flow rsr 1x1 192->192 bf16 in, fh accumulate"),
                       (9, "flow mskip K=4x192 -> 96 subfrom"), (37, "dec conv_pre k7 192->256"), (38, "ups0 A -> bf16"),
-                      (40, "stage1 rb0 c0 k3 d1 bf16 in/res/out"), (41, "stage1 rb0 c1 k3 d2 bf16 in/res, fp32 out"),
-                      (44, "stage1 rb2 c0 k7 d3"), (45, "stage1 rb2 c1 k7 d12 accumulate /3"), (46, "ups1 A 128->4*64 -> bf16")):
+                      (40, "stage1 rb0 conv1 k3 d1 bf16 in/res -> bf16 x1 rows"), (42, "stage1 rb2 conv1 k7 d3 -> bf16 x1 rows"),
+                      (43, "stage1 summed second convs: 3 K slices, 15 taps, 3 bf16 residuals -> bf16 rows"),
+                      (44, "ups1 A 128->4*64, bf16 rows in -> bf16")):
         eng.set_option("conv_dbg", idx)
         sess.synthesize_packed(feed, out="none")
         buf = np.zeros((16 * 16 * 2,), np.float32)
