@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import tempfile
 import threading
@@ -54,51 +53,64 @@ def make_workload(n_utts: int, seed: int, n_vocab: int = 256):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons of this rank's GPU during the timed region (B200_PROFILING.md's clocks line), read through NVML
+    in a thread of this process.  (A polling `nvidia-smi -lms` child per rank re-enumerates every GPU of the box on each sample and
+    contends for the driver lock with the kernel launches: with two ranks it slowed the timed loop 2.4x -- r01 2-GPU run.)"""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
-    def __init__(self, device: int):
-        self.rows = []
-        self.proc = None
-        self.device = device
+    def __init__(self, device: int, period_s: float = 0.1):
+        self.device, self.period = device, period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-aware: NVML enumerates physical GPUs
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.device
+            if vis:
+                ent = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.device < len(ent) and ent[self.device].isdigit():
+                    phys = int(ent[self.device])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:          # no NVML: say so in the JSON instead of guessing
+            self.err = f"NVML unavailable: {e}"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.strip().split(",")])
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as e:
+                self.err = str(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        busy = [s for s in sm if s > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        busy = [s for s in self.sm if s > 0]
+        out = {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+               "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, this process, 100 ms period"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def dist_env():
@@ -218,6 +230,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # settle phase (untimed, before the W warm-up steps): one end-to-end pass and one device pass so that every buffer has its
+    # final size, every kernel module is loaded and the page-locked result pool exists before anything is counted -- the first
+    # CUDA process on a fresh box otherwise showed host-side gaps between launches well into the timed steps (r01 2-GPU runs)
+    for _ in sess.synthesize_many(feeds, out="f32"):
+        pass
+    one_step("none")
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         one_step("none")
     barrier()
@@ -296,7 +315,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "precision": args.precision, "l2_policy": "inputs larger than L2 (per-step activations >> 126 MB)",
                    "frames_per_step_per_gpu": frames // args.steps, "ids_per_step_per_gpu": int(lengths.sum()),
-                   "device_batches": len(feeds), "chunk_frames": args.chunk_frames, "x_realtime": value},
+                   "device_batches": len(feeds), "chunk_frames": args.chunk_frames, "x_realtime": value,
+                   "device_busy_ms_per_step": (stage["text"] + stage["flow"] + stage["dec"]) / args.steps},
         "clocks": clocks,
         "e2e": {"value": e_audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // args.steps},
         "gpu_launches": int(launches_all),

@@ -491,3 +491,34 @@ def test_summed_second_convs_equal_per_conv_launches(lib, tmp_path_factory, pres
     assert np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] < outs[1][2]               # fewer launches: the summed path really ran
     assert snr_db(outs[1][0], outs[0][0]) > 55.0, snr_db(outs[1][0], outs[0][0])
+
+
+@pytest.mark.parametrize("preset,B,tlo,thi,sr", [("x_low", 32, 64, 257, 16000), ("high", 16, 512, 513, 22050)])
+def test_baseline_configs_2_and_4_full_size(lib, tmp_path_factory, preset, B, tlo, thi, sr):
+    """BASELINE configs[1] (x_low, batch of 32 utterances of 64-256 ids) and configs[3] (high = ResBlock1, kernels 3/7/11, batch
+    16 x 512 ids: 8 attention key tiles, multi-chunk decode) at full size through size-independent properties: audio length ==
+    hop * sum(durations), finite, tanh-bounded, and one utterance of the batch re-run alone (B = 1 semantics, voice.py:350)."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, preset, 1)
+    sess = B200Session(p, precision="bf16", seed=9, max_chunk_frames=8192)
+    rs = np.random.RandomState(2)
+    lens = rs.randint(tlo, thi, size=(B,)).astype(np.int64)
+    T = int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd}
+    audio, alen = sess.synthesize_packed(feed)
+    dur = sess.engine.fetch("durations").copy()
+    off = 0
+    for b in range(B):
+        assert int(alen[b]) == arch.hop * max(int(dur[off:off + lens[b]].sum()), 1)
+        off += int(lens[b])
+    assert audio.shape[0] == int(alen.sum()) and np.isfinite(audio).all() and np.abs(audio).max() <= 1.0
+    # the same utterance alone: identical durations (the text side is per-utterance and deterministic given noise_dp)
+    b = B // 2
+    one = B200Session(p, precision="bf16", seed=9)
+    L = int(lens[b])
+    _, alen1 = one.synthesize_packed({"input": ids[b:b + 1, :L], "input_lengths": lens[b:b + 1], "scales": SCALES, "noise_dp": nd[b:b + 1, :, :L]})
+    d1 = one.engine.fetch("durations")
+    o = int(lens[:b].sum())
+    assert np.array_equal(d1[:L], dur[o:o + L]) and int(alen1[0]) == int(alen[b])
