@@ -152,9 +152,9 @@ def main():
     ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--preset", default="medium")
-    ap.add_argument("--max-ids", type=int, default=131072, help="phoneme ids per device batch")
+    ap.add_argument("--max-ids", type=int, default=262144, help="phoneme ids per device batch")
     ap.add_argument("--max-utts", type=int, default=2048, help="utterances per device batch")
-    ap.add_argument("--chunk-frames", type=int, default=131072)
+    ap.add_argument("--chunk-frames", type=int, default=262144)
     ap.add_argument("--cpu-sample", type=int, default=24, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="engine option (A/B experiments), repeatable")

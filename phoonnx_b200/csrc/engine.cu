@@ -61,7 +61,7 @@ struct vits_handle {
     bool finalized = false;
     int precision = 0;
     int text_tc = 1;                 // bf16 mode: text-side GEMMs as bf16x3 on tcgen05 (0: fp32 CUDA cores)
-    int64_t max_chunk_frames = 32768;
+    int64_t max_chunk_frames = 262144;   // frames per decode chunk (r01: larger chunks amortise tails; workspaces grow on demand)
     int64_t launches = 0;
     int num_sms = 148;
 
@@ -111,6 +111,7 @@ struct vits_handle {
     std::vector<cudaEvent_t> event_pool;
     float stage_ms[5] = {0, 0, 0, 0, 0};      // text, flow, decoder; [3] the fused last-stage kernel alone, [4] the other fused MRF stage kernels
     size_t open_stage = 0;
+    int conv_text_counter = 0;
     int64_t kern_launches[2] = {0, 0};        // launches / algorithmic MACs behind stage_ms[3], [4] (vits_kernel_ms)
     double kern_macs[2] = {0, 0};
 };
@@ -280,6 +281,12 @@ int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T
     s.split3 = 1; s.cin = c.slice_cin; s.nks = c.nsl; s.wtc = c.wtc3[0];
     for (int j = 0; j < c.nsl; j++) s.wtc_ks[j] = c.wtc3[j];
     s.dbg = nullptr;
+    if (h->opts.count("conv_text_dbg") && (int)h->opts["conv_text_dbg"] == ++h->conv_text_counter) {
+        int rc = ensure(h, h->conv_dbg, (size_t)TC_DBG_TILES * 16 * 8);
+        if (rc) return rc;
+        CK(h, cudaMemsetAsync(h->conv_dbg.p, 0, (size_t)TC_DBG_TILES * 16 * 8, h->stream));
+        s.dbg = ptr<unsigned long long>(h->conv_dbg);
+    }
     cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream);
     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc (bf16x3) launch: %s", cudaGetErrorString(e));
     h->launches++;
@@ -640,6 +647,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
     h->scales[0] = scales[0]; h->scales[1] = scales[1]; h->scales[2] = scales[2];
     h->seed = seed; h->B = B; h->R = (int)R;
     h->utt_base = h->utt_counter; h->utt_counter += (uint64_t)B;
+    h->conv_text_counter = 0;
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int H = A.hidden, C = A.inter, F = A.filter, Fd = A.dp_filter;
