@@ -5,7 +5,7 @@
 #include <stdint.h>
 
 #define CONV_MAX_TAPS 16
-#define CONV_MAX_SLICES 8
+#define CONV_MAX_SLICES 16
 
 enum ConvEpi { EPI_STORE = 0, EPI_GATE = 1, EPI_SPLIT = 2, EPI_SUBFROM = 3 };
 enum OutAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };

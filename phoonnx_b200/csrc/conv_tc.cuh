@@ -51,6 +51,8 @@ struct TcCfg {
     int nabuf;        // activation tile buffers (1 or 2)
     int naccbuf;      // TMEM accumulator buffers (1 or 2)
     int epi_off;      // byte offset of the epilogue transpose buffers (4 warps x 32 x TC_EPI_PITCH floats)
+    int cluster;      // 2: CTA pairs (cluster 2x1x1) share every weight piece -- each CTA fetches every other piece and multicasts it to both
+                      //    (the ring-mode launches are bound by L2 -> SM weight traffic: a 128-row tile re-streams all taps); 1: off
 };
 
 namespace tc {
@@ -85,6 +87,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// ---- 2-CTA cluster helpers (weight multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one bulk copy delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     if (dbg_on && warp == 0) a.dbg[15] = (unsigned long long)clock64();
 
     if (tid == 0) {
-        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, 1); }
+        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, (uint32_t)c.cluster); }
         for (int i = 0; i < 2; i++) {
             tc::mbar_init(bar_afull0 + 8u * i, TC_LOAD_THREADS);
             tc::mbar_init(bar_aempty0 + 8u * i, 1);
@@ -465,11 +482,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
+    if (c.cluster == 2) tc::cluster_sync_all();         // the peer's barriers exist before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // cluster mode: both CTAs of a pair run the ring for the same number of tile iterations (the even CTA's count); a CTA without
+    // a tile in the last iteration still fetches its share of the pieces and releases the slots
+    const int cl_rank = (c.cluster == 2) ? (int)tc::cluster_ctarank() : 0;
+    const int ring_iters = (c.cluster == 2) ? (a.ntiles - ((int)blockIdx.x & ~1) + (int)gridDim.x - 1) / (int)gridDim.x
+                                            : (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     const int kc_total = a.cin >> 3;                    // 16-byte chunks per activation row (per plane)
-    const int nseg = a.split3 ? 3 : 1;                  // K segments per tap: [xh*wh | xh*wl | xl*wh]
+    // split3: weights hold [wh | wl | wh] per tap; the ring streams only (wh, wl) -- the wh piece serves both xh*wh and xl*wh (the
+    // third copy is never fetched: the text-side GEMMs are bound by L2 -> SM weight traffic, r01g timeline: 2.65 MB per 128-row tile)
+    const int nseg = a.split3 ? 2 : 1;
     const uint32_t lbo_a = (uint32_t)c.rows_a * 16u;
     const uint32_t lbo_b = (uint32_t)c.ntile * 16u;
 
@@ -572,9 +597,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             const uint32_t kc_bytes = (uint32_t)c.ntile * 16u;
             const uint32_t sW_u = tc::smem_u32(sW);
             const long kc_stride = (long)a.npad16 * 8;          // elements between consecutive 8-channel chunks
-            int itp = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, itp++) {
-                if (c.resident && tile != (int)blockIdx.x) break;
+            uint32_t piece = 0;
+            for (int itp = 0; itp < ring_iters; itp++) {
+                if (c.resident && itp > 0) break;
                 TC_STAMP(itp, 7);
                 for (int ks = 0; ks < a.nks; ks++) {
                 const __nv_bfloat16* src = a.wtc_ks[ks] + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
@@ -586,9 +611,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         const uint32_t fb = bar_full0 + 8u * s;
                         tc::mbar_expect_tx(fb, kc_bytes * (uint32_t)nkc);
                         uint32_t dst = sW_u + s * (uint32_t)c.slot_bytes;
+                        if (c.cluster == 2) {
+                            // pieces alternate between the two CTAs; the one whose turn it is fetches for both
+                            if ((int)(piece & 1u) == cl_rank)
+                                for (int kc = 0; kc < nkc; kc++) tc::bulk_g2s_mc(dst + (uint32_t)kc * kc_bytes, src + (long)kc * kc_stride, kc_bytes, fb, (uint16_t)3);
+                            src += (long)nkc * kc_stride;
+                        } else
                         for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s(dst, src, kc_bytes, fb);
+                        piece++;
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
+                    if (a.split3 && (tapseg & 1)) src += (long)kc_total * kc_stride;      // skip the repeated wh segment of this tap
                 }
                 }
                 TC_STAMP(itp, 8);
@@ -604,43 +637,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             const uint32_t piece_a16 = ((uint32_t)(c.piece_ch >> 3) * lbo_a) >> 4;     // A advance per 64-channel piece (16 B units)
             uint32_t s = 0, ph = 0, it = 0;                   // ring slot / parity of its "full" barrier
             uint32_t abuf = 0, aph = 0, cbuf = 0, cph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+            for (int tile = blockIdx.x; (int)it < ring_iters; tile += gridDim.x, it++) {
+                // cluster mode: `real` is false for the pair's last iteration when only the peer has a tile -- the ring handshakes still run
+                const bool real = tile < a.ntiles;
                 TC_STAMP((int)it, 9);
-                tc::mbar_wait(bar_accempty0 + 8u * cbuf, cph ^ 1u);
+                if (real) tc::mbar_wait(bar_accempty0 + 8u * cbuf, cph ^ 1u);
                 TC_STAMP((int)it, 11);
                 const uint32_t dcol = tmem_base + cbuf * (uint32_t)c.ntile;
                 uint32_t accum = 0;
                 for (int ks = 0; ks < a.nks; ks++) {
-                tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
+                if (real) tc::mbar_wait(bar_afull0 + 8u * abuf, aph);
                 TC_STAMP((int)it, 10);
                 tc::tc_fence_after();
                 const uint32_t a16 = ((sA_u + abuf * (uint32_t)c.a_bytes) >> 4) - (uint32_t)c.min_off;   // row 0 <-> tap offset 0
                 const int nt_ks = a.ntaps_ks[0] ? a.ntaps_ks[ks] : a.ntaps;
                 const int tap0 = a.ntaps_ks[0] ? a.tap0_ks[ks] : 0;
+                const uint32_t lo_plane16 = ((uint32_t)kc_total * lbo_a) >> 4;     // the lo plane sits kc_total chunks behind the hi plane
                 for (int tapseg = 0; tapseg < nt_ks * nseg; tapseg++) {
-                    const int tap = a.split3 ? tapseg / 3 : tapseg;
+                    const int tap = a.split3 ? (tapseg >> 1) : tapseg;
                     const int seg = tapseg - tap * nseg;
-                    // segment 2 multiplies the lo plane, which sits kc_total chunks behind the hi plane
-                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap0 + tap] + (seg == 2 ? (((uint32_t)kc_total * lbo_a) >> 4) : 0u);
+                    // split3: piece wh (seg 0) multiplies the hi AND the lo activation plane, piece wl (seg 1) the hi plane
+                    const int npass = (a.split3 && seg == 0) ? 2 : 1;
+                    uint32_t arow16 = a16 + (uint32_t)a.toff[tap0 + tap];
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch, arow16 += piece_a16) {
                         const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
                         if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
+                        for (int pass = 0; pass < (real ? npass : 0); pass++) {
                         // descriptors differ only in the 14-bit start-address field (bytes >> 4)
-                        uint64_t ad = dhi_a | (uint64_t)(arow16 & 0x3FFF);
+                        uint64_t ad = dhi_a | (uint64_t)((arow16 + (pass ? lo_plane16 : 0u)) & 0x3FFF);
                         uint64_t bd = dhi_b | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
                         for (int k = 0; k < nk16; k++) {
                             tc::umma_bf16(dcol, ad, bd, idesc, accum);
                             accum = 1;
                             ad += ad_step; bd += bd_step;
                         }
-                        if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);   // frees the weight slot when these MMAs retire
+                        }
+                        if (!c.resident) {                                          // frees the weight slot when these MMAs retire
+                            if (c.cluster == 2) tc::umma_commit_mc(bar_empty0 + 8u * s, (uint16_t)3);   // ... in both CTAs of the pair
+                            else tc::umma_commit(bar_empty0 + 8u * s);
+                        }
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
                 }
+                if (!real) continue;
                 tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
                 if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
                 }
                 if (c.resident) s = 0;
+                if (!real) continue;
                 tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
                 TC_STAMP((int)it, 12);
                 if (++cbuf == (uint32_t)c.naccbuf) { cbuf = 0; cph ^= 1u; }
@@ -649,6 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (c.cluster == 2) tc::cluster_sync_all();         // no CTA leaves while its peer may still multicast into it / signal its barriers
     if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
 }
 
@@ -669,7 +714,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     int rows = TC_M + (mx - mn);
     rows = ((rows + 7) / 8) * 8 + 1;           // odd row count: (kc + r) mod 8 spreads 16 B chunks over all banks
     c.rows_a = rows;
-    const int planes = a.split3 ? 2 : 1, nseg = a.split3 ? 3 : 1;
+    const int planes = a.split3 ? 2 : 1, nseg = a.split3 ? 2 : 1;     // weight segments streamed per tap (split3: wh, wl)
     c.a_bytes = (planes * (a.cin / 8) * rows * 16 + 127) / 128 * 128;
     c.piece_ch = a.cin < TC_PIECE_CH ? a.cin : TC_PIECE_CH;
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
@@ -692,7 +737,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
             // widest N tile first (the activation tile is re-read once per N tile), then double-buffered
             // activations, then ring depth
             c.resident = 0;
-            const int smax = c.npieces < 4 ? c.npieces : 4;
+            const int smax = c.npieces < 8 ? c.npieces : 8;          // ring depth: bytes in flight hide the L2 round trip
             for (int nabuf = 2; nabuf >= 1 && !ok; nabuf--)
                 for (int ns = smax; ns >= (smax < 2 ? smax : 2) && !ok; ns--)
                     if (total(nabuf, ns) <= limit) { c.nabuf = nabuf; c.nstages = ns; ok = true; }
@@ -717,7 +762,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     return true;
 }
 
-static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStream_t st) {
+static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStream_t st, bool cluster_ok = false) {
     TcCfg c;
     if (!conv_tc_plan(a, c)) return cudaErrorInvalidConfiguration;
     // epilogue variant (compile-time in the kernel)
@@ -756,7 +801,20 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
     int gx = num_sms * occ / (ny < 1 ? 1 : 1);
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) gx = 1;
+    // ring-mode launches: CTA pairs share the weight stream (multicast); needs an even grid
+    c.cluster = (!c.resident && cluster_ok && gx >= 2) ? 2 : 1;
+    if (c.cluster == 2) gx &= ~1;
     dim3 grid(gx, ny);
+    if (c.cluster == 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)c.smem_bytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, fn, a, c);
+    }
     fn<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c);
     return cudaGetLastError();
 }

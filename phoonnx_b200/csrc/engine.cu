@@ -46,6 +46,7 @@ struct Buf {   // grow-only device buffer
     void* p = nullptr; size_t cap = 0;
 };
 
+#define SPLIT3_MAX_CIN 96      // packing.SPLIT3_MAX_CIN
 struct StagePair { cudaEvent_t a, b; int stage; };
 
 }  // namespace
@@ -176,7 +177,7 @@ int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, co
     c.nsl = 0; c.slice_cin = 0;
     if (cin % 16 == 0 && n % 16 == 0) {
         int sl = 0;
-        for (int v = std::min(cin, 96); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
+        for (int v = std::min(cin, SPLIT3_MAX_CIN); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
         if (sl && cin / sl <= CONV_MAX_SLICES) {
             bool all = true;
             for (int j = 0; j < cin / sl; j++) {
@@ -252,7 +253,7 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
             CK(h, cudaMemsetAsync(h->conv_dbg.p, 0, (size_t)TC_DBG_TILES * 16 * 8, h->stream));
             a.dbg = ptr<unsigned long long>(h->conv_dbg);
         }
-        cudaError_t e = conv_tc_launch(a, h->num_sms, h->stream);
+        cudaError_t e = conv_tc_launch(a, h->num_sms, h->stream, h->opts["conv_cluster"] != 0);
         if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc launch: %s", cudaGetErrorString(e));
         h->launches++;
         return 0;
@@ -287,7 +288,7 @@ int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T
         CK(h, cudaMemsetAsync(h->conv_dbg.p, 0, (size_t)TC_DBG_TILES * 16 * 8, h->stream));
         s.dbg = ptr<unsigned long long>(h->conv_dbg);
     }
-    cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream);
+    cudaError_t e = conv_tc_launch(s, h->num_sms, h->stream, h->opts["conv_cluster"] != 0);
     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "conv_tc (bf16x3) launch: %s", cudaGetErrorString(e));
     h->launches++;
     return 0;
@@ -1313,7 +1314,7 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     if (use_tc == 2) {
         // `wtc` holds the K slices back to back ("<n>.wtc3.0", ".1", ...), slice width as in mkconv
         int sl = 0;
-        for (int v = std::min(cin, 96); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
+        for (int v = std::min(cin, SPLIT3_MAX_CIN); v >= 16; v--) if (cin % v == 0 && v % 16 == 0) { sl = v; break; }
         if (!sl || cin / sl > CONV_MAX_SLICES) { cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dmeta); return fail(h, VITS_E_INVALID, "bf16x3: unsupported cin %d", cin); }
         c.nsl = cin / sl; c.slice_cin = sl;
         for (int j = 0; j < c.nsl; j++) c.wtc3[j] = (const __nv_bfloat16*)dwtc + (size_t)j * ntaps * 3 * sl * npad16;

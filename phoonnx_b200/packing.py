@@ -42,7 +42,10 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return (f32_to_bf16_bits(x).astype(np.uint32) << 16).view(np.float32)
 
 
-SPLIT3_MAX_CIN = 96    # widest K slice whose hi+lo activation planes, double-buffered, fit one CTA's shared memory
+SPLIT3_MAX_CIN = 96    # widest K slice whose hi+lo activation planes, double-buffered, fit one CTA's shared memory next to a weight ring.
+                       # (r01 A/B: 48-wide slices deepen the ring from 2-3 to 5 stages but double the activation-tile hand-offs, each a
+                       # ~5k-cycle load -> convert round trip: text stage 74.3 -> 78.3 ms.  The text GEMMs are bound by shared-memory
+                       # capacity: A hi/lo planes + weight ring + epilogue staging)
 
 
 def split3_slice(cin: int) -> int:

@@ -55,7 +55,8 @@ def test_bf16x3_operands_reproduce_fp32_products():
     blobs = {}
     packing.pack_conv(blobs, "c", w, None, tc3=True)
     sl = packing.split3_slice(cin)
-    assert sl == 96 and "c.wtc3.3" in blobs and "c.wtc3.4" not in blobs
+    nsl = cin // sl
+    assert sl == packing.SPLIT3_MAX_CIN and cin % sl == 0 and f"c.wtc3.{nsl - 1}" in blobs and f"c.wtc3.{nsl}" not in blobs
     x = rs.randn(50, cin).astype(np.float32)
     xh = packing.bf16_round(x)
     xl = packing.bf16_round(x - xh)
