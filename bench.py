@@ -36,10 +36,10 @@ SCALES = (0.667, 1.0, 0.8)
 # -- constants copied from the committed captures, not measured by this script (a number taken under a profiler is never a
 # bench value; these only say whether the kernels re-read more than the algorithm needs)
 KERNEL_TRAFFIC = {
-    "k_mrf3_tc<32>": {"bytes_per_launch": 1.074467e9 + 0.129114e9, "algorithmic_bytes_per_launch": 131072 * (64 * 64 * 2 + 256 * 4),
-                      "source": "profiles/r01d_ncu_mrf3.txt"},
-    "k_mrf3_tc<64>": {"bytes_per_launch": 1.073970e9 + 1.027093e9, "algorithmic_bytes_per_launch": 131072 * (64 * 64 * 2) * 2,
-                      "source": "profiles/r01d_ncu_mrf3.txt"},
+    "k_mrf3_tc<32>": {"bytes_per_launch": 2.150258e9 + 0.264484e9, "algorithmic_bytes_per_launch": 262144 * (64 * 64 * 2 + 256 * 4),
+                      "frames_per_launch": 262144, "source": "profiles/r01g_ncu_mrf3.txt"},
+    "k_mrf3_tc<64>": {"bytes_per_launch": 2.150496e9 + 2.104694e9, "algorithmic_bytes_per_launch": 262144 * (64 * 64 * 2) * 2,
+                      "frames_per_launch": 262144, "source": "profiles/r01g_ncu_mrf3.txt"},
 }
 DEC_TRAFFIC = {"bytes": None, "note": "per-kernel DRAM traffic of the two fused kernels is under roofline.kernels[].traffic; the decoder as a "
                                       "whole is a launch family, see profiles/README.md for the per-launch dram bytes of every member"}
