@@ -232,6 +232,8 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2 || RESK == 3);
     constexpr int NRB = (RESK == 3) ? 3 : 1;          // bf16 residual row groups summed (RESK 3: up to three, a.nresb)
     const float resb_inv = has_resb ? 1.f / a.resb_slope : 1.f;
+    const float2 resb_inv2 = make_float2(resb_inv, resb_inv), inv_div2 = make_float2(inv_div, inv_div), outb_sl2 = make_float2(a.outb_slope, a.outb_slope);
+    const bool scaled = a.out_div != 1.f;
     const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);   // this N tile's bias
     uint32_t it = 0;
     int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
@@ -316,7 +318,12 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                         const int nc = ng + hcol;
                         {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) { const float4 bb = *reinterpret_cast<const float4*>(sBias + n0 + hcol + 4 * k); v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w; }
+                            for (int k = 0; k < 4; k++) {
+                                const float4 bb = *reinterpret_cast<const float4*>(sBias + n0 + hcol + 4 * k);
+                                const float2 s0 = __fadd2_rn(make_float2(v[4 * k], v[4 * k + 1]), make_float2(bb.x, bb.y));
+                                const float2 s1 = __fadd2_rn(make_float2(v[4 * k + 2], v[4 * k + 3]), make_float2(bb.z, bb.w));
+                                v[4 * k] = s0.x; v[4 * k + 1] = s0.y; v[4 * k + 2] = s1.x; v[4 * k + 3] = s1.y;
+                            }
                         }
                         if (ur) {
 #pragma unroll
@@ -356,34 +363,37 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                         const int itr = h2 * 4 + u;
                         if (itr >= lpr) continue;              // compile-time
                         const bool okp = itr * rpi + rsub < nrows;
-                        float4 v4 = o[u];
-                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (has_res) r4 = rr[itr];
+                        // packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogue is issue-bound, every pair op saves a slot
+                        float2 va = make_float2(o[u].x, o[u].y), vb = make_float2(o[u].z, o[u].w);
+                        float2 ra = make_float2(0.f, 0.f), rb2 = ra;
+                        if (has_res) { ra = make_float2(rr[itr].x, rr[itr].y); rb2 = make_float2(rr[itr].z, rr[itr].w); }
                         if (has_resb) {
                             // the residual is the conv's own input, stored as the bf16 lrelu operand: invert the (monotone) lrelu
 #pragma unroll
                             for (int j = 0; j < NRB; j++) {
                                 const uint32_t bx = rb[j][itr].x, by = rb[j][itr].y;
-                                const float r0 = tc::bf16_lo_f(bx), r1 = tc::bf16_hi_f(bx), r2 = tc::bf16_lo_f(by), r3 = tc::bf16_hi_f(by);
-                                r4.x += fminf(r0, r0 * resb_inv); r4.y += fminf(r1, r1 * resb_inv); r4.z += fminf(r2, r2 * resb_inv); r4.w += fminf(r3, r3 * resb_inv);
+                                const float2 la = make_float2(tc::bf16_lo_f(bx), tc::bf16_hi_f(bx)), lb = make_float2(tc::bf16_lo_f(by), tc::bf16_hi_f(by));
+                                const float2 ia = __fmul2_rn(la, resb_inv2), ib = __fmul2_rn(lb, resb_inv2);
+                                ra = __fadd2_rn(ra, make_float2(fminf(la.x, ia.x), fminf(la.y, ia.y)));
+                                rb2 = __fadd2_rn(rb2, make_float2(fminf(lb.x, ib.x), fminf(lb.y, ib.y)));
                             }
                         }
                         if (EPI == EPI_SUBFROM) {
-                            v4 = make_float4(r4.x - v4.x, r4.y - v4.y, r4.z - v4.z, r4.w - v4.w);
+                            va = make_float2(ra.x - va.x, ra.y - va.y); vb = make_float2(rb2.x - vb.x, rb2.y - vb.y);
                         } else if (EPI != EPI_GATE) {
-                            v4.x += r4.x; v4.y += r4.y; v4.z += r4.z; v4.w += r4.w;
-                            if (a.out_act == ACT_RELU) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
-                            if (ACC) { v4.x += pp[itr].x; v4.y += pp[itr].y; v4.z += pp[itr].z; v4.w += pp[itr].w; }
-                            v4.x *= inv_div; v4.y *= inv_div; v4.z *= inv_div; v4.w *= inv_div;
+                            va = __fadd2_rn(va, ra); vb = __fadd2_rn(vb, rb2);
+                            if (a.out_act == ACT_RELU) { va.x = fmaxf(va.x, 0.f); va.y = fmaxf(va.y, 0.f); vb.x = fmaxf(vb.x, 0.f); vb.y = fmaxf(vb.y, 0.f); }
+                            if (ACC) { va = __fadd2_rn(va, make_float2(pp[itr].x, pp[itr].y)); vb = __fadd2_rn(vb, make_float2(pp[itr].z, pp[itr].w)); }
+                            if (scaled) { va = __fmul2_rn(va, inv_div2); vb = __fmul2_rn(vb, inv_div2); }      // warp-uniform
                         }
                         if ((EPI == EPI_STORE || EPI == EPI_GATE) && a.outb) {
                             // the consumer's MMA operand: bf16(lrelu(v)), 8 bytes per lane
-                            const float sl = a.outb_slope;
-                            const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(v4.x, v4.x * sl), fmaxf(v4.y, v4.y * sl)),
-                                                         tc::pack_bf16(fmaxf(v4.z, v4.z * sl), fmaxf(v4.w, v4.w * sl)));
+                            const float2 sa = __fmul2_rn(va, outb_sl2), sb = __fmul2_rn(vb, outb_sl2);
+                            const uint2 pk2 = make_uint2(tc::pack_bf16(fmaxf(va.x, sa.x), fmaxf(va.y, sa.y)),
+                                                         tc::pack_bf16(fmaxf(vb.x, sb.x), fmaxf(vb.y, sb.y)));
                             if (okp) *reinterpret_cast<uint2*>(outb0 + (long)(itr * rpi) * a.ldo) = pk2;
                         } else if (okp)
-                            *reinterpret_cast<float4*>(dst0 + (long)(itr * rpi) * ldd) = v4;
+                            *reinterpret_cast<float4*>(dst0 + (long)(itr * rpi) * ldd) = make_float4(va.x, va.y, vb.x, vb.y);
                     }
                 }
                 __syncwarp();

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         const bool active = bb < c.nb;
         const int wr = 128 * bb + 32 * q + lane;                  // window row of this thread
         const float inv_div = 1.f / a.out_div, inv_slope = 1.f / a.slope;
+        const float2 slope2 = make_float2(a.slope, a.slope), inv_slope2 = make_float2(inv_slope, inv_slope), inv_div2 = make_float2(inv_div, inv_div);
         uint32_t n_c1[MRF3_MAX_RB] = {0, 0, 0}, n_c2 = 0, n_post = 0, n_ups = 0;
         long p_row0 = 0; int p_len = 0, p_o0 = 0; bool have_prev = false;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
@@ -250,10 +251,13 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
+                        // packed fp32 pairs (FADD2 / FMUL2): the epilogue warps are issue-bound
                         const float4 bv = *reinterpret_cast<const float4*>(ub_bias + n0 + j);
-                        const float x0 = v[j] + bv.x, x1v = v[j + 1] + bv.y, x2 = v[j + 2] + bv.z, x3 = v[j + 3] + bv.w;
-                        pk[j >> 1] = inu ? tc::pack_bf16(lrelu_max(x0, a.slope), lrelu_max(x1v, a.slope)) : 0u;
-                        pk[(j >> 1) + 1] = inu ? tc::pack_bf16(lrelu_max(x2, a.slope), lrelu_max(x3, a.slope)) : 0u;
+                        const float2 xa = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(bv.x, bv.y));
+                        const float2 xb2 = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(bv.z, bv.w));
+                        const float2 sa = __fmul2_rn(xa, slope2), sb = __fmul2_rn(xb2, slope2);
+                        pk[j >> 1] = inu ? tc::pack_bf16(fmaxf(xa.x, sa.x), fmaxf(xa.y, sa.y)) : 0u;
+                        pk[(j >> 1) + 1] = inu ? tc::pack_bf16(fmaxf(xb2.x, sb.x), fmaxf(xb2.y, sb.y)) : 0u;
                     }
                     if (inr) {
                         *reinterpret_cast<uint4*>(sX + ((size_t)((n0 >> 3) + 0) * c.rx + r) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -281,11 +285,11 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             const bool inr = active && (tm >= 0 && tm < len);
             // this thread's raw x row lives in the operand tile as lrelu(x): row wr + h1max, chunks 4*cg .. 4*cg + 3
             const uint8_t* xop = sX + ((size_t)(4 * cg) * c.rx + (active ? wr + c.h1max : 0)) * 16;
-            float xacc[32];                         // sum_r (x1_r + bias2_r) of this thread's 32 channels
+            float2 xacc[16];                        // sum_r (x1_r + bias2_r) of this thread's 32 channels, as packed pairs
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 bs = *reinterpret_cast<const float4*>(sB + a.nrb * C + 32 * cg + 4 * j);      // sum_r bias2_r
-                xacc[4 * j] = bs.x; xacc[4 * j + 1] = bs.y; xacc[4 * j + 2] = bs.z; xacc[4 * j + 3] = bs.w;
+                xacc[2 * j] = make_float2(bs.x, bs.y); xacc[2 * j + 1] = make_float2(bs.z, bs.w);
             }
             const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(bb * C + 32 * cg);
 
@@ -311,12 +315,15 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 #pragma unroll
                             for (int p2 = 0; p2 < 4; p2++) {
                                 const int ch = n0 + 8 * h8 + 2 * p2;
-                                const float l0 = tc::bf16_lo_f(xw[p2]), l1 = tc::bf16_hi_f(xw[p2]);
-                                const float xv0 = fminf(l0, l0 * inv_slope), xv1 = fminf(l1, l1 * inv_slope);
-                                const float x10 = v[8 * h8 + 2 * p2] + b1[ch] + xv0, x11 = v[8 * h8 + 2 * p2 + 1] + b1[ch + 1] + xv1;
-                                xacc[ch] += x10; xacc[ch + 1] += x11;
+                                const float2 l = make_float2(tc::bf16_lo_f(xw[p2]), tc::bf16_hi_f(xw[p2]));
+                                const float2 li = __fmul2_rn(l, inv_slope2);
+                                const float2 xv = make_float2(fminf(l.x, li.x), fminf(l.y, li.y));
+                                const float2 vb = __fadd2_rn(make_float2(v[8 * h8 + 2 * p2], v[8 * h8 + 2 * p2 + 1]), *reinterpret_cast<const float2*>(b1 + ch));
+                                const float2 x1p = __fadd2_rn(vb, xv);
+                                xacc[ch >> 1] = __fadd2_rn(xacc[ch >> 1], x1p);
+                                const float2 xs = __fmul2_rn(x1p, slope2);
                                 // conv2 zero-pads x1 beyond the utterance
-                                pk[ch >> 1] = inr ? tc::pack_bf16(lrelu_max(x10, a.slope), lrelu_max(x11, a.slope)) : 0u;
+                                pk[ch >> 1] = inr ? tc::pack_bf16(fmaxf(x1p.x, xs.x), fmaxf(x1p.y, xs.y)) : 0u;
                             }
                         }
                     }
@@ -360,9 +367,12 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                         float v[16];
                         tc::tmem_ld16(tlane + acc2_col + (uint32_t)n0, v);
 #pragma unroll
+                        const float2 osl2 = make_float2(osl, osl);
+#pragma unroll
                         for (int j = 0; j < 16; j += 2) {
-                            const float o0v = (v[j] + xacc[n0 + j]) * inv_div, o1v = (v[j + 1] + xacc[n0 + j + 1]) * inv_div;
-                            pk[(n0 + j) >> 1] = st ? tc::pack_bf16(lrelu_max(o0v, osl), lrelu_max(o1v, osl)) : 0u;
+                            const float2 o = __fmul2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), xacc[(n0 + j) >> 1]), inv_div2);
+                            const float2 os = __fmul2_rn(o, osl2);
+                            pk[(n0 + j) >> 1] = st ? tc::pack_bf16(fmaxf(o.x, os.x), fmaxf(o.y, os.y)) : 0u;
                         }
                     }
                     if (post) {
@@ -386,10 +396,10 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 #pragma unroll
                             for (int qd = 0; qd < 4; qd++) {
                                 float4 ov;
-                                ov.x = (v[4 * qd + 0] + xacc[n0 + 4 * qd + 0]) * inv_div;
-                                ov.y = (v[4 * qd + 1] + xacc[n0 + 4 * qd + 1]) * inv_div;
-                                ov.z = (v[4 * qd + 2] + xacc[n0 + 4 * qd + 2]) * inv_div;
-                                ov.w = (v[4 * qd + 3] + xacc[n0 + 4 * qd + 3]) * inv_div;
+                                ov.x = (v[4 * qd + 0] + xacc[(n0 + 4 * qd) >> 1].x) * inv_div;
+                                ov.y = (v[4 * qd + 1] + xacc[(n0 + 4 * qd) >> 1].y) * inv_div;
+                                ov.z = (v[4 * qd + 2] + xacc[(n0 + 4 * qd + 2) >> 1].x) * inv_div;
+                                ov.w = (v[4 * qd + 3] + xacc[(n0 + 4 * qd + 2) >> 1].y) * inv_div;
                                 *(reinterpret_cast<float4*>(orow + n0) + qd) = ov;
                             }
                         }
