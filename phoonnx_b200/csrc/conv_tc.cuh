@@ -24,6 +24,9 @@
 #define TC_DESC_SWAP_LBO_SBO 0
 #endif
 
+#ifndef TC_EXPERIMENT_SKIP_RESB
+#define TC_EXPERIMENT_SKIP_RESB 0      // timing experiment only (wrong results): skip the bf16 residual prefetch
+#endif
 #define TC_M 128
 #define TC_EPI_WARPS 8
 #define TC_LOAD_WARPS 6
@@ -294,7 +297,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
 #pragma unroll
                         for (int j = 0; j < NRB; j++) {
                             rb[j][itr] = make_uint2(0u, 0u);
-                            if (okp && (NRB == 1 || j < a.nresb)) rb[j][itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb + j * a.resb_stride);
+                            if (okp && (NRB == 1 || j < a.nresb) && !TC_EXPERIMENT_SKIP_RESB) rb[j][itr] = *reinterpret_cast<const uint2*>(resb0 + (long)(itr * rpi) * a.ldresb + j * a.resb_stride);
                         }
                     }
                     if (ACC) { pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f); if (okp && acc) pp[itr] = *reinterpret_cast<const float4*>(dst0 + (long)(itr * rpi) * ldd); }
@@ -621,10 +624,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         const uint32_t fb = bar_full0 + 8u * s;
                         tc::mbar_expect_tx(fb, kc_bytes * (uint32_t)nkc);
                         uint32_t dst = sW_u + s * (uint32_t)c.slot_bytes;
+                        // one N tile == all output columns: the chunks of a piece are contiguous in global memory -> ONE bulk copy per piece.
+                        // (r01g experiment: with one 2-4 KB copy per 8-channel chunk the single producer thread's issue rate -- ~90 cycles per
+                        // copy, 240 copies per tile of the summed second convs -- bounded every ring-mode launch, not L2 and not the ring depth)
+                        const bool contig = (c.ntile == a.npad16);
                         if (c.cluster == 2) {
                             // pieces alternate between the two CTAs; the one whose turn it is fetches for both
-                            if ((int)(piece & 1u) == cl_rank)
-                                for (int kc = 0; kc < nkc; kc++) tc::bulk_g2s_mc(dst + (uint32_t)kc * kc_bytes, src + (long)kc * kc_stride, kc_bytes, fb, (uint16_t)3);
+                            if ((int)(piece & 1u) == cl_rank) {
+                                if (contig) tc::bulk_g2s_mc(dst, src, kc_bytes * (uint32_t)nkc, fb, (uint16_t)3);
+                                else for (int kc = 0; kc < nkc; kc++) tc::bulk_g2s_mc(dst + (uint32_t)kc * kc_bytes, src + (long)kc * kc_stride, kc_bytes, fb, (uint16_t)3);
+                            }
+                            src += (long)nkc * kc_stride;
+                        } else if (contig) {
+                            tc::bulk_g2s(dst, src, kc_bytes * (uint32_t)nkc, fb);
                             src += (long)nkc * kc_stride;
                         } else
                         for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s(dst, src, kc_bytes, fb);
