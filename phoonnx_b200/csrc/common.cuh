@@ -39,6 +39,9 @@ struct ConvArgs {
     // K slices (tcgen05 path): the kernel loops over nks slices of `cin` input channels each (activation columns xcol + ks * cin,
     // weights wtc_ks[ks]) and accumulates them in TMEM: one epilogue per tile, activation tiles double-buffered across slices
     int nks;  const __nv_bfloat16* wtc_ks[CONV_MAX_SLICES];
+    // N-tiled copies of the same weights (n > 256 only): [n / wtile][tap][cin/8][wtile][8], so that an N tile's pieces are contiguous
+    // and cross the weight ring as ONE bulk copy each; used when the launch plan's N tile equals wtile (0: none)
+    int wtile;  const __nv_bfloat16* wtc_t_ks[CONV_MAX_SLICES];
     // per-slice tap lists (tcgen05 path, optional): slice ks uses taps toff[tap0_ks[ks] .. + ntaps_ks[ks]) (`ntaps` = the flattened
     // total); all zero = every slice uses toff[0 .. ntaps).  Lets ONE launch sum convolutions with different kernels / dilations.
     int ntaps_ks[CONV_MAX_SLICES];  int tap0_ks[CONV_MAX_SLICES];

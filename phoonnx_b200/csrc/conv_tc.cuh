@@ -219,6 +219,15 @@ __global__ void k_tile_desc(const int* __restrict__ cu, const int* __restrict__ 
     out[tile] = make_int4(cb0 * rate, (cb1 - cb0) * rate, (tile - __ldg(tile_cu + b)) * tm, b);
 }
 
+// [rows][n16][8] -> [n16 / wt][rows][wt][8]  (rows = tap x 8-channel chunk): the N-tiled weight copy, built once at load time
+__global__ void k_retile_weights(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int n16, int wt) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte (8-element) unit per thread
+    if (i >= rows * n16) return;
+    const long r = i / n16; const int n = (int)(i - r * n16);
+    const int ty = n / wt, nn = n - ty * wt;
+    reinterpret_cast<uint4*>(out)[((long)ty * rows + r) * wt + nn] = reinterpret_cast<const uint4*>(in)[i];
+}
+
 #define TC_DBG_TILES 16
 #define TC_STAMP(it_, slot_) do { if (dbg_on && (it_) < TC_DBG_TILES) a.dbg[(it_) * 16 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
@@ -609,13 +618,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             uint32_t s = 0, ph = 1;                       // ring slot and the parity to wait for on its "empty" barrier
             const uint32_t kc_bytes = (uint32_t)c.ntile * 16u;
             const uint32_t sW_u = tc::smem_u32(sW);
-            const long kc_stride = (long)a.npad16 * 8;          // elements between consecutive 8-channel chunks
+            const bool tiled = a.wtile != 0 && a.wtile == c.ntile;      // N-tiled weight copy: this N tile's chunks are contiguous
+            const long kc_stride = tiled ? (long)c.ntile * 8 : (long)a.npad16 * 8;          // elements between consecutive 8-channel chunks
+            const long tile_block = (long)a.ntaps * (a.split3 ? 3 : 1) * kc_total * c.ntile * 8;   // elements of one N tile's block (tiled copy)
             uint32_t piece = 0;
             for (int itp = 0; itp < ring_iters; itp++) {
                 if (c.resident && itp > 0) break;
                 TC_STAMP(itp, 7);
                 for (int ks = 0; ks < a.nks; ks++) {
-                const __nv_bfloat16* src = a.wtc_ks[ks] + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
+                const __nv_bfloat16* src = tiled ? a.wtc_t_ks[ks] + (long)ny * tile_block
+                                                 : a.wtc_ks[ks] + (long)ny * c.ntile * 8;     // (tap 0, chunk 0) of this N tile
                 const int nt_ks = a.ntaps_ks[0] ? a.ntaps_ks[ks] : a.ntaps;
                 for (int tapseg = 0; tapseg < nt_ks * nseg; tapseg++) {
                     for (int ch0 = 0; ch0 < a.cin; ch0 += c.piece_ch) {
@@ -627,7 +639,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         // one N tile == all output columns: the chunks of a piece are contiguous in global memory -> ONE bulk copy per piece.
                         // (r01g experiment: with one 2-4 KB copy per 8-channel chunk the single producer thread's issue rate -- ~90 cycles per
                         // copy, 240 copies per tile of the summed second convs -- bounded every ring-mode launch, not L2 and not the ring depth)
-                        const bool contig = (c.ntile == a.npad16);
+                        const bool contig = tiled || (c.ntile == a.npad16);
                         if (c.cluster == 2) {
                             // pieces alternate between the two CTAs; the one whose turn it is fetches for both
                             if ((int)(piece & 1u) == cl_rank) {

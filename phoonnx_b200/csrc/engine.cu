@@ -37,6 +37,8 @@ struct ConvP {
     int cin = 0, n = 0, npad = 0, npad16 = 0, ntaps = 0; int toff[CONV_MAX_TAPS] = {0};
     // fp32-faithful bf16x3 operands (text side): one blob per K slice of slice_cin input channels
     const __nv_bfloat16* wtc3[CONV_MAX_SLICES] = {nullptr}; int nsl = 0, slice_cin = 0;
+    // N-tiled copies (n > 256): same operands re-laid [n / wtile][tap][cin/8][wtile][8] at load time (k_retile_weights)
+    int wtile = 0; const __nv_bfloat16* wtc_t = nullptr; const __nv_bfloat16* wtc3_t[CONV_MAX_SLICES] = {nullptr};
 };
 
 struct LnP { const float* g = nullptr; const float* b = nullptr; };
@@ -107,6 +109,7 @@ struct vits_handle {
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
     Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b, rowpos;
+    std::vector<void*> owned;         // device allocations made at finalize time (re-tiled weight copies)
     std::vector<float*> rb_b2sum;     // per stage: sum over resblocks of the second conv's bias (ResBlock2; fused conv2 launch)
     std::vector<StagePair> stage_events;
     std::vector<cudaEvent_t> event_pool;
@@ -188,6 +191,30 @@ int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, co
             if (all) { c.nsl = cin / sl; c.slice_cin = sl; }
         }
     }
+    // N-tiled copies for n > 256 (first-choice N tile of conv_tc_plan: the largest multiple-of-16 divisor of npad16 that is <= 256)
+    c.wtile = 0; c.wtc_t = nullptr;
+    for (auto& q : c.wtc3_t) q = nullptr;
+    if (c.npad16 > 256) {
+        int wt = 0;
+        for (int cand = 256; cand >= 16; cand -= 16) if (c.npad16 % cand == 0) { wt = cand; break; }
+        auto retile = [&](const __nv_bfloat16* src, long rows, const __nv_bfloat16** dst) -> int {
+            __nv_bfloat16* d = nullptr;
+            CK(h, cudaMalloc(&d, (size_t)rows * c.npad16 * 16));
+            h->owned.push_back(d);
+            const long units = rows * c.npad16;
+            k_retile_weights<<<(unsigned)((units + 255) / 256), 256, 0, h->stream>>>(src, d, rows, c.npad16, wt);
+            CK(h, cudaGetLastError());
+            *dst = d;
+            return 0;
+        };
+        if (wt) {
+            c.wtile = wt;
+            if (c.wtc && (rc = retile(c.wtc, (long)c.ntaps * (cin / 8), &c.wtc_t))) return rc;
+            for (int j = 0; j < c.nsl; j++)
+                if ((rc = retile(c.wtc3[j], (long)c.ntaps * 3 * (c.slice_cin / 8), &c.wtc3_t[j]))) return rc;
+            CK(h, cudaStreamSynchronize(h->stream));
+        }
+    }
     return 0;
 }
 
@@ -233,6 +260,7 @@ ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out
     a.x = x; a.ldx = ldx; a.xcol = xcol; a.cin = c.cin;
     a.ntaps = c.ntaps; for (int i = 0; i < c.ntaps; i++) a.toff[i] = c.toff[i];
     a.w = c.w; a.wtc = c.wtc; a.n = c.n; a.npad = c.npad; a.npad16 = c.npad16; a.bias = c.b;
+    a.wtile = c.wtc_t ? c.wtile : 0; a.wtc_t_ks[0] = c.wtc_t;
     a.in_act = 0; a.in_slope = 1.f; a.epi = EPI_STORE; a.out_act = ACT_NONE; a.out_div = 1.f;
     a.out = out; a.ldo = ldo; a.ocol = ocol;
     return a;
@@ -280,7 +308,8 @@ int launch_conv_text(vits_handle* h, const ConvP& c, ConvArgs& a, const Tiles& T
     // one launch: the kernel loops over the K slices and accumulates them in TMEM
     ConvArgs s = a;
     s.split3 = 1; s.cin = c.slice_cin; s.nks = c.nsl; s.wtc = c.wtc3[0];
-    for (int j = 0; j < c.nsl; j++) s.wtc_ks[j] = c.wtc3[j];
+    s.wtile = c.wtc3_t[0] ? c.wtile : 0;
+    for (int j = 0; j < c.nsl; j++) { s.wtc_ks[j] = c.wtc3[j]; s.wtc_t_ks[j] = c.wtc3_t[j]; }
     s.dbg = nullptr;
     if (h->opts.count("conv_text_dbg") && (int)h->opts["conv_text_dbg"] == ++h->conv_text_counter) {
         int rc = ensure(h, h->conv_dbg, (size_t)TC_DBG_TILES * 16 * 8);
@@ -479,6 +508,8 @@ int vits_finalize(vits_handle* h) {
     if (C % 8) return fail(h, VITS_E_INVALID, "inter_channels=%d must be a multiple of 8", C);
     if (A.num_bins != SPL_K && A.use_sdp) return fail(h, VITS_E_INVALID, "num_bins=%d unsupported (kernel is specialised for %d)", A.num_bins, SPL_K);
     int rc;
+    for (void* pz : h->owned) cudaFree(pz);
+    h->owned.clear();
     if ((rc = need_f32(h, "enc.emb", &h->emb, (size_t)A.n_vocab * H))) return rc;
     h->enc.resize(A.n_layers);
     std::vector<int> ffn_taps(A.enc_kernel);
@@ -1398,6 +1429,7 @@ void vits_destroy(vits_handle* h) {
                    &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
+    for (void* pz : h->owned) cudaFree(pz);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
