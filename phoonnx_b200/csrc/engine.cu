@@ -108,7 +108,7 @@ struct vits_handle {
     cudaEvent_t ev_chunk = nullptr, ev_out[2] = {nullptr, nullptr};
     bool out_pending[2] = {false, false};
     int audio_sel = 0;
-    Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b, rowpos;
+    Buf audio_alt, facts_b, tdesc_t, tdesc_c, sX1b, rowpos, fpos;
     std::vector<void*> owned;         // device allocations made at finalize time (re-tiled weight copies)
     std::vector<float*> rb_b2sum;     // per stage: sum over resblocks of the second conv's bias (ResBlock2; fused conv2 launch)
     std::vector<StagePair> stage_events;
@@ -957,7 +957,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0)));
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
-            (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) ||
+            (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) || (rc = ensure(h, h->fpos, (size_t)Fr * 8)) ||
             (rc = ensure(h, h->dpre, (size_t)Fr * A.up_init * 4)) ||
             (rc = ensure(h, h->sX, Fr * stage_elems_per_frame * 4)) || (rc = ensure(h, h->sT1, Fr * stage_elems_per_frame * 4)) ||
             (rc = ensure(h, h->sXSa, Fr * stage_elems_per_frame * 4)) || (rc = ensure(h, h->sXSb, Fr * stage_elems_per_frame * 4)) ||
@@ -981,11 +981,11 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         float *P = ptr<float>(h->P), *fh = ptr<float>(h->fh), *facts = ptr<float>(h->facts), *fskip = ptr<float>(h->fskip);
         // ---- prior expansion + sampling (models.py:705-718)
         stage_begin(h, 1);
-        k_frame_index<<<(Fr + 255) / 256, 256, 0, st>>>(ptr<int>(h->cum), ptr<int>(h->tile_t), T1.cu, b_lo, nB, Fr, ptr<int>(h->fidx));
+        k_frame_index<<<(Fr + 255) / 256, 256, 0, st>>>(ptr<int>(h->cum), ptr<int>(h->tile_t), T1.cu, b_lo, nB, Fr, ptr<int>(h->fidx), ptr<int2>(h->fpos));
         h->launches++;
         {
-            long n = (long)Fr * C;
-            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ptr<float>(h->stats), ptr<int>(h->fidx), T1.cu, b_lo, nB,
+            long n = (long)Fr * (C / 4);
+            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ptr<float>(h->stats), ptr<int>(h->fidx), ptr<int2>(h->fpos),
                                                                          d_injz, z_stride, h->scales[0], h->seed, h->utt_base, P, Fr, C);
             h->launches++;
         }
@@ -1426,7 +1426,7 @@ void vits_destroy(vits_handle* h) {
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos, &h->fpos};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
     for (void* pz : h->owned) cudaFree(pz);
