@@ -28,6 +28,7 @@
 #define TC_EXPERIMENT_SKIP_RESB 0      // timing experiment only (wrong results): skip the bf16 residual prefetch
 #endif
 #define TC_M 128
+#define TC_LOAD_BATCH 8          // fp32 loader: (row, chunk) items whose 2 x LDG.128 are in flight per thread before any conversion
 #define TC_EPI_WARPS 8
 #define TC_LOAD_WARPS 6
 #define TC_THREADS ((TC_EPI_WARPS + TC_LOAD_WARPS + 2) * 32)
@@ -246,6 +247,8 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     const float resb_inv = has_resb ? 1.f / a.resb_slope : 1.f;
     const float2 resb_inv2 = make_float2(resb_inv, resb_inv), inv_div2 = make_float2(inv_div, inv_div), outb_sl2 = make_float2(a.outb_slope, a.outb_slope);
     const bool scaled = a.out_div != 1.f;
+    // gate outputs straight to bf16 operand rows (lrelu slope 1 = identity; 16-byte aligned rows)
+    const bool gate_direct = (EPI == EPI_GATE) && a.outb != nullptr && a.outb_slope == 1.f && (a.ldo % 8 == 0) && (a.ocol % 8 == 0);
     const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);   // this N tile's bias
     uint32_t it = 0;
     int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
@@ -347,8 +350,19 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                             float gt[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) gt[j] = tanh_fast(v[2 * j]) * fmaf(0.5f, tanh_fast(0.5f * v[2 * j + 1]), 0.5f);
+                            if (gate_direct) {
+                                // bf16 operand rows for the next GEMM: this thread's row gets 8 gate outputs = 16 contiguous bytes; 32 lanes fill
+                                // 32 full 32-byte sectors per pair of stores.  No transpose, no second phase (the staged path's
+                                // STS -> syncwarp -> LDS -> STG chain was ~40 % of this epilogue's latency).
+                                if (lane < nrows) {
+                                    __nv_bfloat16* orow = a.outb + (row0 + trow0 + lane) * (long)a.ldo + a.ocol + og + (hcol >> 1);
+                                    *reinterpret_cast<uint4*>(orow) = make_uint4(tc::pack_bf16(gt[0], gt[1]), tc::pack_bf16(gt[2], gt[3]),
+                                                                                 tc::pack_bf16(gt[4], gt[5]), tc::pack_bf16(gt[6], gt[7]));
+                                }
+                            } else {
                             *reinterpret_cast<float4*>(srow + (hcol >> 1)) = make_float4(gt[0], gt[1], gt[2], gt[3]);
                             *reinterpret_cast<float4*>(srow + (hcol >> 1) + 4) = make_float4(gt[4], gt[5], gt[6], gt[7]);
+                            }
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; k++)
@@ -356,6 +370,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
                         }
                     }
                 }
+                if (gate_direct) { if (dbg_on) { const long long t2 = clock64(); ph1 += t2 - tq; tq = t2; } return; }
                 __syncwarp();
                 if (dbg_on) { const long long t2 = clock64(); ph1 += t2 - tq; tq = t2; }
                 // ---- phase 2: staged rows + prefetched residual / accumulate operands -> global
@@ -565,15 +580,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                 TC_STAMP(it, 6);
                 continue;
             }
-            // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; 4 items (8 x LDG.128) in
+            // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; TC_LOAD_BATCH items (2 x LDG.128 each) in
             // flight per thread before any conversion so the load latency is paid once per batch
             int r = lr0, kc = lk0;
-            for (int base = lt; base < items; base += 4 * TC_LOAD_THREADS) {
-                float4 v0[4], v1[4];
-                int rr[4], kk[4];
-                bool ok[4];
+            for (int base = lt; base < items; base += TC_LOAD_BATCH * TC_LOAD_THREADS) {
+                float4 v0[TC_LOAD_BATCH], v1[TC_LOAD_BATCH];
+                int rr[TC_LOAD_BATCH], kk[TC_LOAD_BATCH];
+                bool ok[TC_LOAD_BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < TC_LOAD_BATCH; u++) {
                     rr[u] = r; kk[u] = kc;
                     ok[u] = (base + u * TC_LOAD_THREADS < items);
                     v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
@@ -585,7 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                     if (kc >= kc_total) { kc -= kc_total; r++; }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < TC_LOAD_BATCH; u++) {
                     if (!ok[u]) continue;
                     float4 a0 = v0[u], a1 = v1[u];
                     if (a.in_act) {
