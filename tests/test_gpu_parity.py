@@ -522,3 +522,27 @@ def test_baseline_configs_2_and_4_full_size(lib, tmp_path_factory, preset, B, tl
     d1 = one.engine.fetch("durations")
     o = int(lens[:b].sum())
     assert np.array_equal(d1[:L], dur[o:o + L]) and int(alen1[0]) == int(alen[b])
+
+
+def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
+    """Optional 2-CTA cluster mode (`conv_cluster`, `mrf_cluster`): CTA pairs share the weight ring through multicast bulk copies and
+    multicast tcgen05.commit.  Same MMAs in the same order -> the audio is bit-identical to the default launches; odd tile counts
+    exercise the round where only one CTA of a pair has a tile."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, "medium", 1)
+    rs = np.random.RandomState(8)
+    lens = np.array([97, 3, 160, 41, 1, 77, 130], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
+    outs = []
+    for opt in (0, 1):
+        sess = B200Session(p, precision="bf16")
+        sess.engine.set_option("conv_cluster", opt)
+        sess.engine.set_option("mrf_cluster", opt)
+        a, alen = sess.synthesize_packed(feed)
+        outs.append((a.copy(), alen.copy()))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
