@@ -260,6 +260,9 @@ def main():
         for audio, alen in sess.synthesize_many(feeds, out="f32"):
             frames += int(alen.sum()) // arch.hop
             nbytes += audio.nbytes
+            head = audio[:1 << 20]              # cheap sanity check of every result: a NaN tile or an unbounded sample is a failed run
+            if not (np.isfinite(head).all() and float(np.abs(head).max()) <= 1.0):
+                raise SystemExit("bench.py: synthesised audio is not finite / not tanh-bounded")
         return frames, nbytes
 
     e2e_step()

@@ -419,7 +419,7 @@ cudaError_t mrf3_launch_timed(vits_handle* h, const Mrf3Args& m, const Mrf3Cfg& 
     cudaError_t e = mrf3_tiles_launch(m, c, h->stream);
     if (e != cudaSuccess) return e;
     const size_t slot = sub_begin(h, stage);
-    e = mrf3_kernel_launch(m, c, h->num_sms, h->stream, h->opts["mrf_cluster"] != 0);
+    e = mrf3_kernel_launch(m, c, h->num_sms, h->stream);
     sub_end(h, slot);
     return e;
 }

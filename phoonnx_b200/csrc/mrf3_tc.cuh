@@ -67,9 +67,6 @@ struct Mrf3Cfg {
     int slot_bytes, nstages, resident, npieces;
     int tmem_cols;
     int nmw;                     // MMA-issuing warps (2 when the M blocks split evenly)
-    int cluster;                 // 2: CTA pairs share the weight stream -- each CTA fetches every other ring piece and multicasts it to both
-                                 //    (all SMs read the same 8 KB piece at the same time: the r01e timeline shows the C=64 stage's conv1
-                                 //    phases paced by weight delivery at ~12 B/clk/SM); 1: off.  Set by the launcher.
     int nub, u_rows, u_bytes, upw_bytes;   // mode U: M blocks of the ups pass, rows / bytes of its input tile, bytes of both weight halves
     int bias_off, postw_off, sp_off;   // sp: per-row per-tap partial sums of conv_post, [span + 8][MRF3_SP_PITCH] floats
     int smem_bytes;
@@ -134,7 +131,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     const bool modeU = a.up_u != 0;
     if (tid == 0) {
         const uint32_t nmw = (uint32_t)c.nmw;           // every commit-tracked barrier gets one arrival per MMA warp
-        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, nmw * (uint32_t)c.cluster); }
+        for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, nmw); }
         tc::mbar_init(bar_in, 32);
         tc::mbar_init(bar_in_free, modeU ? nmw : MRF3_EPI_THREADS);
         tc::mbar_init(bar_ups, nmw);
@@ -169,15 +166,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     if (warp == MRF3_EPI_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
-    if (c.cluster == 2) tc::cluster_sync_all();        // the peer's barriers exist before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // cluster mode: both CTAs of a pair run the weight ring for the even CTA's number of tiles (a CTA without a tile in the last
-    // round still fetches its share of the pieces and releases the slots)
-    const int cl_rank = (c.cluster == 2) ? (int)tc::cluster_ctarank() : 0;
-    const int my_iters = ((int)blockIdx.x < a.ntiles) ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int ring_iters = (c.cluster == 2) ? (((int)blockIdx.x & ~1) < a.ntiles ? (a.ntiles - ((int)blockIdx.x & ~1) + (int)gridDim.x - 1) / (int)gridDim.x : 0)
-                                            : my_iters;
 
     constexpr int KC = C / 8;                       // 16-byte chunks per row
     constexpr int NG = C / 32;                      // 32-channel groups per row
@@ -436,21 +426,16 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 tc::bulk_g2s(tc::smem_u32(sUW) + half_bytes, a.up_w[1], half_bytes, bar_upw);
             }
             uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
-            uint32_t piece = 0;
-            for (int itp = 0; itp < ring_iters; itp++) {
-                if (c.resident && itp > 0) break;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                if (c.resident && tile != (int)blockIdx.x) break;
                 // issue order of the MMA warp: C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2)
                 for (int cv = 0; cv < 2; cv++)
                     for (int r = 0; r < a.nrb; r++) {
                         const __nv_bfloat16* wsrc = a.w[r][cv];
-                        for (int tap = 0; tap < a.k[r]; tap++, piece++) {
+                        for (int tap = 0; tap < a.k[r]; tap++) {
                             if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
                             const uint32_t fb = bar_full0 + 8u * s;
                             tc::mbar_expect_tx(fb, (uint32_t)c.slot_bytes);
-                            if (c.cluster == 2) {
-                                if ((int)(piece & 1u) == cl_rank)
-                                    tc::bulk_g2s_mc(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb, (uint16_t)3);
-                            } else
                             tc::bulk_g2s(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb);
                             wsrc += C * C;
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
@@ -569,10 +554,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                                 for (int k16 = 0; k16 < C / 16; k16++)
                                     tc::umma_bf16_lh(dcol0 + (uint32_t)C, alo + 128u + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0);
                             }
-                            if (!c.resident) {
-                                if (c.cluster == 2) tc::umma_commit_mc(bar_empty0 + 8u * s, (uint16_t)3);
-                                else tc::umma_commit(bar_empty0 + 8u * s);
-                            }
+                            if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
                         tc::umma_commit(cv ? bar_c2 : (bar_c1 + 8u * (uint32_t)r));
@@ -582,15 +564,6 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 if (c.resident) { s = 0; }
             }
             if (post && it > 0) issue_post(it - 1);          // the last tile's conv_post
-            // cluster mode: the peer has one more tile than this CTA -- keep the shared ring turning (no MMAs, just hand the slots back)
-            if (c.cluster == 2 && !c.resident)
-                for (int extra = my_iters; extra < ring_iters; extra++)
-                    for (int r2 = 0; r2 < 2 * a.nrb; r2++)
-                        for (int tap = 0; tap < a.k[r2 % a.nrb]; tap++) {
-                            tc::mbar_wait(bar_full0 + 8u * s, ph);
-                            tc::umma_commit_mc(bar_empty0 + 8u * s, (uint16_t)3);
-                            if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
-                        }
         }
     } else {
         // ===================== input-row loader (warp 18): cp.async, 16 B per lane, zero fill outside the utterance =====================
@@ -637,7 +610,6 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (c.cluster == 2) tc::cluster_sync_all();        // no CTA leaves while its peer may still multicast into it / signal its barriers
     if (warp == MRF3_EPI_WARPS) tc::tmem_dealloc(tmem_base, (uint32_t)c.tmem_cols);
 }
 
@@ -711,7 +683,7 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
 }
 
 template <int C>
-static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st, bool cluster_ok) {
+static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -725,20 +697,7 @@ static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int
     int gx = num_sms;                       // one persistent CTA per SM (TMEM: 512 columns each)
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) return cudaSuccess;
-    Mrf3Cfg cc = c;
-    cc.cluster = (!c.resident && cluster_ok && gx >= 2) ? 2 : 1;
-    if (cc.cluster == 2) {
-        gx &= ~1;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(gx); cfg.blockDim = dim3(MRF3_THREADS); cfg.dynamicSmemBytes = (size_t)c.smem_bytes; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_mrf3_tc<C>, a, cc);
-    }
-    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, cc);
+    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c);
     return cudaGetLastError();
 }
 
@@ -750,9 +709,9 @@ static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c,
     return cudaGetLastError();
 }
 
-static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st, bool cluster_ok = false) {
-    if (a.C == 32) return mrf3_launch_t<32>(a, c, num_sms, st, cluster_ok);
-    if (a.C == 64) return mrf3_launch_t<64>(a, c, num_sms, st, cluster_ok);
+static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+    if (a.C == 32) return mrf3_launch_t<32>(a, c, num_sms, st);
+    if (a.C == 64) return mrf3_launch_t<64>(a, c, num_sms, st);
     return cudaErrorInvalidConfiguration;
 }
 

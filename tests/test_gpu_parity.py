@@ -525,9 +525,9 @@ def test_baseline_configs_2_and_4_full_size(lib, tmp_path_factory, preset, B, tl
 
 
 def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
-    """Optional 2-CTA cluster mode (`conv_cluster`, `mrf_cluster`): CTA pairs share the weight ring through multicast bulk copies and
-    multicast tcgen05.commit.  Same MMAs in the same order -> the audio is bit-identical to the default launches; odd tile counts
-    exercise the round where only one CTA of a pair has a tile."""
+    """Optional 2-CTA cluster mode of the conv kernel (`conv_cluster`): CTA pairs share the weight ring through multicast bulk
+    copies and multicast tcgen05.commit.  Same MMAs in the same order -> the audio is bit-identical to the default launches; odd
+    tile counts exercise the round where only one CTA of a pair has a tile."""
     from phoonnx_b200.session import B200Session
     p, arch, _ = _voice(tmp_path_factory, "medium", 1)
     rs = np.random.RandomState(8)
@@ -541,8 +541,7 @@ def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
     for opt in (0, 1):
         sess = B200Session(p, precision="bf16")
         sess.engine.set_option("conv_cluster", opt)
-        sess.engine.set_option("mrf_cluster", opt)
         a, alen = sess.synthesize_packed(feed)
         outs.append((a.copy(), alen.copy()))
     assert np.array_equal(outs[0][1], outs[1][1])
-    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.isfinite(outs[1][0]).all() and np.array_equal(outs[0][0], outs[1][0])
