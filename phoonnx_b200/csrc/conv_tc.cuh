@@ -147,6 +147,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// tcgen05.mma with the two shared-memory descriptors given as (lo, hi) 32-bit halves: only `lo` (start address >> 4 | LBO << 16)
+// changes between the MMAs of a conv, by plain 32-bit adds; `hi` (SBO, version) is loop-invariant
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -682,7 +689,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             const uint32_t idesc = tc::make_idesc(TC_M, c.ntile);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_a = tc::make_desc(0, lbo_a, 128u), dhi_b = tc::make_desc(0, lbo_b, 128u);   // start-address field = 0
-            const uint64_t ad_step = (uint64_t)((2u * lbo_a) >> 4), bd_step = (uint64_t)((2u * lbo_b) >> 4);
+            const uint32_t a_k16 = (2u * lbo_a) >> 4, b_k16 = (2u * lbo_b) >> 4;               // start-field advance per K = 16 step
+            const uint32_t ahi = (uint32_t)(dhi_a >> 32), bhi = (uint32_t)(dhi_b >> 32);
+            const uint32_t a_lbo_hi = (uint32_t)dhi_a & 0xFFFF0000u, b_lbo_hi = (uint32_t)dhi_b & 0xFFFF0000u;   // LBO fields of the low words
             const uint32_t piece_a16 = ((uint32_t)(c.piece_ch >> 3) * lbo_a) >> 4;     // A advance per 64-channel piece (16 B units)
             uint32_t s = 0, ph = 0, it = 0;                   // ring slot / parity of its "full" barrier
             uint32_t abuf = 0, aph = 0, cbuf = 0, cph = 0;
@@ -712,13 +721,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         const int nk16 = min(c.piece_ch, a.cin - ch0) >> 4;
                         if (!c.resident || it == 0) { tc::mbar_wait(bar_full0 + 8u * s, ph); tc::tc_fence_after(); }
                         for (int pass = 0; pass < (real ? npass : 0); pass++) {
-                        // descriptors differ only in the 14-bit start-address field (bytes >> 4)
-                        uint64_t ad = dhi_a | (uint64_t)((arow16 + (pass ? lo_plane16 : 0u)) & 0x3FFF);
-                        uint64_t bd = dhi_b | (uint64_t)(((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFF);
+                        // descriptor low words: start address (16-byte units) | LBO << 16; only the start field moves (by plain 32-bit
+                        // adds), the high words (SBO, version) are loop-invariant.  With 64-bit descriptors rebuilt per MMA the single
+                        // issuing thread needed ~145 cycles per MMA (r01h timeline: 24 MMAs of a k3 conv in 3.3k cycles) against 64
+                        // executed at N = 128 -- the issue loop, not the tensor pipe, paced every launch with N <= 256
+                        uint32_t alo = ((arow16 + (pass ? lo_plane16 : 0u)) & 0x3FFFu) | a_lbo_hi;
+                        uint32_t blo = (((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFFu) | b_lbo_hi;
+#pragma unroll 4
                         for (int k = 0; k < nk16; k++) {
-                            tc::umma_bf16(dcol, ad, bd, idesc, accum);
+                            tc::umma_bf16_lh(dcol, alo, ahi, blo, bhi, idesc, accum);
                             accum = 1;
-                            ad += ad_step; bd += bd_step;
+                            alo += a_k16; blo += b_k16;
                         }
                         }
                         if (!c.resident) {                                          // frees the weight slot when these MMAs retire
