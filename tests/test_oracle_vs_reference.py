@@ -51,3 +51,25 @@ def test_mac_closed_forms_high_and_xlow():
     assert make_arch("x_low").flow_mac_per_frame() == 1769472
     assert make_arch("x_low").enc_mac_per_id() == 1566720
     assert make_arch("x_low").dp_mac_per_id() == 141120
+
+
+def test_lightning_checkpoint_file_loads_like_the_exported_file(tmp_path):
+    """a Lightning ``.ckpt`` of the reference's generator (``model_g.*`` keys, weight-norm pairs still in the coupling
+    flow, ``hyper_parameters`` alongside; export_onnx.py:227-245 reads the same file) gives the same canonical tensors and
+    architecture as the ONNX file exported from that model."""
+    import torch
+    from phoonnx_b200.weights import load_model
+    m = rb.build_reference_model("x_low", n_speakers=1)
+    sd = {"model_g." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd["model_d.discriminators.0.convs.0.bias"] = torch.zeros(4)            # discriminator weights ride along in real checkpoints
+    assert any(k.endswith(".weight_g") for k in sd), "the reference keeps weight-norm in the flow at checkpoint time"
+    ck = str(tmp_path / "voice.ckpt")
+    torch.save({"state_dict": sd, "hyper_parameters": {"sample_rate": 16000, "quality": "x_low"}, "epoch": 3}, ck)
+    onnx_path = str(tmp_path / "voice.onnx")
+    rb.export_onnx(m, onnx_path, n_speakers=1)
+    Wc, ac, hc = load_model(ck)
+    Wo, ao, ho = load_model(onnx_path)
+    assert set(Wc) == set(Wo)
+    for k in Wo:
+        assert np.allclose(Wc[k], Wo[k], atol=1e-6), k
+    assert ac == ao and hc.inputs == ho.inputs
