@@ -201,6 +201,14 @@ def main():
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        # one rank per GPU: run (and allocate the page-locked result pool) on the CPUs / NUMA node next to this rank's GPU
+        # (8-GPU check of round 1: device-resident rate scaled linearly, the end-to-end rate lost 15 % to the host side)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from phoonnx_b200.session import B200Session
     sess = B200Session(path, device=local, precision=args.precision, max_chunk_frames=args.chunk_frames, seed=1000 * rank)
