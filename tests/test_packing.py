@@ -103,3 +103,37 @@ def test_flow_tail_composition_matches_skip_then_post():
         got = sum(acts[i].astype(np.float64) @ blobs[f"flow.{s}.mskip.{i}.w"][0, :, :half].astype(np.float64) for i in range(L))
         got = got + blobs[f"flow.{s}.mskip.b"][:half]
         assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max()), np.abs(got - want).max()
+
+
+def test_summed_second_convs_algebra():
+    """The unfused ResBlock2 stage runs `sum_r [ x1_r + conv_{k_r,d_r2}(lrelu x1_r) ] / n_r` as ONE launch over the rows
+    [lrelu(x1_0) | lrelu(x1_1) | lrelu(x1_2)] (K slices with per-slice taps, residual recovered by inverting the leaky-relu;
+    csrc/conv_tc.cuh, engine.cu `stage_sum2`).  Same numbers as modules.py:355-364 evaluated resblock by resblock."""
+    import emulate as E
+    rs = np.random.RandomState(3)
+    L, C, slope = 300, 16, 0.1
+    ks, dils = (3, 5, 7), ((1, 2), (2, 6), (3, 12))
+    x = rs.randn(L, C).astype(np.float32)
+    w1 = [rs.randn(k, C, C).astype(np.float32) / np.sqrt(k * C) for k in ks]
+    w2 = [rs.randn(k, C, C).astype(np.float32) / np.sqrt(k * C) for k in ks]
+    b1 = [rs.randn(C).astype(np.float32) * 0.1 for _ in ks]
+    b2 = [rs.randn(C).astype(np.float32) * 0.1 for _ in ks]
+    # reference order: resblock by resblock
+    ref = np.zeros((L, C), np.float64)
+    x1s = []
+    for r, k in enumerate(ks):
+        x1 = x + E.conv_cl(E.lrelu(x, slope), w1[r], b1[r], E.sym_taps(k, dils[r][0]), C)
+        x1s.append(x1)
+        ref += x1 + E.conv_cl(E.lrelu(x1, slope), w2[r], b2[r], E.sym_taps(k, dils[r][1]), C)
+    ref /= len(ks)
+    # summed launch: operand rows side by side, one accumulator, flattened tap list
+    rows = np.concatenate([E.lrelu(x1, slope) for x1 in x1s], axis=1)                 # [L, 3C]
+    acc = np.zeros((L, C), np.float64)
+    for r, k in enumerate(ks):
+        acc += E.conv_cl(rows[:, r * C:(r + 1) * C], w2[r], None, E.sym_taps(k, dils[r][1]), C)
+    res = np.zeros((L, C), np.float64)
+    for r in range(len(ks)):
+        v = rows[:, r * C:(r + 1) * C].astype(np.float64)
+        res += np.minimum(v, v / slope)                                               # lrelu^-1: x = min(v, v / slope)
+    out = (acc + res + np.sum(b2, axis=0)) / len(ks)
+    assert np.abs(out - ref).max() < 1e-5
