@@ -6,15 +6,18 @@
 //     addr(row, k) = (k / 8) * LBO + row * 16 B + (k % 8) * 2 B        (SBO = 128 B)
 // is just a 16-byte-aligned start-address offset in the UMMA smem descriptor -- no im2col
 // copy and no re-fetch per tap.
-//   * activations: fp32 channel-last in HBM -> (leaky-relu) -> bf16 -> smem by the 4 epilogue
-//     warps (the fused "input activation"), zero-filled outside the utterance;
-//   * weights: pre-packed bf16 [tap][C_in/8][N][8] streamed by one producer thread with
-//     cp.async.bulk (TMA bulk, SASS UBLKCP) through an mbarrier ring, or kept resident in smem
-//     for the whole persistent CTA when they fit;
-//   * MMAs: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (SASS UTCHMMA), M=128,
-//     N<=256, K=16; completion via tcgen05.commit -> mbarrier;
-//   * epilogue: tcgen05.ld 32x32b (SASS LDTM) -> bias / speaker bias / residual / gate /
-//     split-accumulate / tanh -> fp32 stores.
+//   * activations: fp32 channel-last rows -> (leaky-relu) -> bf16 (or bf16 hi / lo planes for the fp32-faithful bf16x3 product)
+//     -> smem by the 6 loader warps, or rows a producer already wrote as bf16 MMA operands via cp.async; zero-filled outside
+//     the utterance;
+//   * weights: pre-packed bf16 [tap][C_in/8][N][8] (N-tiled copies for N > 256) streamed by one producer thread, one
+//     cp.async.bulk (SASS UBLKCP) per <= 64-channel piece through an mbarrier ring, or kept resident in smem for the whole
+//     persistent CTA when they fit; optional 2-CTA cluster mode multicasts every piece to a CTA pair;
+//   * MMAs: one elected thread, tcgen05.mma.cta_group::1.kind::f16 (SASS UTCHMMA), M=128, N<=256, K=16; K slices (with their
+//     own tap lists) accumulate in TMEM; completion via tcgen05.commit -> mbarrier;
+//   * epilogue (8 warps, one kernel instantiation per variant): tcgen05.ld 32x32b (SASS LDTM) -> bias / speaker bias /
+//     residual(s) / gate / split-accumulate -> smem transpose -> coalesced fp32 or bf16-operand-row stores.
+// What bounds it: the SM's 128 B/clk shared-memory port, shared by the MMA operand reads, the loader and the
+// epilogue transpose.
 #pragma once
 #include <type_traits>
 #include "common.cuh"
