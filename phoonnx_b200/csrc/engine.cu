@@ -871,7 +871,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         const int f_lo = h->h_cu_y[b_lo];
         std::vector<int> cu_local(nB + 1);
         for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
-        // fused MRF stage kernel (mrf2_tc.cuh; mrf_tc.cuh with option mrf_v1) where the stage qualifies: bf16 mode,
+        // fused MRF stage kernel (mrf3_tc.cuh; mrf2_tc.cuh / mrf_tc.cuh with options mrf_v2 / mrf_v1, kept as test references) where the stage qualifies: bf16 mode,
         // ResBlock2, 32/64 channels.  The last stage also absorbs lrelu -> conv_post -> tanh.
         std::vector<MrfArgs> mrf_args(A.n_ups + 1);
         std::vector<MrfCfg> mrf_cfg(A.n_ups + 1);

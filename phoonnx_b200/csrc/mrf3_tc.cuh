@@ -21,8 +21,9 @@
 //     accumulator column (p, c) of input row q is x[u*q + p, c]; 16 epilogue warps (quadrant x phase) turn it into
 //     the lrelu'd operand tile.  x never exists in HBM;
 //   * one conv1 accumulator per resblock (TMEM: (n_r + 1) * NB * C = 512 columns; conv_post reuses the last conv1
-//     buffer) and the issue order C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2) | post: every C1 is queued before the first
-//     epilogue result is needed, so E1(r) overlaps C1(r+1..) and C2(r-1).
+//     buffer) and the issue order C1(0) post(previous tile) C1(1) C1(2) | C2(0) C2(1) ups(next tile) C2(2): every C1 is queued
+//     before the first epilogue result is needed, so E1(r) overlaps C1(r+1..) and C2(r-1); the previous tile's conv_post goes in
+//     behind this tile's first conv1 instead of idling the tensor pipe at the tile's end.
 //
 //   * two MMA-issuing warps, each owning half of the M blocks (distinct accumulators, so the result does not depend on
 //     how their instructions interleave): one thread's descriptor set-up (R2UR moves, uniform adds) does not overlap
