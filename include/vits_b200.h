@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VITS_B200_ABI_VERSION 1
+#define VITS_B200_ABI_VERSION 2
 
 enum {
     VITS_OK = 0,
@@ -59,6 +59,19 @@ typedef struct vits_arch {
 
 /* ABI / build information: returns VITS_B200_ABI_VERSION. */
 int vits_abi_version(void);
+
+/* What a caller can ask a loaded voice (the reference reads the same facts from the voice's JSON config and from
+ * session.get_inputs(), voice.py:347: whether a `sid` input exists; phoonnx/config.py sample_rate / num_speakers). */
+typedef struct vits_info {
+    int32_t n_vocab, n_speakers, has_sid;      /* has_sid: the feed needs `sid` (multi-speaker voice, voice.py:370)      */
+    int32_t hidden, inter;                     /* encoder width, latent channels (noise_z rows)                          */
+    int32_t sample_rate, hop;                  /* audio samples per frame: utterance b has y_lengths[b] * hop samples    */
+    int32_t resblock_type, use_sdp;
+    int32_t precision;                         /* 0 fp32 CUDA cores, 1 bf16 tcgen05                                      */
+    int32_t device, num_sms, finalized;
+    int32_t reserved[8];
+} vits_info;
+int vits_describe(vits_handle* h, vits_info* info);
 
 /* Replaces InferenceSession(...) construction (voice.py:167-171): binds device `device_id`,
  * creates the stream and an empty weight table. */
@@ -111,6 +124,24 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
  */
 int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t out_kind,
                 void* out, int64_t out_capacity, float volume, int32_t normalize);
+/*   out_kind     3: float32 to a DEVICE buffer `out` of the caller (stream-ordered copy on the handle's stream, no host
+ *                   synchronisation: pair it with vits_set_stream() to stay inside the caller's own CUDA stream)
+ *   | VITS_OUT_ASYNC (kinds 1 and 2): return once the device->host transfer is enqueued on the copy stream; the result is complete
+ *                   after vits_wait_ticket(h, vits_output_ticket(h)).  Per call, no session-wide mode: a blocking call made
+ *                   while an asynchronous result is in flight neither disturbs it nor returns early itself. */
+#define VITS_OUT_ASYNC 0x100
+int64_t vits_output_ticket(vits_handle* h);                 /* ticket of the most recent vits_decode with host output (>= 1) */
+int vits_wait_ticket(vits_handle* h, int64_t ticket);       /* returns when that call's host buffer is complete               */
+
+/* Samples the output buffer of vits_decode must hold.  sum_ids <= 0: EXACT figure of the last successful vits_prepare
+ * (total_frames * hop; VITS_E_STATE before any).  sum_ids > 0: a planning figure for that many phoneme ids at
+ * `length_scale` BEFORE vits_prepare has run (durations are data: 16 frames per id is an allowance, not a bound --
+ * size the real buffer from vits_prepare's total_frames). */
+int64_t vits_max_output_samples(vits_handle* h, int64_t sum_ids, float length_scale);
+
+/* Run every later call of this handle on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the
+ * handle's own stream).  Pending work on the previous stream is completed first. */
+int vits_set_stream(vits_handle* h, void* cuda_stream);
 
 /* Output buffers.  onnxruntime allocates the array run() returns (voice.py:374-377); here the caller does, and a
  * page-locked buffer from vits_host_alloc() makes the device->host transfer a true asynchronous DMA on the handle's
@@ -122,9 +153,10 @@ int vits_host_free(void* p);
 int vits_wait_output(vits_handle* h, int older_only);   /* older_only: leave the most recent vits_decode's transfer in flight */
 
 /* Test / debugging: copy a stage tensor of the last prepare/decode to the host.
- * names: "x" [sumT,H], "m_p" [sumT,C], "logs_p" [sumT,C], "logw" [sumT], "durations" (int32
- * bits, [sumT]), "frame_index" (int32 bits, [frames of last chunk]), "z_p" / "z"
- * [frames of last chunk, C].  Returns the element count written (<= capacity) or <0. */
+ * names: "x" [sumT,H], "stats" [sumT,2C] (m_p | logs_p), "logw" [sumT], "durations" / "cum" (int32
+ * bits, [sumT]), "noise_dp" [2][sumT] (option debug_keep_noise_dp); per-chunk workspaces "frame_index"
+ * (int32 bits), "z_p" / "z" [frames, C] -- available only when the last vits_decode ran as ONE chunk
+ * (VITS_E_STATE otherwise).  Returns the element count written (<= capacity) or <0. */
 int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity_elems);
 
 /* Device-side timing of everything enqueued between start and stop on the handle's
@@ -144,19 +176,6 @@ int vits_stage_ms(vits_handle* h, float* text_ms, float* flow_ms, float* dec_ms)
  * (ConvTranspose1d + multi-receptive-field ResBlocks + lrelu / conv_post / tanh, models.py:352-366, one kernel), 1 the other fused
  * multi-receptive-field stages.  The measurement behind bench.py's per-kernel roofline. */
 int vits_kernel_ms(vits_handle* h, int which, float* ms, int64_t* launches, double* macs);
-
-/* Test hook: one convolution (single utterance of L rows, channel-last) through the production
- * launch path -- use_tc = 0: fp32 CUDA-core kernel, 1: tcgen05 kernel.  `out` is [L, out_cols]
- * and is read first when `accumulate` is set.  epi: 0 store, 1 gate (out_cols = n/2),
- * 2 split (first n/2 columns accumulate into out[:, :n/2], the rest into out[:, n/2:]), 3 res - v. */
-int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, const int* taps, int ntaps,
-                   const float* w32, const uint16_t* wtc, const float* bias, int n, int in_act, float in_slope,
-                   int epi, const float* res, int accumulate, float out_div, int out_act, float* out, int out_cols);
-
-/* Test hook: tcgen05.mma issue-rate probe (M=128, K=16, N=n; `nd` accumulators and `na` activation row offsets in
- * rotation, operand tile of `rows` rows).  Returns the average cycles per MMA (issue only / issue + completion). */
-int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
-                        double* total_cycles);
 
 const char* vits_last_error(vits_handle* h);
 void vits_destroy(vits_handle* h);

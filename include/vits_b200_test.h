@@ -1,0 +1,30 @@
+/*
+ * vits_b200_test.h -- test-only entry points of libvits_b200.so.  NOT part of the drop-in boundary (include/vits_b200.h):
+ * nothing on the reference side binds these; tests/ and tools/ use them to pin single kernels against numpy.
+ */
+#ifndef VITS_B200_TEST_H
+#define VITS_B200_TEST_H
+
+#include "vits_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Test hook: one convolution (single utterance of L rows, channel-last) through the production
+ * launch path -- use_tc = 0: fp32 CUDA-core kernel, 1: tcgen05 kernel.  `out` is [L, out_cols]
+ * and is read first when `accumulate` is set.  epi: 0 store, 1 gate (out_cols = n/2),
+ * 2 split (first n/2 columns accumulate into out[:, :n/2], the rest into out[:, n/2:]), 3 res - v. */
+int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, const int* taps, int ntaps,
+                   const float* w32, const uint16_t* wtc, const float* bias, int n, int in_act, float in_slope,
+                   int epi, const float* res, int accumulate, float out_div, int out_act, float* out, int out_cols);
+
+/* Test hook: tcgen05.mma issue-rate probe (M=128, K=16, N=n; `nd` accumulators and `na` activation row offsets in
+ * rotation, operand tile of `rows` rows).  Returns the average cycles per MMA (issue only / issue + completion). */
+int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
+                        double* total_cycles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITS_B200_TEST_H */

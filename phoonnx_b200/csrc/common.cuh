@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <limits.h>
 
 #define CONV_MAX_TAPS 16
 #define CONV_MAX_SLICES 16

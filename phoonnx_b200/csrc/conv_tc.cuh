@@ -189,6 +189,47 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
     return pred != 0;
 }
+// ---- warp-uniform issue path (round 2).  The whole issuing warp runs the loop, converged; only the asynchronous instruction itself
+// is predicated on the elect.sync flag.  With the loop inside a single-lane branch (round 1) every descriptor lived in a vector
+// register and each UTCHMMA cost 4 R2UR moves plus vector adds (~95 cycles per MMA issued against 40 executed); in converged code
+// ptxas keeps descriptors, ring slots and barrier addresses in uniform registers and emits UIADD3 / UTCHMMA / UTCBAR / UBLKCP
+// back to back (the elect predicate folds away: a uniform-datapath instruction executes once per warp).
+__device__ __forceinline__ uint32_t elect_flag() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
+__device__ __forceinline__ void umma_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, uint32_t el) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(el) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh_e(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accum, uint32_t el) {
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum), "r"(el) : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(el) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_e(uint32_t bar, uint16_t mask, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(bar), "h"(mask), "r"(el) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes, uint32_t el) {
+    asm volatile("{\n\t.reg .b64 st;\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n\t}"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask), "r"(el) : "memory");
+}
+// a value every lane of the (converged) warp holds identically, in a form ptxas can keep in a uniform register
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&p);
@@ -506,9 +547,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     const uint32_t bar_accempty0 = bar_accfull0 + 16u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 8);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform in a form ptxas can see (role branches stay converged)
     const int ny = blockIdx.y;
-    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 &&
+    const bool dbg_on_cta = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    const bool dbg_on = dbg_on_cta && lane == 0 &&
                         (warp == 0 || warp == TC_EPI_WARPS || warp >= TC_EPI_WARPS + TC_LOAD_WARPS);
     if (dbg_on && warp == 0) a.dbg[15] = (unsigned long long)clock64();
 
@@ -638,8 +681,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             }
         }
     } else if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) {
-        // ================= weight producer (one thread, cp.async.bulk ring) =================
-        if (tc::elect_one()) {
+        // ================= weight producer (cp.async.bulk ring; warp-uniform loop, copies predicated on the elected lane) =================
+        {
+            const uint32_t el = tc::elect_flag();
+            const bool dbg_on = dbg_on_cta && el != 0;
             uint32_t s = 0, ph = 1;                       // ring slot and the parity to wait for on its "empty" barrier
             const uint32_t kc_bytes = (uint32_t)c.ntile * 16u;
             const uint32_t sW_u = tc::smem_u32(sW);
@@ -659,7 +704,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         const int nkc = min(c.piece_ch, a.cin - ch0) >> 3;
                         if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
                         const uint32_t fb = bar_full0 + 8u * s;
-                        tc::mbar_expect_tx(fb, kc_bytes * (uint32_t)nkc);
+                        tc::mbar_expect_tx_e(fb, kc_bytes * (uint32_t)nkc, el);
                         uint32_t dst = sW_u + s * (uint32_t)c.slot_bytes;
                         // one N tile == all output columns: the chunks of a piece are contiguous in global memory -> ONE bulk copy per piece.
                         // (r01g experiment: with one 2-4 KB copy per 8-channel chunk the single producer thread's issue rate -- ~90 cycles per
@@ -668,15 +713,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         if (c.cluster == 2) {
                             // pieces alternate between the two CTAs; the one whose turn it is fetches for both
                             if ((int)(piece & 1u) == cl_rank) {
-                                if (contig) tc::bulk_g2s_mc(dst, src, kc_bytes * (uint32_t)nkc, fb, (uint16_t)3);
-                                else for (int kc = 0; kc < nkc; kc++) tc::bulk_g2s_mc(dst + (uint32_t)kc * kc_bytes, src + (long)kc * kc_stride, kc_bytes, fb, (uint16_t)3);
+                                if (contig) tc::bulk_g2s_mc_e(dst, src, kc_bytes * (uint32_t)nkc, fb, (uint16_t)3, el);
+                                else for (int kc = 0; kc < nkc; kc++) tc::bulk_g2s_mc_e(dst + (uint32_t)kc * kc_bytes, src + (long)kc * kc_stride, kc_bytes, fb, (uint16_t)3, el);
                             }
                             src += (long)nkc * kc_stride;
                         } else if (contig) {
-                            tc::bulk_g2s(dst, src, kc_bytes * (uint32_t)nkc, fb);
+                            tc::bulk_g2s_e(dst, src, kc_bytes * (uint32_t)nkc, fb, el);
                             src += (long)nkc * kc_stride;
                         } else
-                        for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s(dst, src, kc_bytes, fb);
+                        for (int kc = 0; kc < nkc; kc++, dst += kc_bytes, src += kc_stride) tc::bulk_g2s_e(dst, src, kc_bytes, fb, el);
                         piece++;
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
@@ -687,8 +732,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             }
         }
     } else {
-        // ================= MMA issuer (one thread) =================
-        if (tc::elect_one()) {
+        // ================= MMA issuer (warp-uniform loop, tcgen05.mma / commit predicated on the elected lane) =================
+        {
+            const uint32_t el = tc::elect_flag();
+            const uint32_t tmem_base = tc::uniform_u32(*tmem_slot);
+            const bool dbg_on = dbg_on_cta && el != 0;
             const uint32_t idesc = tc::make_idesc(TC_M, c.ntile);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_a = tc::make_desc(0, lbo_a, 128u), dhi_b = tc::make_desc(0, lbo_b, 128u);   // start-address field = 0
@@ -732,25 +780,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         uint32_t blo = (((sW_u + s * (uint32_t)c.slot_bytes) >> 4) & 0x3FFFu) | b_lbo_hi;
 #pragma unroll 4
                         for (int k = 0; k < nk16; k++) {
-                            tc::umma_bf16_lh(dcol, alo, ahi, blo, bhi, idesc, accum);
+                            tc::umma_bf16_lh_e(dcol, alo, ahi, blo, bhi, idesc, accum, el);
                             accum = 1;
                             alo += a_k16; blo += b_k16;
                         }
                         }
                         if (!c.resident) {                                          // frees the weight slot when these MMAs retire
-                            if (c.cluster == 2) tc::umma_commit_mc(bar_empty0 + 8u * s, (uint16_t)3);   // ... in both CTAs of the pair
-                            else tc::umma_commit(bar_empty0 + 8u * s);
+                            if (c.cluster == 2) tc::umma_commit_mc_e(bar_empty0 + 8u * s, (uint16_t)3, el);   // ... in both CTAs of the pair
+                            else tc::umma_commit_e(bar_empty0 + 8u * s, el);
                         }
                         if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                     }
                 }
                 if (!real) continue;
-                tc::umma_commit(bar_aempty0 + 8u * abuf);                     // activation buffer may be refilled
+                tc::umma_commit_e(bar_aempty0 + 8u * abuf, el);                     // activation buffer may be refilled
                 if (++abuf == (uint32_t)c.nabuf) { abuf = 0; aph ^= 1u; }
                 }
                 if (c.resident) s = 0;
                 if (!real) continue;
-                tc::umma_commit(bar_accfull0 + 8u * cbuf);                    // accumulator ready for the epilogue
+                tc::umma_commit_e(bar_accfull0 + 8u * cbuf, el);                    // accumulator ready for the epilogue
                 TC_STAMP((int)it, 12);
                 if (++cbuf == (uint32_t)c.naccbuf) { cbuf = 0; cph ^= 1u; }
             }

@@ -9,6 +9,7 @@
 // ends with the only host sync of the path: the per-utterance frame counts.  Phase 2
 // (vits_decode) runs the frame side in chunks bounded by a frame budget.
 #include "../../include/vits_b200.h"
+#include "../../include/vits_b200_test.h"
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "attention.cuh"
@@ -95,9 +96,13 @@ struct vits_handle {
     bool prepared = false;
     int64_t total_frames = 0;
     int last_chunk_frames = 0;
+    int last_nchunks = 0;             // chunks of the last vits_decode (chunk tensors can only be fetched when it was one)
+    cudaStream_t own_stream = nullptr;   // the stream vits_create made (h->stream is this one unless vits_set_stream gave another)
+    int64_t ticket = 0;               // number of vits_decode calls that produced host output so far
+    int64_t ticket_of[2] = {0, 0};    // ticket whose transfer ev_out[i] tracks
 
     Buf ids, cu_t, tile_t, sid, x, y, qkv, att, ffn, stats, d0, d1, gdp, hp, z0, z1, logw, dur, cum, ylen;
-    Buf inj_dp, inj_z;
+    Buf inj_dp, inj_z, dbg_dp, audio16_alt;
     Buf chunk_meta, tdesc, P, fh, facts, fskip, fidx, dpre, sX, sT1, sYa, sYb, sXSa, sXSb, audio, peaks, audio16, cu_y_dev, dbg_zp, mrf_dbg, conv_dbg;
     int conv_counter = 0;
 
@@ -456,6 +461,7 @@ int vits_create(const vits_arch* arch, int device_id, vits_handle** out) {
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h; return VITS_E_CUDA;
     }
+    h->own_stream = h->stream;
     cudaEventCreate(&h->ev_t0); cudaEventCreate(&h->ev_t1);
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_chunk, cudaEventDisableTiming);
@@ -767,6 +773,12 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         if ((rc = launch_conv_text(h, h->dp_proj, a, T))) return rc;
         k_noise_dp<<<(R + 255) / 256, 256, 0, st>>>(z0, z1, d_inj, dp_stride, T.cu, B, (int)R, h->scales[2], seed, h->utt_base);
         h->launches++;
+        if (h->opts.count("debug_keep_noise_dp") && h->opts["debug_keep_noise_dp"] != 0) {
+            // test hook: the duration predictor's noise (models.py:111) as drawn, [z0 | z1], before the flows overwrite it
+            if ((rc = ensure(h, h->dbg_dp, (size_t)R * 2 * 4))) return rc;
+            CK(h, cudaMemcpyAsync(h->dbg_dp.p, z0, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+            CK(h, cudaMemcpyAsync(ptr<float>(h->dbg_dp) + R, z1, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+        }
         for (int k = 0; k < A.n_cflows; k++) {
             std::swap(z0, z1);                                   // Flip (modules.py:386)
             auto& cf = h->cflows[k];
@@ -812,6 +824,8 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
     h->h_cu_y.assign(B + 1, 0);
     int64_t tot = 0;
     for (int b = 0; b < B; b++) {
+        // k_durations saturates an utterance's frame count at INT_MAX instead of wrapping
+        if (h->h_ylen[b] < 1 || h->h_ylen[b] > (1 << 30)) return fail(h, VITS_E_INVALID, "durations overflow: utterance %d has more than 2^30 frames", b);
         tot += h->h_ylen[b];
         if (tot > (1ll << 30)) return fail(h, VITS_E_INVALID, "durations overflow: more than 2^30 frames");
         h->h_cu_y[b + 1] = (int)tot;
@@ -833,7 +847,9 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
     h->conv_counter = 0;
     int hop = 1; for (int i = 0; i < A.n_ups; i++) hop *= A.up_rates[i];
     const int64_t total_samples = h->total_frames * hop;
-    if (out_kind < 0 || out_kind > 2) return fail(h, VITS_E_INVALID, "out_kind %d", out_kind);
+    const bool async_flag = (out_kind & VITS_OUT_ASYNC) != 0;
+    out_kind &= ~VITS_OUT_ASYNC;
+    if (out_kind < 0 || out_kind > 3) return fail(h, VITS_E_INVALID, "out_kind %d", out_kind);
     if (out_kind != 0 && (!out || out_capacity < total_samples)) return fail(h, VITS_E_INVALID, "output buffer too small: %lld < %lld samples", (long long)out_capacity, (long long)total_samples);
     if (noise_z) for (int b = 0; b < B; b++) if (z_stride < h->h_ylen[b]) return fail(h, VITS_E_INVALID, "noise_z stride %lld < frames %d of utterance %d", (long long)z_stride, h->h_ylen[b], b);
     CK(h, cudaSetDevice(h->device));
@@ -853,7 +869,20 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
     Buf& abuf = asel ? h->audio_alt : h->audio;
     if ((rc = ensure(h, abuf, std::max<int64_t>(total_samples, 1) * 4))) return rc;
     float* audio = ptr<float>(abuf);
-    const bool async_out = h->opts.count("async_output") && h->opts["async_output"] != 0;
+    const bool async_out = async_flag || (h->opts.count("async_output") && h->opts["async_output"] != 0);
+    // int16 results (out_kind 2) leave per chunk like fp32 ones: chunks are whole utterances, so the per-utterance peak is known
+    // when the chunk's kernels finish; two device buffers alternate like the fp32 ones
+    int16_t* audio16 = nullptr;
+    if (out_kind == 2) {
+        Buf& a16 = asel ? h->audio16_alt : h->audio16;
+        if ((rc = ensure(h, a16, std::max<int64_t>(total_samples, 1) * 2 + 16)) || (rc = ensure(h, h->peaks, (size_t)B * 4)) ||
+            (rc = ensure(h, h->cu_y_dev, (size_t)(B + 1) * 4)))
+            return rc;
+        audio16 = ptr<int16_t>(a16);
+        CK(h, cudaMemcpyAsync(h->cu_y_dev.p, h->h_cu_y.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemsetAsync(h->peaks.p, 0, (size_t)B * 4, st));
+    }
+    h->last_nchunks = 0;
     // per-stage geometry
     std::vector<int> rates(A.n_ups + 1), chans(A.n_ups + 1);
     rates[0] = 1; chans[0] = A.up_init;
@@ -869,6 +898,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         const int nB = b_hi - b_lo;
         const int Fr = (int)fr;
         const int f_lo = h->h_cu_y[b_lo];
+        h->last_nchunks++;
         std::vector<int> cu_local(nB + 1);
         for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
         // fused MRF stage kernel (mrf3_tc.cuh; mrf2_tc.cuh / mrf_tc.cuh with options mrf_v2 / mrf_v1, kept as test references) where the stage qualifies: bf16 mode,
@@ -985,7 +1015,9 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         h->launches++;
         {
             long n = (long)Fr * (C / 4);
-            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ptr<float>(h->stats), ptr<int>(h->fidx), ptr<int2>(h->fpos),
+            // test hook "debug_eps": m_p = logs_p = 0, so z_p IS the noise draw (times noise_scale) -- the statistical test of the device RNG
+            const float* stats_in = (h->opts.count("debug_eps") && h->opts["debug_eps"] != 0) ? nullptr : ptr<float>(h->stats);
+            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_in, ptr<int>(h->fidx), ptr<int2>(h->fpos),
                                                                          d_injz, z_stride, h->scales[0], h->seed, h->utt_base, P, Fr, C);
             h->launches++;
         }
@@ -1208,35 +1240,37 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         CK(h, cudaGetLastError());
         stage_end(h);
-        if (out_kind == 1) {
+        if (out_kind == 2) {
+            // caller-side post-processing on device (voice.py:271-282, 88-91) for this chunk's utterances
+            dim3 g(32, (unsigned)std::min(nB, 65535));
+            k_absmax<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo);
+            k_to_int16<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo, normalize, volume, audio16);
+            h->launches += 2;
+            CK(h, cudaGetLastError());
+        }
+        if (out_kind == 1 || out_kind == 2) {
             // this chunk's audio leaves on the copy stream while the next chunk computes
             CK(h, cudaEventRecord(h->ev_chunk, st));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk, 0));
+            if (out_kind == 1)
+                CK(h, cudaMemcpyAsync(static_cast<float*>(out) + (int64_t)f_lo * hop, audio + (int64_t)f_lo * hop, (size_t)Fr * hop * 4,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+            else
+                CK(h, cudaMemcpyAsync(static_cast<int16_t*>(out) + (int64_t)f_lo * hop, audio16 + (int64_t)f_lo * hop, (size_t)Fr * hop * 2,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+        } else if (out_kind == 3) {
+            // device-resident result: `out` is a device pointer of the caller; stream-ordered, no host synchronisation
             CK(h, cudaMemcpyAsync(static_cast<float*>(out) + (int64_t)f_lo * hop, audio + (int64_t)f_lo * hop, (size_t)Fr * hop * 4,
-                                  cudaMemcpyDeviceToHost, h->copy_stream));
+                                  cudaMemcpyDeviceToDevice, st));
         }
         b_lo = b_hi;
     }
     // ---- output
-    if (out_kind == 1) {
+    if (out_kind == 1 || out_kind == 2) {
         CK(h, cudaEventRecord(h->ev_out[asel], h->copy_stream));
         h->out_pending[asel] = true;
+        h->ticket_of[asel] = ++h->ticket;
         if (!async_out) { CK(h, cudaEventSynchronize(h->ev_out[asel])); h->out_pending[asel] = false; }
-    } else if (out_kind == 2) {
-        // caller-side post-processing on device (voice.py:271-282, 88-91)
-        if ((rc = ensure(h, h->peaks, B * 4)) || (rc = ensure(h, h->cu_y_dev, (B + 1) * 4)) ||
-            (rc = ensure(h, h->audio16, total_samples * 2 + 16)))
-            return rc;
-        CK(h, cudaMemcpyAsync(h->cu_y_dev.p, h->h_cu_y.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
-        CK(h, cudaMemsetAsync(h->peaks.p, 0, B * 4, st));
-        dim3 g(32, B);
-        k_absmax<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev), B, hop, ptr<unsigned int>(h->peaks));
-        k_to_int16<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev), B, hop, ptr<unsigned int>(h->peaks), normalize, volume,
-                                      ptr<int16_t>(h->audio16));
-        h->launches += 2;
-        CK(h, cudaGetLastError());
-        CK(h, cudaMemcpyAsync(out, h->audio16.p, total_samples * 2, cudaMemcpyDeviceToHost, st));
-        CK(h, cudaStreamSynchronize(st));
     }
     return VITS_OK;
 }
@@ -1254,9 +1288,15 @@ int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity
     else if (k == "logw") { src = h->logw.p; n = R; }
     else if (k == "durations") { src = h->dur.p; n = R; }
     else if (k == "cum") { src = h->cum.p; n = R; }
-    else if (k == "frame_index") { src = h->fidx.p; n = Fr; }
-    else if (k == "z_p") { src = h->dbg_zp.p; n = h->dbg_zp.p ? Fr * A.inter : 0; }
-    else if (k == "z") { src = h->P.p; n = Fr * A.inter; }
+    else if (k == "noise_dp") { src = h->dbg_dp.p; n = h->dbg_dp.p ? 2 * R : 0; }
+    else if (k == "frame_index" || k == "z_p" || k == "z") {
+        // per-chunk workspaces: after a multi-chunk decode they hold the LAST chunk only -- refuse instead of returning a fragment
+        if (h->last_nchunks != 1)
+            return fail(h, VITS_E_STATE, "stage tensor '%s' is per chunk and the last vits_decode used %d chunks (raise max_chunk_frames or fetch after a single-chunk call)", name, h->last_nchunks);
+        if (k == "frame_index") { src = h->fidx.p; n = Fr; }
+        else if (k == "z_p") { src = h->dbg_zp.p; n = h->dbg_zp.p ? Fr * A.inter : 0; }
+        else { src = h->P.p; n = Fr * A.inter; }
+    }
     else if (k == "conv_dbg") { src = h->conv_dbg.p; n = h->conv_dbg.p ? TC_DBG_TILES * 16 * 2 : 0; }
     else if (k == "mrf_dbg") { src = h->mrf_dbg.p; n = h->mrf_dbg.p ? MRF2_DBG_TILES * 48 * 2 : 0; }
     else return fail(h, VITS_E_INVALID, "unknown stage tensor '%s'", name);
@@ -1368,6 +1408,60 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
     return rc;
 }
 
+int vits_describe(vits_handle* h, vits_info* info) {
+    if (!h || !info) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const vits_arch& A = h->A;
+    memset(info, 0, sizeof *info);
+    int hop = 1; for (int i = 0; i < A.n_ups; i++) hop *= A.up_rates[i];
+    info->n_vocab = A.n_vocab; info->n_speakers = A.n_speakers; info->has_sid = A.n_speakers > 1;
+    info->hidden = A.hidden; info->inter = A.inter; info->sample_rate = A.sample_rate; info->hop = hop;
+    info->resblock_type = A.resblock_type; info->use_sdp = A.use_sdp; info->precision = h->precision;
+    info->device = h->device; info->num_sms = h->num_sms; info->finalized = h->finalized ? 1 : 0;
+    return VITS_OK;
+}
+
+int64_t vits_max_output_samples(vits_handle* h, int64_t sum_ids, float length_scale) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const vits_arch& A = h->A;
+    int64_t hop = 1; for (int i = 0; i < A.n_ups; i++) hop *= A.up_rates[i];
+    // after a successful vits_prepare the frame count is known exactly (the durations are data): that is what vits_decode needs
+    if (sum_ids <= 0) return h->prepared ? h->total_frames * hop : (int64_t)VITS_E_STATE;
+    // before it, only a planning figure exists: durations are ceil(exp(logw) * length_scale) per id, unbounded in principle
+    // (the kernel clamps a single id at 10^6 frames); 16 frames per id at length_scale 1 has never been exceeded by a voice we have
+    // seen (mean 3.5, p99 6, max 12) -- callers must still size the real buffer from vits_prepare's total_frames
+    const double per_id = 16.0 * (length_scale > 0.f ? (double)length_scale : 1.0);
+    return (int64_t)std::ceil((double)sum_ids * per_id) * hop;
+}
+
+int vits_set_stream(vits_handle* h, void* cuda_stream) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));          // nothing of ours is left behind on the old stream
+    resolve_stage_events(h);
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return VITS_OK;
+}
+
+int64_t vits_output_ticket(vits_handle* h) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return h->ticket;
+}
+
+int vits_wait_ticket(vits_handle* h, int64_t ticket) {
+    if (!h) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(h, cudaSetDevice(h->device));
+    // a transfer older than the two tracked ones finished before its device buffer was reused (vits_decode waits for that)
+    for (int i = 0; i < 2; i++)
+        if (h->ticket_of[i] == ticket && h->out_pending[i]) { CK(h, cudaEventSynchronize(h->ev_out[i])); h->out_pending[i] = false; }
+    if (ticket > h->ticket) return fail(h, VITS_E_INVALID, "ticket %lld has not been issued (last: %lld)", (long long)ticket, (long long)h->ticket);
+    return VITS_OK;
+}
+
 int vits_wait_output(vits_handle* h, int older_only) {
     if (!h) return VITS_E_INVALID;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1421,12 +1515,13 @@ void vits_destroy(vits_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->own_stream != h->stream) cudaStreamSynchronize(h->own_stream);
     resolve_stage_events(h);
     for (auto& kv : h->blobs) cudaFree(kv.second.p);
     Buf* bufs[] = {&h->ids, &h->tile_t, &h->sid, &h->x, &h->y, &h->qkv, &h->att, &h->ffn, &h->stats, &h->d0, &h->d1,
                    &h->gdp, &h->hp, &h->z0, &h->z1, &h->logw, &h->dur, &h->cum, &h->ylen, &h->inj_dp, &h->inj_z,
                    &h->chunk_meta, &h->tdesc, &h->P, &h->fh, &h->facts, &h->fskip, &h->fidx, &h->dpre, &h->sX, &h->sT1, &h->sYa,
-                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos, &h->fpos};
+                   &h->sYb, &h->sXSa, &h->sXSb, &h->audio, &h->peaks, &h->audio16, &h->cu_y_dev, &h->dbg_zp, &h->mrf_dbg, &h->conv_dbg, &h->audio_alt, &h->facts_b, &h->tdesc_t, &h->tdesc_c, &h->sX1b, &h->rowpos, &h->fpos, &h->dbg_dp, &h->audio16_alt};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     for (float* pz : h->rb_b2sum) if (pz) cudaFree(pz);
     for (void* pz : h->owned) cudaFree(pz);
@@ -1436,7 +1531,7 @@ void vits_destroy(vits_handle* h) {
     for (int i = 0; i < 2; i++) if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 

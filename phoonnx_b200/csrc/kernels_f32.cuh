@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) k_durations(const float* __restrict__ log
                                                    const int* __restrict__ cu, int* __restrict__ dur,
                                                    int* __restrict__ cum, int* __restrict__ y_len) {
     __shared__ int wsum[8];
-    __shared__ int carry_s;
+    __shared__ long long carry_s;      // 64-bit: 2^20 ids x 10^6 frames would wrap an int; cum / y_len saturate at INT_MAX and the host rejects
     const int b = blockIdx.x;
     const int r0 = cu[b], T = cu[b + 1] - r0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -531,14 +531,14 @@ __global__ void __launch_bounds__(256) k_durations(const float* __restrict__ log
         __syncthreads();
         int woff = 0;
         for (int k = 0; k < warp; k++) woff += wsum[k];
-        const int carry = carry_s;
-        const int incl = carry + woff + v;
-        if (t < T) { dur[r0 + t] = d; cum[r0 + t] = incl; }
+        const long long carry = carry_s;
+        const long long incl = carry + (long long)woff + (long long)v;      // a 256-id block sums to <= 2.56e8: woff + v fits an int
+        if (t < T) { dur[r0 + t] = d; cum[r0 + t] = (int)min(incl, (long long)INT_MAX); }
         __syncthreads();
         if (tid == 255) carry_s = incl;
         __syncthreads();
     }
-    if (tid == 0) y_len[b] = max(carry_s, 1);
+    if (tid == 0) y_len[b] = (int)min(max(carry_s, 1ll), (long long)INT_MAX);
 }
 
 // frame j of utterance b -> phoneme index: first t with cum[t] > j (searchsorted right), -1 if none
@@ -574,7 +574,7 @@ __global__ void k_expand_sample(const float* __restrict__ stats, const int* __re
     const int src = __ldg(fidx + f);
     const int2 bj = __ldg(fpos + f);
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f), lg = m;
-    if (src >= 0) {
+    if (src >= 0 && stats) {          // stats == nullptr: test hook, z_p = eps * noise_scale
         m = __ldg(reinterpret_cast<const float4*>(stats + (long)src * 2 * C + c));
         lg = __ldg(reinterpret_cast<const float4*>(stats + (long)src * 2 * C + C + c));
     }
@@ -641,28 +641,30 @@ __global__ void __launch_bounds__(256) k_conv_post(const float* __restrict__ x, 
 // ------------------------------------------------------------------------------------------
 __global__ void k_absmax(const float* __restrict__ audio, const int* __restrict__ cu, int B, int rate,
                          unsigned int* __restrict__ peak_bits) {
-    // grid: (chunks, B)
-    const int b = blockIdx.y;
-    const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
-    float m = 0.f;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(audio[s0 + i]));
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order as uints
+    // grid: (chunks, min(B, 65535)); utterances beyond the grid's y extent are covered by the loop
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
+        float m = 0.f;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+            m = fmaxf(m, fabsf(audio[s0 + i]));
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) atomicMax(peak_bits + b, __float_as_uint(m));   // non-negative floats order as uints
+    }
 }
 __global__ void k_to_int16(const float* __restrict__ audio, const int* __restrict__ cu, int B, int rate,
                            const unsigned int* __restrict__ peak_bits, int normalize, float volume,
                            int16_t* __restrict__ out) {
-    const int b = blockIdx.y;
-    const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
-    const float peak = __uint_as_float(peak_bits[b]);
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        float v = audio[s0 + i];
-        if (normalize) v = (peak < 1e-8f) ? 0.f : (v / peak);
-        if (volume != 1.f) v = v * volume;
-        v = fminf(fmaxf(v, -1.f), 1.f);
-        float s = v * 32767.0f;
-        s = fminf(fmaxf(s, -32767.f), 32767.f);
-        out[s0 + i] = (int16_t)s;      // numpy astype(int16) truncates toward zero, as does this cast
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
+        const float peak = __uint_as_float(peak_bits[b]);
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+            float v = audio[s0 + i];
+            if (normalize) v = (peak < 1e-8f) ? 0.f : (v / peak);
+            if (volume != 1.f) v = v * volume;
+            v = fminf(fmaxf(v, -1.f), 1.f);
+            float s = v * 32767.0f;
+            s = fminf(fmaxf(s, -32767.f), 32767.f);
+            out[s0 + i] = (int16_t)s;      // numpy astype(int16) truncates toward zero, as does this cast
+        }
     }
 }

@@ -88,6 +88,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 }  // namespace tc
 
+// Issue order of the 2 * n_r convs of a tile (round 2).  Round 1 issued every conv1 first and then the conv2s back to back; with ONE
+// x1 operand tile each conv2 -> stage x1(r+1) -> conv2 hand-off then idled the tensor pipe (r02a timeline: 0.4-1.0k cycles each, ~3.5k
+// of a 19k-cycle tile).  Interleaved -- C1(0) C1(1) C2(0) C1(2) C2(1) ... C2(n_r - 1) -- conv1(r+1) runs while the epilogue warps turn
+// conv1(r) into x1(r), and conv2(r-1) while they work on conv1(r): every conv2 finds its operand staged and the x1 tile free.
+__device__ __forceinline__ void mrf3_step(int step, int nrb, int& cv, int& r) {
+    if (step == 0) { cv = 0; r = 0; }
+    else if (step == 2 * nrb - 1) { cv = 1; r = nrb - 1; }
+    else { const int j = step - 1; cv = j & 1; r = cv ? (j >> 1) : (j >> 1) + 1; }
+}
+
 #define MRF3_SP_PITCH 9
 #define MRF3_STAMP(it_, slot_) do { if (dbg_on && (it_) < MRF3_DBG_TILES) a.dbg[(it_) * 48 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
@@ -120,7 +130,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     uint8_t* sWp = smem + c.postw_off;
     float* sP = reinterpret_cast<float*>(smem + c.sp_off);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform in a form ptxas can see (role branches stay converged)
     const bool post = a.post_w != nullptr;
     const bool modeU = a.up_u != 0;
     if (tid == 0) {
@@ -337,6 +348,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 tc::tc_fence_before();
                 tc::mbar_arrive(bar_x1);
                 MRF3_STAMP(it, 7 + 4 * r);
+                if (a.dbg != nullptr && blockIdx.x == 0 && tid == 480 && it < MRF3_DBG_TILES) a.dbg[it * 48 + (r == 0 ? 23 : 41 + r)] = (unsigned long long)clock64();   // the same event seen by warp 15
             }
             n_x1e += (uint32_t)a.nrb;
             if (modeU && tile + (int)gridDim.x < a.ntiles) {
@@ -412,25 +424,28 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         if (post && have_prev) post_epilogue();
     } else if (warp == MRF3_EPI_WARPS) {
         // ===================== weight producer =====================
-        if (tc::elect_one()) {
+        {
+            // the whole warp runs the loop converged; only the copies / arrivals are predicated on the elected lane (conv_tc.cuh)
+            const uint32_t el = tc::elect_flag();
             if (modeU) {
-                tc::mbar_expect_tx(bar_upw, (uint32_t)c.upw_bytes);
+                tc::mbar_expect_tx_e(bar_upw, (uint32_t)c.upw_bytes, el);
                 const uint32_t half_bytes = (uint32_t)c.upw_bytes >> 1;
-                tc::bulk_g2s(tc::smem_u32(sUW), a.up_w[0], half_bytes, bar_upw);
-                tc::bulk_g2s(tc::smem_u32(sUW) + half_bytes, a.up_w[1], half_bytes, bar_upw);
+                tc::bulk_g2s_e(tc::smem_u32(sUW), a.up_w[0], half_bytes, bar_upw, el);
+                tc::bulk_g2s_e(tc::smem_u32(sUW) + half_bytes, a.up_w[1], half_bytes, bar_upw, el);
             }
             uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its "empty" barrier
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 if (c.resident && tile != (int)blockIdx.x) break;
-                // issue order of the MMA warp: C1(0) C1(1) C1(2) | C2(0) C2(1) C2(2)
-                for (int cv = 0; cv < 2; cv++)
-                    for (int r = 0; r < a.nrb; r++) {
+                // same order as the MMA warps issue the convs (mrf3_step): C1(0) C1(1) C2(0) C1(2) C2(1) C2(2)
+                for (int step = 0; step < 2 * a.nrb; step++) {
+                        int cv, r;
+                        mrf3_step(step, a.nrb, cv, r);
                         const __nv_bfloat16* wsrc = a.w[r][cv];
                         for (int tap = 0; tap < a.k[r]; tap++) {
                             if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
                             const uint32_t fb = bar_full0 + 8u * s;
-                            tc::mbar_expect_tx(fb, (uint32_t)c.slot_bytes);
-                            tc::bulk_g2s(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb);
+                            tc::mbar_expect_tx_e(fb, (uint32_t)c.slot_bytes, el);
+                            tc::bulk_g2s_e(tc::smem_u32(sW) + s * (uint32_t)c.slot_bytes, wsrc, (uint32_t)c.slot_bytes, fb, el);
                             wsrc += C * C;
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
@@ -442,7 +457,11 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         const int mw = (warp == MRF3_EPI_WARPS + 3) ? 1 : 0;
         const int bb_lo = mw * (c.nb / c.nmw), bb_hi = bb_lo + c.nb / c.nmw;
         const int ub_lo = (c.nmw == 2 && c.nub == 2) ? mw : 0, ub_hi = (c.nmw == 2 && c.nub == 2) ? mw + 1 : (mw == 0 ? c.nub : 0);
-        if (mw < c.nmw && tc::elect_one()) {
+        if (mw < c.nmw) {
+            // warp-uniform issue loop: all 32 lanes run it converged (and wait on the barriers); tcgen05.mma / tcgen05.commit are
+            // predicated on the elected lane, descriptors and barrier addresses live in uniform registers (conv_tc.cuh, round 2)
+            const uint32_t el = tc::elect_flag();
+            const uint32_t tmem_base = tc::uniform_u32(*tmem_slot);
             const uint32_t idesc = tc::make_idesc(128, C), idesc_post = tc::make_idesc(128, 16), idesc_up = tc::make_idesc(128, N2 > 0 ? N2 : 16);
             const uint32_t sX_u = tc::smem_u32(sX), sX1_u = tc::smem_u32(sX1), sW_u = tc::smem_u32(sW);
             const uint64_t dhi_x = tc::make_desc(0, lbo_x, 128u), dhi_x1 = tc::make_desc(0, lbo_x1, 128u), dhi_w = tc::make_desc(0, lbo_w, 128u);
@@ -457,7 +476,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             uint32_t s = 0, ph = 0, it = 0, n_x1 = 0;           // ring slot / parity of its "full" barrier
             const uint32_t slot16 = (uint32_t)c.slot_bytes >> 4;
             const int nbw = bb_hi - bb_lo;                     // M blocks of this warp: 1 or 2
-            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && mw == 0;
+            const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && mw == 0 && el != 0;
             // ---- ConvTranspose1d as a GEMM over input rows: accumulator (ub) columns [half * N2, +N2) = taps of that half
             auto issue_ups = [&](uint32_t itn) {
                 tc::mbar_wait(bar_in, itn & 1);
@@ -471,13 +490,13 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                             uint64_t ad = dhi_u | (uint64_t)((u16 + (uint32_t)(ub * 128 + half + tap)) & 0x3FFF);
                             uint64_t bd = dhi_uw | (uint64_t)((uw16 + (uint32_t)(half * 2 + tap) * uw_tap16) & 0x3FFF);
                             for (int k16 = 0; k16 < (a.up_cin >> 4); k16++) {
-                                tc::umma_bf16(dcol, ad, bd, idesc_up, (tap > 0 || k16) ? 1u : 0u);
+                                tc::umma_bf16_e(dcol, ad, bd, idesc_up, (tap > 0 || k16) ? 1u : 0u, el);
                                 ad += ad_step_u; bd += bd_step_u;
                             }
                         }
                     }
-                tc::umma_commit(bar_in_free);             // the loader may overwrite sU
-                tc::umma_commit(bar_ups);
+                tc::umma_commit_e(bar_in_free, el);             // the loader may overwrite sU
+                tc::umma_commit_e(bar_ups, el);
                 MRF3_STAMP((int)itn, 21);
             };
             // conv_post partial sums P[t][tap] of tile `itp` over its stage output sitting in sX1 (tap offset 0, N = 16).  Issued
@@ -493,11 +512,11 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     uint64_t bd = dhi_wp | (uint64_t)(wp16 & 0x3FFF);
 #pragma unroll
                     for (int k16 = 0; k16 < C / 16; k16++) {
-                        tc::umma_bf16(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, k16 ? 1u : 0u);
+                        tc::umma_bf16_e(tmem_base + accp_col + (uint32_t)(bb * 16), ad, bd, idesc_post, k16 ? 1u : 0u, el);
                         ad += ad_step_x1; bd += 32u;     // two 8-channel chunks of 16 x 16 B
                     }
                 }
-                tc::umma_commit(bar_post_done);
+                tc::umma_commit_e(bar_post_done, el);
                 MRF3_STAMP((int)itp, 41);
             };
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
@@ -509,13 +528,17 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                     tc::tc_fence_after();
                 }
                 MRF3_STAMP((int)it, 22);
-                for (int cv = 0; cv < 2; cv++) {
-                    for (int r = 0; r < a.nrb; r++) {
+                for (int step = 0; step < 2 * a.nrb; step++) {
+                    {
+                        int cv, r;
+                        mrf3_step(step, a.nrb, cv, r);
                         if (cv == 1) {
                             // the next tile's ConvTranspose goes in before the last conv2: its accumulators (conv1 buffers 0..) were
                             // drained when x1(n_r - 2) was staged, and E0 of the next tile then runs under conv2(n_r - 1)
                             if (modeU && r == a.nrb - 1 && tile + (int)gridDim.x < a.ntiles) issue_ups(it + 1);
+                            MRF3_STAMP((int)it, 36 + r);
                             tc::mbar_wait(bar_x1, n_x1 & 1); n_x1++;                       // x1(r) staged, acc1[r] drained
+                            if (r == 0) MRF3_STAMP((int)it, 18);
                             if (r == 0 && it > 0) tc::mbar_wait(bar_acc2_free, (it - 1) & 1);   // previous tile's output drained
                             tc::tc_fence_after();
                         } else if (post && it > 0) {
@@ -542,16 +565,16 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                             const uint32_t acc0 = tap > 0 ? 1u : acc_first;
 #pragma unroll
                             for (int k16 = 0; k16 < C / 16; k16++)
-                                tc::umma_bf16_lh(dcol0, alo + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0);
+                                tc::umma_bf16_lh_e(dcol0, alo + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0, el);
                             if (nbw == 2) {
 #pragma unroll
                                 for (int k16 = 0; k16 < C / 16; k16++)
-                                    tc::umma_bf16_lh(dcol0 + (uint32_t)C, alo + 128u + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0);
+                                    tc::umma_bf16_lh_e(dcol0 + (uint32_t)C, alo + 128u + (uint32_t)k16 * a_k16, ahi, blo + (uint32_t)k16 * b_k16, bhi, idesc, k16 ? 1u : acc0, el);
                             }
-                            if (!c.resident) tc::umma_commit(bar_empty0 + 8u * s);
+                            if (!c.resident) tc::umma_commit_e(bar_empty0 + 8u * s, el);
                             if (++s == (uint32_t)c.nstages) { s = 0; ph ^= 1u; }
                         }
-                        tc::umma_commit(cv ? bar_c2 : (bar_c1 + 8u * (uint32_t)r));
+                        tc::umma_commit_e(cv ? bar_c2 : (bar_c1 + 8u * (uint32_t)r), el);
                         MRF3_STAMP((int)it, 25 + 2 * (cv * 3 + r));
                     }
                 }

@@ -39,6 +39,12 @@ class CArch(C.Structure):
     ]
 
 
+class CInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_speakers", "has_sid", "hidden", "inter", "sample_rate", "hop",
+                                         "resblock_type", "use_sdp", "precision", "device", "num_sms", "finalized")] + \
+               [("reserved", C.c_int32 * 8)]
+
+
 def to_c_arch(a: VitsArch) -> CArch:
     c = CArch()
     for f in ("n_vocab", "hidden", "inter", "filter", "n_heads", "n_layers", "enc_kernel", "window", "n_speakers",
@@ -106,6 +112,15 @@ def load_library(path: Optional[str] = None):
     lib.vits_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.vits_host_free.argtypes = [C.c_void_p]
     lib.vits_wait_output.argtypes = [H, C.c_int]
+    lib.vits_describe.argtypes = [H, C.POINTER(CInfo)]
+    lib.vits_max_output_samples.argtypes = [H, C.c_int64, C.c_float]
+    lib.vits_max_output_samples.restype = C.c_int64
+    lib.vits_set_stream.argtypes = [H, C.c_void_p]
+    lib.vits_output_ticket.argtypes = [H]
+    lib.vits_output_ticket.restype = C.c_int64
+    lib.vits_wait_ticket.argtypes = [H, C.c_int64]
+    for fn in ("vits_describe", "vits_set_stream", "vits_wait_ticket"):
+        getattr(lib, fn).restype = C.c_int
     for fn in ("vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare", "vits_decode",
                "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_host_alloc", "vits_host_free", "vits_wait_output"):
         getattr(lib, fn).restype = C.c_int
@@ -118,7 +133,11 @@ EXPORTED_SYMBOLS = (
     "vits_abi_version", "vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare",
     "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_launch_count",
     "vits_last_error", "vits_destroy", "vits_host_alloc", "vits_host_free", "vits_wait_output",
+    "vits_describe", "vits_max_output_samples", "vits_set_stream", "vits_output_ticket", "vits_wait_ticket",
 )
+# include/vits_b200_test.h: test-only hooks, not part of the drop-in boundary
+TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe")
+VITS_OUT_ASYNC = 0x100
 
 _DT = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.int32): 2}
 
@@ -143,14 +162,25 @@ class _PinnedBlock:
 
 
 class PinnedPool:
-    """Size-classed pool of cudaHostAlloc'd blocks (vits_host_alloc): allocation costs milliseconds, reuse is free."""
+    """Size-classed pool of cudaHostAlloc'd blocks (vits_host_alloc): allocation costs milliseconds, reuse is free.
+    Classes are powers of two up to 256 MiB and multiples of 64 MiB above (a 2.2 GB result pins 2.25 GB, not 4)."""
+
+    BIG = 256 << 20
+    STEP = 64 << 20
 
     def __init__(self, lib, max_cached_bytes: int = 8 << 30):
         self.lib, self.free, self.cached, self.max_cached = lib, {}, 0, max_cached_bytes
+        self.closed = False
+
+    @classmethod
+    def size_class(cls, nbytes: int) -> int:
+        if nbytes <= cls.BIG:
+            return 1 << max(16, (nbytes - 1).bit_length())
+        return (nbytes + cls.STEP - 1) // cls.STEP * cls.STEP
 
     def take(self, n: int, dtype) -> np.ndarray:
         nbytes = max(1, n * np.dtype(dtype).itemsize)
-        cls = 1 << max(16, (nbytes - 1).bit_length())
+        cls = self.size_class(nbytes)
         lst = self.free.get(cls)
         if lst:
             blk = lst.pop()
@@ -163,13 +193,16 @@ class PinnedPool:
         return blk.array(n, dtype)
 
     def _give_back(self, blk):
-        if self.cached + blk.nbytes > self.max_cached:
+        # after close() nothing is cached any more: a block whose last array dies later is freed on the spot
+        if self.closed or self.cached + blk.nbytes > self.max_cached:
             self.lib.vits_host_free(C.c_void_p(blk.ptr))
             return
         self.free.setdefault(blk.nbytes, []).append(blk)
         self.cached += blk.nbytes
 
-    def drain(self):
+    def drain(self, close: bool = False):
+        if close:
+            self.closed = True
         for lst in self.free.values():
             for blk in lst:
                 self.lib.vits_host_free(C.c_void_p(blk.ptr))
@@ -201,6 +234,7 @@ class Engine:
         self._B = 0
         self._ylen = None
         self._pool = PinnedPool(self.lib)
+        self.last_ticket = 0
 
     # ------------------------------------------------------------------
     def _check(self, rc: int):
@@ -252,7 +286,10 @@ class Engine:
         return ylen
 
     def decode(self, noise_z: Optional[np.ndarray] = None, out: str = "f32", volume: float = 1.0,
-               normalize: bool = True) -> Optional[np.ndarray]:
+               normalize: bool = True, asynchronous: bool = False) -> Optional[np.ndarray]:
+        """``asynchronous=True`` (host outputs only): returns as soon as the device->host transfer is enqueued; the array is
+        complete after ``wait_ticket(self.last_ticket)``.  It is a per-call flag -- a blocking decode() issued while an
+        asynchronous result is still in flight waits for ITS OWN buffer only and does not disturb the other one."""
         if self._ylen is None:
             raise RuntimeError("decode() before prepare()")
         total = int(self._ylen.sum()) * self.hop
@@ -265,20 +302,42 @@ class Engine:
         if out == "none":
             self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 0, None, 0, volume, int(normalize)))
             return None
-        if out == "f32":
-            # page-locked result: the device->host transfer is a DMA on the copy stream; with set_async_output(True)
-            # it is still in flight when this returns and wait_output() completes it
-            buf = self._pool.take(total, np.float32)
-            self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 1, _ptr(buf), total, volume, int(normalize)))
-            return buf
-        if out == "i16":
-            buf = self._pool.take(total, np.int16)
-            self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 2, _ptr(buf), total, volume, int(normalize)))
-            return buf
-        raise ValueError("out must be 'none', 'f32' or 'i16'")
+        if out not in ("f32", "i16"):
+            raise ValueError("out must be 'none', 'f32' or 'i16'")
+        # page-locked result: the device->host transfer is a DMA on the copy stream, chunk by chunk
+        kind = (1 if out == "f32" else 2) | (VITS_OUT_ASYNC if asynchronous else 0)
+        buf = self._pool.take(total, np.float32 if out == "f32" else np.int16)
+        self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, kind, _ptr(buf), total, volume, int(normalize)))
+        self.last_ticket = int(self.lib.vits_output_ticket(self._h))
+        return buf
 
-    def set_async_output(self, on: bool):
-        self.set_option("async_output", 1 if on else 0)
+    def decode_to_device(self, dev_ptr: int, capacity: int, noise_z: Optional[np.ndarray] = None):
+        """float32 audio into a caller-owned DEVICE buffer (out_kind 3): stream-ordered, no host synchronisation."""
+        if self._ylen is None:
+            raise RuntimeError("decode() before prepare()")
+        nz, stride = None, 0
+        if noise_z is not None:
+            nz = np.ascontiguousarray(noise_z, dtype=np.float32)
+            stride = nz.shape[2]
+        self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, 3, C.c_void_p(int(dev_ptr)), int(capacity), 1.0, 1))
+
+    def wait_ticket(self, ticket: int):
+        self._check(self.lib.vits_wait_ticket(self._h, int(ticket)))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on the caller's CUDA stream (``torch.cuda.Stream.cuda_stream`` or any cudaStream_t as an int); None restores."""
+        self._check(self.lib.vits_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
+    def describe(self) -> Dict[str, int]:
+        info = CInfo()
+        self._check(self.lib.vits_describe(self._h, C.byref(info)))
+        return {n: int(getattr(info, n)) for n, _ in CInfo._fields_ if n != "reserved"}
+
+    def max_output_samples(self, sum_ids: int = 0, length_scale: float = 1.0) -> int:
+        n = int(self.lib.vits_max_output_samples(self._h, int(sum_ids), float(length_scale)))
+        if n < 0:
+            self._check(n)
+        return n
 
     def wait_output(self, older_only: bool = False):
         self._check(self.lib.vits_wait_output(self._h, 1 if older_only else 0))
@@ -287,7 +346,9 @@ class Engine:
         a = self.arch
         frames = int(self._ylen.sum())
         cap = {"x": self._R * a.hidden, "stats": self._R * 2 * a.inter, "logw": self._R, "durations": self._R,
-               "cum": self._R, "frame_index": frames, "z_p": frames * a.inter, "z": frames * a.inter}[name]
+               "cum": self._R, "noise_dp": 2 * self._R,
+               # per-chunk workspaces: the C side refuses them after a multi-chunk decode (a fragment would be silently wrong)
+               "frame_index": frames, "z_p": frames * a.inter, "z": frames * a.inter}[name]
         is_int = name in ("durations", "cum", "frame_index")
         buf = np.empty((cap,), np.int32 if is_int else np.float32)
         n = self.lib.vits_fetch(self._h, name.encode(), _ptr(buf), cap)
@@ -321,7 +382,7 @@ class Engine:
         if getattr(self, "_h", None):
             self.lib.vits_destroy(self._h)
             self._h = C.c_void_p()
-            self._pool.drain()
+            self._pool.drain(close=True)
 
     def __del__(self):
         try:

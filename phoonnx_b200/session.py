@@ -110,8 +110,9 @@ class B200Session:
                 raise ValueError("'sid' must be int64 [B] (voice.py:370)")
         return x, lens, scales, sid
 
-    def synthesize_packed(self, feed, out: str = "f32", volume: float = 1.0, normalize: bool = True):
-        """Returns (packed audio of all utterances, samples per utterance)."""
+    def synthesize_packed(self, feed, out: str = "f32", volume: float = 1.0, normalize: bool = True, asynchronous: bool = False):
+        """Returns (packed audio of all utterances, samples per utterance).  ``asynchronous=True``: the array is still being
+        filled by the copy stream when this returns; ``self.engine.wait_ticket(self.engine.last_ticket)`` completes it."""
         x, lens, scales, sid = self._unpack_feed(feed)
         B, T = x.shape
         mask = np.arange(T)[None, :] < lens[:, None]
@@ -119,30 +120,43 @@ class B200Session:
         self._calls += 1
         ylen = self.engine.prepare(ids, lens, scales, sid, feed.get("noise_dp"), feed.get("logw"),
                                    seed=self._seed + self._calls)
-        audio = self.engine.decode(feed.get("noise_z"), out=out, volume=volume, normalize=normalize)
+        audio = self.engine.decode(feed.get("noise_z"), out=out, volume=volume, normalize=normalize, asynchronous=asynchronous)
         self.last_lengths = ylen * self.engine.hop
         return audio, self.last_lengths
 
     def synthesize_many(self, feeds, out: str = "f32", volume: float = 1.0, normalize: bool = True):
         """Batched form of the serial loop in ``TTSVoice.synthesize`` (voice.py:265-269): yields
         ``(packed audio, samples per utterance)`` per feed, in order, with the device->host transfer of batch k
-        overlapping the kernels of batch k+1 (page-locked results, copy stream; include/vits_b200.h)."""
+        overlapping the kernels of batch k+1 (page-locked results, copy stream; include/vits_b200.h).
+
+        Asynchrony is a per-call flag and every result is waited for by ITS OWN ticket, so ``run()`` /
+        ``synthesize_packed()`` calls made on this session from inside the consumer loop stay blocking and correct, and a
+        feed that raises does not lose the result that was already in flight (it is yielded before the error propagates)."""
         eng = self.engine
-        eng.set_async_output(True)
+        prev = None                                     # (audio, lengths, ticket) of the batch whose transfer is in flight
         try:
-            prev = None
             for feed in feeds:
-                cur = self.synthesize_packed(feed, out=out, volume=volume, normalize=normalize)
+                try:
+                    audio, alen = self.synthesize_packed(feed, out=out, volume=volume, normalize=normalize, asynchronous=True)
+                except Exception:
+                    if prev is not None:
+                        p, prev = prev, None
+                        eng.wait_ticket(p[2])
+                        yield p[0], p[1]
+                    raise
+                cur = (audio, alen, eng.last_ticket)
                 if prev is not None:
-                    eng.wait_output(older_only=True)
-                    yield prev
+                    p, prev = prev, cur
+                    eng.wait_ticket(p[2])
+                    yield p[0], p[1]
                 prev = cur
             if prev is not None:
-                eng.wait_output()
-                yield prev
+                p, prev = prev, None
+                eng.wait_ticket(p[2])
+                yield p[0], p[1]
         finally:
-            eng.wait_output()
-            eng.set_async_output(False)
+            if prev is not None:                        # consumer abandoned the generator: do not leave a DMA into a dead buffer
+                eng.wait_ticket(prev[2])
 
     def end_profiling(self):
         return None

@@ -56,30 +56,110 @@ def patch_phoonnx(device: int = 0, precision: str = "fp32") -> None:
     )
 
 
-def synthesize_batch(voice, phoneme_id_lists: Sequence[Sequence[int]], syn_config=None) -> List[np.ndarray]:
-    """Batched form of ``TTSVoice.phoneme_ids_to_audio`` (voice.py:328-379): all
-    sentences go to the engine as one varlen batch instead of one ``run()`` per sentence
-    (voice.py:265-269).  Returns one float32 array per sentence, identical to what the per-sentence
-    call returns for the same noise."""
+def _syn_value(sc, cfg, name, default=None):
+    v = None if sc is None else getattr(sc, name, None)
+    if v is None:
+        v = getattr(cfg, name, default)
+    return default if v is None else v
+
+
+def ids_to_audio_batch(voice, phoneme_id_lists: Sequence[Sequence[int]], syn_config=None) -> List[np.ndarray]:
+    """Batched form of ``TTSVoice.phoneme_ids_to_audio`` (voice.py:328-379): all sentences go to the engine as ONE varlen
+    batch instead of one ``run()`` per sentence (voice.py:265-269).  Returns one float32 array per sentence, identical to what
+    the per-sentence call returns for the same noise (every utterance is synthesised with B=1 semantics)."""
     sess = voice.session
     if not isinstance(sess, B200Session):
         raise TypeError("synthesize_batch needs a voice backed by B200Session")
+    if not len(phoneme_id_lists):
+        return []
     cfg = voice.config
-    sc = syn_config
-    g = lambda name, default: default if sc is None or getattr(sc, name, None) is None else getattr(sc, name)  # noqa: E731
-    scales = np.array([g("noise_scale", cfg.noise_scale), g("length_scale", cfg.length_scale),
-                       g("noise_w_scale", cfg.noise_w_scale)], dtype=np.float32)        # order: voice.py:364-367
+    scales = np.array([_syn_value(syn_config, cfg, "noise_scale", 0.667), _syn_value(syn_config, cfg, "length_scale", 1.0),
+                       _syn_value(syn_config, cfg, "noise_w_scale", 0.8)], dtype=np.float32)        # order: voice.py:364-367
     B = len(phoneme_id_lists)
     lens = np.array([len(p) for p in phoneme_id_lists], np.int64)
+    if lens.min() < 1:
+        raise ValueError("empty phoneme-id sequence")
     x = np.zeros((B, int(lens.max())), np.int64)
     for b, p in enumerate(phoneme_id_lists):
         x[b, : len(p)] = np.asarray(p, np.int64)
     feed = {"input": x, "input_lengths": lens, "scales": scales}
     if sess.arch.n_speakers > 1:
-        feed["sid"] = np.full((B,), g("speaker_id", 0) or 0, np.int64)
+        sid = _syn_value(syn_config, cfg, "speaker_id", 0) or 0                                     # voice.py:357, 370
+        feed["sid"] = np.full((B,), int(sid), np.int64)
     audio, alen = sess.synthesize_packed(feed)
     out, off = [], 0
     for b in range(B):
         out.append(audio[off:off + int(alen[b])])
         off += int(alen[b])
+    return out
+
+
+def _postprocess(audio: np.ndarray, syn_config) -> np.ndarray:
+    """The caller-side steps of TTSVoice.synthesize (voice.py:271-282), unchanged."""
+    if syn_config is None or getattr(syn_config, "normalize_audio", True):
+        max_val = np.max(np.abs(audio)) if audio.size else 0.0
+        audio = np.zeros_like(audio) if max_val < 1e-8 else audio / max_val
+    vol = 1.0 if syn_config is None else getattr(syn_config, "volume", 1.0)
+    if vol != 1.0:
+        audio = audio * vol
+    return np.clip(audio, -1.0, 1.0).astype(np.float32)
+
+
+def _text_to_id_lists(voice, text: str, syn_config) -> List[List[int]]:
+    """Everything TTSVoice.synthesize does to a text before the session is called (voice.py:245-263): phonetic spellings,
+    diacritics, phonemisation, id mapping -- the reference's own methods, on the CPU, untouched."""
+    sc = syn_config
+    spell = getattr(voice, "phonetic_spellings", None)
+    if spell and (sc is None or getattr(sc, "enable_phonetic_spellings", True)):
+        text = spell.apply(text)
+    if sc is not None and getattr(sc, "add_diacritics", False):
+        text = voice.phonemizer.add_diacritics(text, voice.config.lang_code)
+    return [ids for ids in (voice.phonemes_to_ids(ph) for ph in voice.phonemize(text) if ph) if ids]
+
+
+def synthesize_batch(voice, texts, syn_config=None, max_workers: Optional[int] = None):
+    """Batched ``TTSVoice.synthesize`` (voice.py:236-290).
+
+    ``texts``: a sequence of strings (or, for callers that phonemise themselves, of phoneme-id lists).  Texts are phonemised
+    on a CPU thread pool with the voice's own phonemizer (the reference loops over them serially); ALL sentences of ALL texts
+    then go to the engine as one varlen batch, and the per-sentence post-processing of ``synthesize`` (normalise, volume,
+    clip) is applied to each result.  Returns one list per input: for a text, its ``AudioChunk``s in sentence order (the
+    reference's class when phoonnx is importable); for an id list, a single float32 array (no post-processing, exactly
+    ``phoneme_ids_to_audio``)."""
+    texts = list(texts)
+    if not texts:
+        return []
+    is_text = [isinstance(t, str) for t in texts]
+    if any(is_text):
+        from concurrent.futures import ThreadPoolExecutor
+        idx = [i for i, f in enumerate(is_text) if f]
+        with ThreadPoolExecutor(max_workers=max_workers or min(32, len(idx))) as pool:
+            sent = list(pool.map(lambda i: _text_to_id_lists(voice, texts[i], syn_config), idx))
+        per_text = dict(zip(idx, sent))
+    else:
+        per_text = {}
+    flat: List[Sequence[int]] = []
+    spans = []
+    for i, t in enumerate(texts):
+        lists = per_text[i] if is_text[i] else [list(t)]
+        spans.append((len(flat), len(flat) + len(lists)))
+        flat.extend(lists)
+    audios = ids_to_audio_batch(voice, flat, syn_config) if flat else []
+    chunk_cls = None
+    if any(is_text):
+        import sys
+        chunk_cls = getattr(sys.modules.get(type(voice).__module__), "AudioChunk", None)
+    out = []
+    for i, (lo, hi) in enumerate(spans):
+        if not is_text[i]:
+            out.append(audios[lo])
+            continue
+        chunks = []
+        for a in audios[lo:hi]:
+            a = _postprocess(np.asarray(a), syn_config)
+            if chunk_cls is not None:
+                chunks.append(chunk_cls(sample_rate=voice.config.sample_rate, sample_width=2, sample_channels=1, audio_float_array=a))
+            else:
+                chunks.append(a)
+        out.append(chunks)
     return out

@@ -10,8 +10,8 @@ import pytest
 from conftest import ROOT, has_gpu
 
 
-def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "vits_b200.h")).read()
+def declared_symbols(header="vits_b200.h"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(vits_[a-z0-9_]+)\s*\(", hdr)))
 
@@ -20,16 +20,28 @@ def test_header_symbols_are_exported(built_lib):
     names = declared_symbols()
     assert {"vits_create", "vits_upload", "vits_finalize", "vits_prepare", "vits_decode", "vits_destroy",
             "vits_last_error", "vits_fetch"} <= set(names)
+    assert {"vits_describe", "vits_max_output_samples", "vits_set_stream", "vits_output_ticket", "vits_wait_ticket"} <= set(names)
     lib = ctypes.CDLL(built_lib)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vits_b200.h but not exported"
     lib.vits_abi_version.restype = ctypes.c_int
-    assert lib.vits_abi_version() == 1
+    assert lib.vits_abi_version() == 2
+
+
+def test_test_hooks_live_in_their_own_header(built_lib):
+    """The product header declares no vits_test_* entry point; the test header's hooks are exported too."""
+    assert not [n for n in declared_symbols() if n.startswith("vits_test_")]
+    hooks = declared_symbols("vits_b200_test.h")
+    assert hooks and all(n.startswith("vits_test_") for n in hooks)
+    lib = ctypes.CDLL(built_lib)
+    for n in hooks:
+        assert hasattr(lib, n), n
 
 
 def test_python_binding_covers_header(built_lib):
     from phoonnx_b200 import engine
-    assert set(engine.EXPORTED_SYMBOLS) <= set(declared_symbols())
+    assert set(engine.EXPORTED_SYMBOLS) == set(declared_symbols())
+    assert set(engine.TEST_SYMBOLS) == set(declared_symbols("vits_b200_test.h"))
     engine.load_library()
 
 

@@ -1,0 +1,204 @@
+"""Boundary entry points added in round 2, on a real B200 (run with -m gpu): vits_describe, vits_max_output_samples, per-call
+asynchronous output with tickets, chunked int16 output, device-pointer output on a caller stream, the multi-chunk fetch guard,
+and phoonnx_b200.voice.synthesize_batch on a minimal stand-in voice object with the real engine underneath (the reference
+package is absent on the GPU box; its own TTSVoice is exercised on CPU in tests/test_voice_batch.py)."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCALES = np.array([0.667, 1.0, 0.8], np.float32)
+
+
+def _voice_file(tmp_path_factory, preset="tiny", ns=1, seed=5):
+    from phoonnx_b200 import modelgen
+    p = str(tmp_path_factory.mktemp("voice") / f"{preset}_{ns}.onnx")
+    _, arch = modelgen.make_voice(p, preset, ns, seed=seed)
+    return p, arch
+
+
+def _feeds(arch, rs, sizes):
+    out = []
+    for B in sizes:
+        lens = rs.randint(5, 60, size=(B,)).astype(np.int64)
+        ids = rs.randint(0, arch.n_vocab, (B, int(lens.max()))).astype(np.int64)
+        out.append({"input": ids, "input_lengths": lens, "scales": SCALES})
+    return out
+
+
+def test_describe_and_output_size(built_lib, tmp_path_factory):
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "tiny", 3)
+    sess = B200Session(p, precision="bf16")
+    info = sess.engine.describe()
+    assert info["n_vocab"] == arch.n_vocab and info["n_speakers"] == 3 and info["has_sid"] == 1
+    assert info["hop"] == arch.hop and info["sample_rate"] == arch.sample_rate and info["inter"] == arch.inter
+    assert info["precision"] == 1 and info["finalized"] == 1 and info["num_sms"] >= 100
+    with pytest.raises(RuntimeError):
+        sess.engine.max_output_samples()                       # exact figure: only after a prepare
+    plan = sess.engine.max_output_samples(100, 1.0)
+    assert plan == 100 * 16 * arch.hop and sess.engine.max_output_samples(100, 2.0) == 2 * plan
+    feed = {"input": np.arange(40, dtype=np.int64)[None] % arch.n_vocab, "input_lengths": np.array([40], np.int64),
+            "scales": SCALES, "sid": np.array([1], np.int64)}
+    audio, alen = sess.synthesize_packed(feed)
+    assert sess.engine.max_output_samples() == int(alen.sum()) == audio.shape[0] <= plan
+
+
+def test_async_is_per_call_and_waited_by_ticket(built_lib, tmp_path_factory):
+    """a blocking run() issued from inside the consumer loop of synthesize_many must return complete audio
+    and must not disturb the generator's results."""
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "x_low", 1)
+    rs = np.random.RandomState(5)
+    feeds = _feeds(arch, rs, (3, 1, 4, 2, 5, 3))
+    z = np.array([0.0, 1.0, 0.0], np.float32)
+    feeds = [dict(f, scales=z) for f in feeds]                 # zero noise: results do not depend on the call number
+    probe = {"input": feeds[2]["input"][:1], "input_lengths": feeds[2]["input_lengths"][:1], "scales": z}
+    ref = B200Session(p, precision="fp32", max_chunk_frames=96)
+    serial = [tuple(np.array(v) for v in ref.synthesize_packed(f)) for f in feeds]
+    want_probe = np.array(ref.run(None, probe)[0])
+    sess = B200Session(p, precision="fp32", max_chunk_frames=96)    # several chunks per batch: per-chunk transfers
+    got, probes = [], []
+    for audio, alen in sess.synthesize_many(feeds):
+        got.append((np.array(audio), np.array(alen)))
+        probes.append(np.array(sess.run(None, probe)[0]))      # blocking call while the next batch's transfer is in flight
+    assert len(got) == len(serial)
+    for (a0, n0), (a1, n1) in zip(serial, got):
+        assert np.array_equal(n0, n1) and np.array_equal(a0, a1)
+    assert all(np.array_equal(q, want_probe) for q in probes)
+    # tickets: explicit asynchronous decode + wait
+    a, n = sess.synthesize_packed(feeds[0], asynchronous=True)
+    t = sess.engine.last_ticket
+    assert t >= 1
+    sess.engine.wait_ticket(t)
+    assert np.array_equal(np.array(a), serial[0][0])
+    sess.engine.wait_ticket(t)                                  # waiting twice is harmless
+    with pytest.raises(ValueError):
+        sess.engine.wait_ticket(t + 5)                          # never issued
+
+
+def test_int16_output_is_chunked_and_exact(built_lib, tmp_path_factory):
+    """out_kind 2 leaves per chunk on the copy stream like fp32 (round 1: one synchronous copy at the end) and stays bit-exact
+    vs numpy (voice.py:271-282, 88-91), across chunk boundaries and in the pipelined batch call."""
+    from oracle.vits_oracle import postprocess_int16
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "tiny", 1)
+    rs = np.random.RandomState(6)
+    z = np.array([0.0, 1.0, 0.0], np.float32)
+    feeds = [dict(f, scales=z) for f in _feeds(arch, rs, (6, 3, 7))]
+    ref = B200Session(p, precision="fp32")
+    f32 = [tuple(np.array(v) for v in ref.synthesize_packed(f)) for f in feeds]
+    for chunk in (None, 64):
+        sess = B200Session(p, precision="fp32", max_chunk_frames=chunk)
+        for vol, norm in ((1.0, True), (0.4, True), (2.5, False)):
+            outs = list(sess.synthesize_many(feeds, out="i16", volume=vol, normalize=norm))
+            for (a32, alen), (a16, alen16) in zip(f32, outs):
+                assert a16.dtype == np.int16 and np.array_equal(alen, alen16)
+                off = 0
+                for n in alen:
+                    n = int(n)
+                    assert np.array_equal(a16[off:off + n], postprocess_int16(a32[off:off + n], vol, norm)), (chunk, vol, norm)
+                    off += n
+
+
+def test_device_output_on_a_caller_stream(built_lib, tmp_path_factory):
+    """out_kind 3: float32 audio into a device buffer of the caller, on the caller's CUDA stream, no host synchronisation inside
+    the call (cudaStream_t + device-pointer output)."""
+    import torch
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "tiny", 1)
+    rs = np.random.RandomState(7)
+    f = dict(_feeds(arch, rs, (5,))[0], scales=np.array([0.0, 1.0, 0.0], np.float32))
+    sess = B200Session(p, precision="fp32")
+    want, alen = sess.synthesize_packed(f)
+    want = np.array(want)
+    eng = sess.engine
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    x, lens, scales, sid = sess._unpack_feed(f)
+    ids = x[np.arange(x.shape[1])[None, :] < lens[:, None]]
+    eng.prepare(ids, lens, scales, None, seed=1)
+    n = eng.max_output_samples()
+    assert n == want.shape[0]
+    dev = torch.full((n + 8,), 7.0, dtype=torch.float32, device="cuda")
+    eng.decode_to_device(dev.data_ptr(), n)
+    stream.synchronize()
+    got = dev.cpu().numpy()
+    assert np.array_equal(got[:n], want) and (got[n:] == 7.0).all()
+    with pytest.raises(ValueError):
+        eng.decode_to_device(dev.data_ptr(), n - 1)             # capacity too small
+    eng.set_stream(None)
+    again, _ = sess.synthesize_packed(f)
+    assert np.array_equal(np.array(again), want)
+
+
+def test_chunk_tensors_are_refused_after_a_multi_chunk_decode(built_lib, tmp_path_factory):
+    """z / z_p / frame_index are per-chunk workspaces; after a multi-chunk decode a fetch used to return the last
+    chunk's rows silently."""
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "tiny", 1)
+    rs = np.random.RandomState(8)
+    f = _feeds(arch, rs, (6,))[0]
+    sess = B200Session(p, precision="fp32", max_chunk_frames=32)
+    sess.engine.set_option("debug_keep_zp", 1)
+    _, alen = sess.synthesize_packed(f)
+    assert int(alen.sum()) // arch.hop > 64
+    for name in ("z", "z_p", "frame_index"):
+        with pytest.raises(RuntimeError):
+            sess.engine.fetch(name)
+    assert sess.engine.fetch("durations").shape[0] == int(f["input_lengths"].sum())     # text-side tensors are whole
+    sess.engine.set_option("max_chunk_frames", 1 << 20)
+    _, alen = sess.synthesize_packed(f)
+    assert sess.engine.fetch("z").shape[0] == (int(alen.sum()) // arch.hop) * arch.inter
+
+
+class _StandInVoice:
+    """The four members synthesize_batch touches on a TTSVoice (voice.py:105-123, 173-234): session, config, phonemize,
+    phonemes_to_ids.  Characters are phonemes; sentences end at '.'."""
+
+    class Cfg:
+        noise_scale, length_scale, noise_w_scale = 0.0, 1.0, 0.0
+        sample_rate, lang_code = 16000, "en"
+
+    def __init__(self, session, n_vocab):
+        self.session, self.config, self.n_vocab = session, self.Cfg(), n_vocab
+        self.phonetic_spellings, self.threads = None, set()
+
+    def phonemize(self, text):
+        self.threads.add(threading.get_ident())
+        return [list(s.strip()) for s in text.split(".") if s.strip()]
+
+    def phonemes_to_ids(self, phonemes):
+        ids = [1]
+        for ph in phonemes:
+            ids += [0, 3 + (ord(ph) % (self.n_vocab - 3))]
+        return ids + [0, 2]
+
+
+def test_synthesize_batch_equals_per_sentence_runs(built_lib, tmp_path_factory):
+    """One varlen batch for all sentences of all texts == the reference's one run() per sentence (voice.py:265-269, 328-379) at
+    zero noise, bit for bit in fp32 mode (every utterance is synthesised with B=1 semantics)."""
+    from phoonnx_b200.session import B200Session
+    from phoonnx_b200.voice import synthesize_batch
+    p, arch = _voice_file(tmp_path_factory, "x_low", 1)
+    sess = B200Session(p, precision="fp32", sample_rate=16000)
+    voice = _StandInVoice(sess, arch.n_vocab)
+    texts = ["hello world. this is a test.", "one more sentence", "a. b. c.", [1, 0, 20, 0, 59, 0, 2]]
+    n0 = sess.engine.launch_count()
+    out = synthesize_batch(voice, texts)
+    n_batch = sess.engine.launch_count() - n0
+    assert [len(o) if isinstance(o, list) else -1 for o in out] == [2, 1, 3, -1]
+    z = np.array([0.0, 1.0, 0.0], np.float32)
+    n0 = sess.engine.launch_count()
+    for t, o in zip(texts, out):
+        sents = [voice.phonemes_to_ids(ph) for ph in voice.phonemize(t)] if isinstance(t, str) else [t]
+        res = o if isinstance(o, list) else [o]
+        for ids, a in zip(sents, res):
+            one = sess.run(None, {"input": np.asarray([ids], np.int64), "input_lengths": np.array([len(ids)], np.int64), "scales": z})[0].squeeze()
+            if isinstance(t, str):          # the caller-side post-processing of TTSVoice.synthesize (voice.py:271-282)
+                m = np.abs(one).max()
+                one = np.clip(one / m if m >= 1e-8 else np.zeros_like(one), -1.0, 1.0).astype(np.float32)
+            assert a.shape == one.shape and np.array_equal(np.asarray(a), one)
+    assert n_batch < (sess.engine.launch_count() - n0) / 3      # one pass over the kernels instead of one per sentence

@@ -43,6 +43,8 @@ def timeline(sess, stage, arch):
     t0 = st[0, 0]
     names = {0: "E top", 1: "E ups acc ready", 2: "E X staged (E0)", 3: "E post(prev) done", 16: "E c2 final done", 17: "E final epi done",
              20: "M top", 21: "M ups issued", 22: "M X ready", 40: "M post rdy", 41: "M post issued", 44: "L top", 45: "L in free", 46: "L landed"}
+    names.update({36: "M before wait x1(0)", 37: "M before wait x1(1)", 38: "M before wait x1(2)", 18: "M after wait x1(0)",
+                  23: "E(warp 15) x1(0) staged", 42: "E(warp 15) x1(1) staged", 43: "E(warp 15) x1(2) staged"})
     for r in range(3):
         names[4 + 4 * r] = f"E c1({r}) done"; names[5 + 4 * r] = f"E E1({r}) math done"
         names[6 + 4 * r] = f"E c2({r - 1}) done"; names[7 + 4 * r] = f"E x1({r}) staged"
