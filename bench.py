@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""Throughput benchmark of the phoneme-ids -> audio hot path (BASELINE.json metric:
-audio-seconds synthesised per second at 1/2/4/8 B200 + HiFi-GAN decoder fraction of tensor peak).
+"""Benchmark of the phoneme-ids -> audio hot path (BASELINE.json metric: audio-seconds synthesised per second at 1/2/4/8 B200 +
+HiFi-GAN decoder fraction of tensor peak).
 
-  python bench.py --gpus N --steps K --warmup W            # this engine (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N ...             # the reference's CPU path (oracle port), host cores
+  python bench.py --gpus N --steps K --warmup W                  # this engine, BASELINE config 5 (the driver's line)
+  python bench.py --config C1|C2|C3|C4|C5 ...                    # every BASELINE.json config; lines under profiles/
+  python bench.py --scaling strong --gpus N ...                  # C5 as ONE 4096-utterance job sharded over the ranks
+  python bench.py --impl reference --gpus N ...                  # the reference's own SynthesizerTrn.infer on the host cores
 
-Workload (BASELINE.json configs[4], "VITS medium throughput sweep"): Piper-style VITS medium,
-random-init (phoonnx_b200.modelgen, exporter-format file), U utterances per GPU of
-randint(64,257) phoneme ids (seed 2 + rank), length-bucketed, scales (0.667, 1.0, 0.8), noise
-generated on device.  A "step" is one pass over the rank's U utterances.  Utterances shard across
-ranks with no data-path collective: weak scaling, per-GPU work fixed.
+Workloads (random-init voices written by phoonnx_b200.modelgen in the exporter's file format):
+  C1  medium, ONE utterance of 128 ids per run() -- what TTSVoice sends (voice.py:350-351): per-call latency p50 / p99
+  C2  x_low, 32 utterances of randint(64,257) ids (seed 0), one device batch per step
+  C3  medium, 8 speakers, 64 utterances (seed 1), sid = arange % 8
+  C4  high (ResBlock1, kernels 3/7/11), 16 utterances of 512 ids
+  C5  medium, 4096 utterances of randint(64,257) ids (seed 2), length-bucketed.  Default ("weak"): every rank runs its own 4096
+      (seed 2 + rank) -- per-GPU work fixed, the line the driver compares across rounds.  "strong": ONE list (seed 2) dealt to the
+      ranks by scheduler.plan(lengths, world, rank); the end-to-end number then includes the host gather: every rank's audio lands
+      in ONE host buffer (POSIX shared memory, owned by rank 0) in original utterance order.  No collective on the data path
+      (SURVEY.md 8e): NCCL carries the start/stop barriers and the max-over-ranks of the timings only; the gather's hand-shake
+      is a flag array in the same shared segment.
 
-One JSON line on stdout (rank 0).  `value` = audio-seconds / second with inputs resident on the
-device (CUDA events on the engine's stream, max over ranks); `e2e` = the same through the
-session call with HOST buffers (ids in, float32 audio out, copies inside the timed region).
+One JSON line on stdout (rank 0).  `value` = audio-seconds / second with inputs resident on the device (CUDA events on the engine's
+stream, max over ranks); `e2e` = the same through the session call with HOST buffers (ids in, float32 audio out, copies inside the
+timed region; median of three passes).
 """
 from __future__ import annotations
 
@@ -31,23 +39,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SCALES = (0.667, 1.0, 0.8)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`, one launch over a 131072-frame chunk of this workload)
-# -- constants copied from the committed captures, not measured by this script (a number taken under a profiler is never a
-# bench value; these only say whether the kernels re-read more than the algorithm needs)
-KERNEL_TRAFFIC = {
-    "k_mrf3_tc<32>": {"bytes_per_launch": 2.150258e9 + 0.264484e9, "algorithmic_bytes_per_launch": 262144 * (64 * 64 * 2 + 256 * 4),
-                      "frames_per_launch": 262144, "source": "profiles/r01g_ncu_mrf3.txt"},
-    "k_mrf3_tc<64>": {"bytes_per_launch": 2.150496e9 + 2.104694e9, "algorithmic_bytes_per_launch": 262144 * (64 * 64 * 2) * 2,
-                      "frames_per_launch": 262144, "source": "profiles/r01g_ncu_mrf3.txt"},
+CONFIGS = {
+    # name: preset, speakers, utterances, (lo, hi) ids, lengths seed, description
+    "C1": dict(preset="medium", ns=1, utts=1, lo=128, hi=129, seed=0, what="single utterance of 128 phoneme ids per call (latency)"),
+    "C2": dict(preset="x_low", ns=1, utts=32, lo=64, hi=257, seed=0, what="batch of 32 utterances of randint(64,257) ids"),
+    "C3": dict(preset="medium", ns=8, utts=64, lo=64, hi=257, seed=1, what="8 speakers, batch of 64 utterances of randint(64,257) ids"),
+    "C4": dict(preset="high", ns=1, utts=16, lo=512, hi=513, seed=0, what="ResBlock1 decoder, batch of 16 utterances of 512 ids"),
+    "C5": dict(preset="medium", ns=1, utts=4096, lo=64, hi=257, seed=2, what="utterances of randint(64,257) ids, length-bucketed"),
 }
-DEC_TRAFFIC = {"bytes": None, "note": "per-kernel DRAM traffic of the two fused kernels is under roofline.kernels[].traffic; the decoder as a "
-                                      "whole is a launch family, see profiles/README.md for the per-launch dram bytes of every member"}
+
+# DRAM bytes per FRAME of the two fused kernels (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch over a
+# 262 144-frame chunk, divided by its frames) -- copied from the committed capture, not measured by this script (a number taken
+# under a profiler is never a bench value).  bench.py scales them by the frames per launch it measured.
+KERNEL_TRAFFIC = {
+    "k_mrf3_tc<32>": {"bytes_per_frame": (2.150258e9 + 0.264484e9) / 262144, "algorithmic_bytes_per_frame": 64 * 64 * 2 + 256 * 4,
+                      "source": "profiles/r01g_ncu_mrf3.txt"},
+    "k_mrf3_tc<64>": {"bytes_per_frame": (2.150496e9 + 2.104694e9) / 262144, "algorithmic_bytes_per_frame": 64 * 64 * 2 * 2,
+                      "source": "profiles/r01g_ncu_mrf3.txt"},
+}
 
 
-def make_workload(n_utts: int, seed: int, n_vocab: int = 256):
+def make_workload(n_utts: int, seed: int, n_vocab: int = 256, lo: int = 64, hi: int = 257):
     rs = np.random.RandomState(seed)
-    lengths = rs.randint(64, 257, size=(n_utts,)).astype(np.int64)
+    lengths = rs.randint(lo, hi, size=(n_utts,)).astype(np.int64)
     utts = [rs.randint(0, n_vocab, size=(int(L),)).astype(np.int64) for L in lengths]
     return utts, lengths
 
@@ -70,8 +86,7 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES-aware: NVML enumerates physical GPUs
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")      # NVML enumerates physical GPUs
             phys = self.device
             if vis:
                 ent = [v.strip() for v in vis.split(",") if v.strip()]
@@ -114,33 +129,237 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def cpu_baseline(path: str, utts, sample_idx, threads: int):
-    """Oracle (CPU port of the reference arithmetic) on a bounded sample, all host threads."""
+# ---------------------------------------------------------------------------------------------------------------------------
+# Reference arm: the UNMODIFIED reference (pip-installed into baseline/_ref from /root/reference), its own
+# SynthesizerTrn.infer (models.py:681-722 -- the graph export_onnx.py traces and onnxruntime would run; onnxruntime itself is not
+# installable offline) on the host cores, B=1 per call like TTSVoice (voice.py:265-269, 350-351), in a pool of worker processes
+# of REF_THREADS torch threads each (a single B=1 process cannot use a whole host: r01 timed exactly that and under-reported).
+# Falls back to the oracle port (kind "port") only if baseline/_ref is missing.
+# ---------------------------------------------------------------------------------------------------------------------------
+REF_THREADS = 4
+_ref_state = {}
+
+
+def _ref_build_model(path: str):
+    """The reference's SynthesizerTrn carrying exactly the weights of the voice file the engine loads."""
+    import types
+    import warnings
     import torch
-    from oracle.vits_oracle import VitsOracle
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    name = "phoonnx_train.vits.monotonic_align"           # Cython, training-only (models.py:646); its cp310 .so is absent here
+    if name not in sys.modules:
+        sys.modules[name] = types.ModuleType(name)
+    from phoonnx_train.vits.models import SynthesizerTrn
     from phoonnx_b200.weights import load_model
+    W, a, _ = load_model(path)
+    kw = dict(n_vocab=a.n_vocab, spec_channels=513, segment_size=32, inter_channels=a.inter, hidden_channels=a.hidden,
+              filter_channels=a.filter, n_heads=a.n_heads, n_layers=a.n_layers, kernel_size=a.enc_kernel, p_dropout=0.1,
+              resblock=a.resblock, resblock_kernel_sizes=tuple(a.rb_kernels), resblock_dilation_sizes=tuple(tuple(d) for d in a.rb_dilations),
+              upsample_rates=tuple(a.up_rates), upsample_initial_channel=a.up_init, upsample_kernel_sizes=tuple(a.up_kernels),
+              n_speakers=a.n_speakers, gin_channels=a.gin, use_sdp=a.use_sdp)                 # lightning.py:86-106
+    import contextlib
+    with warnings.catch_warnings(), contextlib.redirect_stdout(open(os.devnull, "w")):      # the reference print()s while removing weight norm
+        warnings.simplefilter("ignore")
+        m = SynthesizerTrn(**kw).eval()
+        m.dec.remove_weight_norm()                          # export_onnx.py:242-245
+        for f in m.flow.flows:                              # the exporter folds the flows' weight norm into constants (SURVEY.md 8a W)
+            if hasattr(f, "enc"):
+                f.enc.remove_weight_norm()
+    sd = m.state_dict()
+    missing = []
+    with torch.no_grad():
+        for k, v in sd.items():
+            if k in W:
+                v.copy_(torch.from_numpy(np.ascontiguousarray(W[k])).reshape(v.shape))
+            elif not (k.startswith("enc_q.") or k.startswith("dp.post_") or k.startswith("dp.flows.1.")):
+                missing.append(k)                           # everything infer() touches must come from the file
+    if missing:
+        raise RuntimeError(f"voice file lacks tensors of the reference model: {missing[:5]}")
+    return m, a
+
+
+def _ref_worker_init(path: str, threads: int):
+    import torch
     torch.set_num_threads(threads)
+    m, a = _ref_build_model(path)
+    _ref_state.update(model=m, arch=a)
+
+
+def _ref_worker_run(job):
+    import torch
+    ids, sid = job
+    m, a = _ref_state["model"], _ref_state["arch"]
+    with torch.no_grad():
+        x = torch.from_numpy(np.asarray(ids, np.int64))[None]
+        o = m.infer(x, torch.tensor([x.shape[1]]), sid=None if sid is None else torch.tensor([int(sid)]),
+                    noise_scale=SCALES[0], length_scale=SCALES[1], noise_scale_w=SCALES[2])[0]
+    return int(o.shape[-1])
+
+
+class ReferencePool:
+    def __init__(self, path: str, cores: int):
+        import multiprocessing as mp
+        self.kind = "reference" if os.path.isdir(os.path.join(REF_DIR, "phoonnx_train", "vits")) else "port"
+        self.path, self.cores = path, cores
+        self.threads = min(REF_THREADS, cores)
+        self.procs = max(1, cores // self.threads)
+        self.pool = None
+        if self.kind == "reference":
+            ctx = mp.get_context("spawn")                   # the parent may already hold a CUDA context
+            self.pool = ctx.Pool(self.procs, initializer=_ref_worker_init, initargs=(path, self.threads))
+            self.pool.map(_ref_worker_run, [(np.arange(16) % 200, 0 if self._ns() > 1 else None)] * self.procs)     # build + first call
+
+    def _ns(self):
+        from phoonnx_b200.weights import load_model
+        if not hasattr(self, "_arch"):
+            self._arch = load_model(self.path)[1]
+        return self._arch.n_speakers
+
+    def run(self, utts, sids):
+        """(audio seconds, wall seconds) for these utterances, B=1 per call."""
+        arch_sr = self._arch.sample_rate if hasattr(self, "_arch") else None
+        if self.kind == "reference":
+            jobs = [(u, None if sids is None else int(s)) for u, s in zip(utts, sids if sids is not None else [None] * len(utts))]
+            jobs.sort(key=lambda j: -len(j[0]))             # longest first: the pool's tail stays short
+            t0 = time.perf_counter()
+            samples = self.pool.map(_ref_worker_run, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            self._ns()
+            return sum(samples) / self._arch.sample_rate, dt
+        # fallback: the oracle port in this process (all threads) -- reported as kind "port"
+        import torch
+        from oracle.vits_oracle import VitsOracle
+        from phoonnx_b200.weights import load_model
+        torch.set_num_threads(self.cores)
+        W, arch, _ = load_model(self.path)
+        orc = VitsOracle(W, arch)
+        rs = np.random.RandomState(99)
+        noise = [(rs.randn(2, len(u)).astype(np.float32), rs.randn(arch.inter, 24 * len(u)).astype(np.float32)) for u in utts]
+        t0 = time.perf_counter()
+        n = 0
+        for i, u in enumerate(utts):
+            n += orc.infer(u, SCALES, None if sids is None else int(sids[i]), noise[i][0], noise[i][1], stages=False)["audio"].shape[0]
+        return n / arch.sample_rate, time.perf_counter() - t0
+
+    def describe(self, sample: str):
+        if self.kind == "reference":
+            how = (f"the reference's own phoonnx_train.vits.models.SynthesizerTrn.infer (baseline/_ref, unmodified; torch-CPU; onnxruntime is "
+                   f"not installable offline), B=1 per call like voice.py:265-269, {self.procs} worker processes x {self.threads} torch threads")
+        else:
+            how = "oracle/vits_oracle.py (torch-CPU port; baseline/_ref missing), B=1 loop, one process"
+        return {"cores": self.procs * self.threads if self.kind == "reference" else self.cores, "kind": self.kind, "sample": f"{sample}; {how}"}
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def spot_check(sess, path, utts, sids, picks):
+    """Checker leg (outside every timed region): the engine at scales (0, 1, 0) vs the CPU oracle on a few utterances of the
+    benched workload -- a fast kernel whose results differ from the reference's is not done."""
+    from oracle.vits_oracle import VitsOracle
+    from phoonnx_b200 import scheduler
+    from phoonnx_b200.weights import load_model
     W, arch, _ = load_model(path)
     orc = VitsOracle(W, arch)
-    rs = np.random.RandomState(99)
-    audio_s, t0 = 0.0, time.perf_counter()
-    frames = 0
-    for i in sample_idx:
-        ids = utts[i]
-        T = len(ids)
-        nd = rs.randn(2, T).astype(np.float32)
-        nz = rs.randn(arch.inter, 24 * T).astype(np.float32)
-        r = orc.infer(ids, SCALES, None, nd, nz, stages=False)
-        audio_s += r["audio"].shape[0] / arch.sample_rate
-        frames += int(r["y_len"])
-    dt = time.perf_counter() - t0
-    return audio_s, dt, frames
+    z = np.asarray((0.0, 1.0, 0.0), np.float32)
+    x, lens = scheduler.pad_batch([utts[i] for i in picks])
+    feed = {"input": x, "input_lengths": lens, "scales": z}
+    if sids is not None:
+        feed["sid"] = np.asarray([sids[i] for i in picks], np.int64)
+    audio, alen = sess.synthesize_packed(feed)
+    audio = np.array(audio)
+    off, worst, compared = 0, 1e9, 0
+    for j, i in enumerate(picks):
+        r = orc.infer(utts[i], z, None if sids is None else int(sids[i]), None, None, stages=False)
+        n = int(alen[j])
+        if r["audio"].shape[0] == n:                        # (a ceil tie changes the length: skipped, counted below)
+            d = audio[off:off + n] - r["audio"]
+            worst = min(worst, 10 * np.log10(float((r["audio"].astype(np.float64) ** 2).sum()) / max(float((d.astype(np.float64) ** 2).sum()), 1e-30)))
+            compared += 1
+        off += n
+    return {"utterances": len(picks), "compared": compared, "worst_snr_db": None if compared == 0 else round(float(worst), 1),
+            "scales": [0.0, 1.0, 0.0], "checker": "oracle/vits_oracle.py"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Strong scaling: host gather into one buffer in original order (shared memory owned by rank 0)
+# ---------------------------------------------------------------------------------------------------------------------------
+class HostGather:
+    """ONE host buffer for the whole job's audio in ORIGINAL utterance order, filled by every rank in parallel.  Layout of the
+    shared segment: flags int64[2 * world] | frames int64[n_utts] | audio float32[capacity].  Hand-shake without a collective:
+    a rank publishes its utterances' frame counts, then its flag; when every flag shows the step number each rank computes the
+    same exclusive scan and copies its utterances to their final places (thread pool: numpy slice copies release the GIL)."""
+
+    def __init__(self, name: str, world: int, rank: int, n_utts: int, capacity_samples: int, create: bool):
+        from multiprocessing import shared_memory
+        self.world, self.rank, self.n = world, rank, n_utts
+        hdr = 8 * (2 * world + n_utts)
+        hdr = (hdr + 4095) // 4096 * 4096
+        size = hdr + 4 * capacity_samples
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0)
+        buf = self.shm.buf
+        self.flags = np.frombuffer(buf, np.int64, 2 * world, 0)
+        self.frames = np.frombuffer(buf, np.int64, n_utts, 8 * 2 * world)
+        self.audio = np.frombuffer(buf, np.float32, capacity_samples, hdr)
+        self.capacity = capacity_samples
+        if create:
+            self.flags[:] = 0
+            self.frames[:] = 0
+            self.audio[:] = 0.0                             # first touch: the pages exist before anything is timed
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(max_workers=max(2, min(16, (os.cpu_count() or 8) // max(1, world))))
+
+    def _wait_all(self, col: int, step: int):
+        spins = 0
+        while int(self.flags[col * self.world:(col + 1) * self.world].min()) < step:
+            spins += 1
+            if spins > 200:
+                time.sleep(0.0001)
+            if spins > 2_000_000:
+                raise RuntimeError("host gather: a rank never published its lengths")
+
+    def gather(self, step: int, hop: int, results):
+        """results: [(global utterance indices, packed audio, samples per utterance)] of this rank's device batches."""
+        for idx, _, alen in results:
+            self.frames[idx] = alen // hop
+        self.flags[self.rank] = step
+        self._wait_all(0, step)
+        offs = np.concatenate([[0], np.cumsum(self.frames)]) * hop
+        if int(offs[-1]) > self.capacity:
+            raise RuntimeError("host gather: result buffer too small")
+        jobs = []
+        for idx, audio, alen in results:
+            src = np.concatenate([[0], np.cumsum(alen)])
+            for j, g in enumerate(idx):
+                jobs.append((int(offs[g]), audio, int(src[j]), int(alen[j])))
+        dst = self.audio
+
+        def cp(chunk):
+            for o, a, s, n in chunk:
+                dst[o:o + n] = a[s:s + n]
+
+        k = max(1, len(jobs) // (4 * self.pool._max_workers))
+        list(self.pool.map(cp, [jobs[i:i + k] for i in range(0, len(jobs), k)]))
+        self.flags[self.world + self.rank] = step
+        if self.rank == 0:
+            self._wait_all(1, step)
+        return int(offs[-1])
+
+    def close(self, unlink: bool):
+        self.pool.shutdown()
+        del self.flags, self.frames, self.audio
+        self.shm.close()
+        if unlink:
+            try:
+                self.shm.unlink()
+            except Exception:
+                pass
 
 
 def main():
@@ -149,48 +368,68 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU per step")
+    ap.add_argument("--config", default="C5", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="C5 only: per-GPU work fixed (driver line) or ONE job sharded over the ranks")
+    ap.add_argument("--utts", type=int, default=None, help="override the config's utterance count (per GPU in weak mode)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--preset", default="medium")
+    ap.add_argument("--preset", default=None, help="override the config's voice preset")
     ap.add_argument("--max-ids", type=int, default=262144, help="phoneme ids per device batch")
     ap.add_argument("--max-utts", type=int, default=2048, help="utterances per device batch")
     ap.add_argument("--chunk-frames", type=int, default=262144)
-    ap.add_argument("--cpu-sample", type=int, default=24, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--calls", type=int, default=300, help="C1: timed run() calls per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section of the default C5 line")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="engine option (A/B experiments), repeatable")
     args = ap.parse_args()
 
     rank, world, local = dist_env()
+    cfg = dict(CONFIGS[args.config])
+    if args.preset:
+        cfg["preset"] = args.preset
+    if args.utts:
+        cfg["utts"] = args.utts
+    strong = args.scaling == "strong"
+    if strong and args.config != "C5":
+        raise SystemExit("--scaling strong applies to C5 (the sharded throughput sweep)")
     from phoonnx_b200 import modelgen, scheduler
     tmp = tempfile.mkdtemp(prefix="vits_bench_")
-    path = os.path.join(tmp, f"{args.preset}.onnx")
-    _, arch = modelgen.make_voice(path, args.preset, n_speakers=1, seed=1234)
-    utts, lengths = make_workload(args.utts, seed=2 + rank, n_vocab=arch.n_vocab)
+    path = os.path.join(tmp, f"{cfg['preset']}.onnx")
+    _, arch = modelgen.make_voice(path, cfg["preset"], n_speakers=cfg["ns"], seed=1234)
+    wl_seed = cfg["seed"] + (rank if (args.config == "C5" and not strong) else 0)
+    utts, lengths = make_workload(cfg["utts"], seed=wl_seed, n_vocab=arch.n_vocab, lo=cfg["lo"], hi=cfg["hi"])
+    sids = (np.arange(cfg["utts"]) % cfg["ns"]).astype(np.int64) if cfg["ns"] > 1 else None
     n_threads = os.cpu_count() or 1
-    sample_idx = list(range(0, args.utts, max(1, args.utts // max(1, args.cpu_sample))))[: args.cpu_sample]
-    workload = (f"C5: VITS {args.preset} (random-init, exporter-format file), {args.utts} utterances/GPU of "
-                f"randint(64,257) phoneme ids, length-bucketed, scales {SCALES}, {arch.sample_rate} Hz")
+    sample_idx = list(range(0, cfg["utts"], max(1, cfg["utts"] // max(1, args.cpu_sample))))[: args.cpu_sample]
+    per = "" if args.config != "C5" else (" in total" if strong else "/GPU")
+    workload = (f"{args.config}: VITS {cfg['preset']} (random-init, exporter-format file), "
+                f"{(str(cfg['utts']) + per + ' ') if args.config == 'C5' else ''}{cfg['what']}, scales {SCALES}, {arch.sample_rate} Hz")
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
+        pool = ReferencePool(path, n_threads)
+        # a step = the bounded sample of the workload (small configs: the whole workload; C1: 16 calls of its one utterance)
+        su = [utts[i] for i in sample_idx] if args.config != "C1" else [utts[0]] * 16
+        ss = None if sids is None else [sids[i] for i in sample_idx]
         vals = []
         for s in range(args.warmup + args.steps):
-            a_s, dt, _ = cpu_baseline(path, utts, sample_idx if s >= args.warmup else sample_idx[:2], n_threads)
-            if s >= args.warmup:
-                vals.append((a_s, dt))
+            if s < args.warmup:
+                pool.run(su[:max(2, pool.procs)], None if ss is None else ss[:max(2, pool.procs)])
+            else:
+                vals.append(pool.run(su, ss))
         a_tot = sum(v[0] for v in vals); t_tot = sum(v[1] for v in vals)
         v = a_tot / t_tot
+        sample = (f"{len(su)} of the {cfg['utts']} utterances per step" if args.config != "C1" else "16 calls of the single 128-id utterance per step")
+        cb = dict(pool.describe(sample), value=v, unit="audio-s/s")
         line = {"impl": "reference", "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "sample": f"{len(sample_idx)} utterances (every {args.utts // max(1, len(sample_idx))}th) per step"},
-                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": n_threads, "kind": "port",
-                                 "sample": f"{len(sample_idx)} of the {args.utts} utterances per step, B=1 loop like voice.py:265-269; "
-                                           "oracle/vits_oracle.py (torch-CPU restatement of SynthesizerTrn.infer; onnxruntime is not installable offline)"},
+                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "sample": sample}, "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
+        pool.close()
         return
 
     # ------------------------------------------------------------------ this engine
@@ -202,7 +441,6 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         # one rank per GPU: run (and allocate the page-locked result pool) on the CPUs / NUMA node next to this rank's GPU
-        # (8-GPU check of round 1: device-resident rate scaled linearly, the end-to-end rate lost 15 % to the host side)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -216,100 +454,44 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=", 1)
         eng.set_option(k, float(v))
-    batches = scheduler.plan(lengths, 1, 0, max_ids=args.max_ids, max_utts=args.max_utts)
-    feeds = []
-    for bidx in batches:
-        x, lens = scheduler.pad_batch([utts[i] for i in bidx])
-        feeds.append({"input": x, "input_lengths": lens, "scales": np.asarray(SCALES, np.float32)})
-    h2d = sum(int(f["input_lengths"].sum()) * 8 + f["input_lengths"].size * 8 + 12 for f in feeds)
 
-    def one_step(out_kind: str):
-        frames = 0
-        nbytes = 0
-        for f in feeds:
-            audio, alen = sess.synthesize_packed(f, out=out_kind)
-            frames += int(alen.sum()) // arch.hop
-            if audio is not None:
-                nbytes += audio.nbytes
-        return frames, nbytes
+    def make_feeds(w, r):
+        batches = scheduler.plan(lengths, w, r, max_ids=args.max_ids, max_utts=args.max_utts)
+        feeds = []
+        for bidx in batches:
+            x, lens = scheduler.pad_batch([utts[i] for i in bidx])
+            f = {"input": x, "input_lengths": lens, "scales": np.asarray(SCALES, np.float32)}
+            if sids is not None:
+                f["sid"] = sids[bidx]
+            feeds.append(f)
+        return batches, feeds
+
+    batches, feeds = make_feeds(world, rank) if strong else make_feeds(1, 0)
+    h2d = sum(int(f["input_lengths"].sum()) * 8 + f["input_lengths"].size * 8 + 12 + (f["input_lengths"].size * 8 if "sid" in f else 0) for f in feeds)
 
     def barrier():
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # settle phase (untimed, before the W warm-up steps): one end-to-end pass and one device pass so that every buffer has its
-    # final size, every kernel module is loaded and the page-locked result pool exists before anything is counted -- the first
-    # CUDA process on a fresh box otherwise showed host-side gaps between launches well into the timed steps (r01 2-GPU runs)
-    for _ in sess.synthesize_many(feeds, out="f32"):
-        pass
-    one_step("none")
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        one_step("none")
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
-    launches0 = eng.launch_count()
-    eng.timer_start()
-    frames = 0
-    for _ in range(args.steps):
-        fr, _ = one_step("none")
-        frames += fr
-    dev_ms = eng.timer_stop()
-    barrier()
-    launches = eng.launch_count() - launches0
-    stage = eng.stage_ms()
-    kern = [eng.kernel_ms(0), eng.kernel_ms(1)]       # (ms, launches, algorithmic MACs) of the two fused decoder kernels
-    clocks = sampler.stop()
-    # end-to-end: host ids -> host float32 audio through the session's batch call (B200Session.synthesize_many: the
-    # device->host transfer of batch k overlaps the kernels of batch k+1; every result is complete when it is yielded)
-    def e2e_step(nsteps=1):
-        # the K steps go through ONE synthesize_many stream, as a service would run them: the device->host DMA of the last batch of
-        # step s runs under the kernels of step s + 1 (every result is complete and checked before the timed region ends)
+    def device_step(fs):
+        frames = 0
+        for f in fs:
+            _, alen = sess.synthesize_packed(f, out="none")
+            frames += int(alen.sum()) // arch.hop
+        return frames
+
+    def e2e_pass(fs, nsteps):
+        """K steps through ONE synthesize_many stream, as a service would run them: host ids in, complete host float32 audio out,
+        the device->host DMA of batch k under the kernels of batch k+1; every result is checked before the timed region ends."""
         frames = nbytes = 0
-        for audio, alen in sess.synthesize_many(feeds * nsteps, out="f32"):
+        for audio, alen in sess.synthesize_many(fs * nsteps, out="f32"):
             frames += int(alen.sum()) // arch.hop
             nbytes += audio.nbytes
-            head = audio[:1 << 20]              # cheap sanity check of every result: a NaN tile or an unbounded sample is a failed run
+            head = audio[:1 << 20]              # a NaN tile or an unbounded sample is a failed run
             if not (np.isfinite(head).all() and float(np.abs(head).max()) <= 1.0):
                 raise SystemExit("bench.py: synthesised audio is not finite / not tanh-bounded")
         return frames, nbytes
-
-    e2e_step(args.steps)        # untimed: the same K-step stream once, so the page-locked result pool has every block the stream needs
-    barrier()
-    t0 = time.perf_counter()
-    e_frames, d2h = e2e_step(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    # the end-to-end number is wall-clock on the host: a second K-step pass guards it against a one-off host stall (seen on the first
-    # CUDA process of a fresh box); the faster pass is reported, both are in the JSON line
-    t0 = time.perf_counter()
-    e_frames2, d2h2 = e2e_step(args.steps)
-    torch.cuda.synchronize()
-    e2e_s2 = time.perf_counter() - t0
-    barrier()
-    e2e_passes = [e2e_s, e2e_s2]
-    if e2e_s2 < e2e_s:
-        e2e_s, e_frames, d2h = e2e_s2, e_frames2, d2h2
-
-    audio_s = frames * arch.hop / arch.sample_rate
-    e_audio_s = e_frames * arch.hop / arch.sample_rate
-    if use_dist:
-        t = torch.tensor([dev_ms, e2e_s] + e2e_passes, device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([audio_s, e_audio_s, float(frames), float(launches), stage["dec"]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, p1, p2 = t.tolist()
-        e2e_passes = [p1, p2]
-        e2e_s = min(p1, p2)                     # the faster pass by its slowest rank
-        audio_s, e_audio_s, frames_all, launches_all, dec_ms_sum = s.tolist()
-    else:
-        frames_all, launches_all, dec_ms_sum = float(frames), float(launches), stage["dec"]
-    if rank != 0:
-        if use_dist:
-            dist.destroy_process_group()
-        return
 
     peaks = {}
     try:
@@ -318,46 +500,257 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+
+    # ================================================================== C1: per-call latency of B200Session.run
+    if args.config == "C1":
+        feed = {"input": utts[0][None], "input_lengths": np.asarray([len(utts[0])], np.int64), "scales": np.asarray(SCALES, np.float32)}
+        for _ in range(20 + 5 * args.warmup):
+            sess.run(None, feed)
+        barrier()
+        sampler = ClockSampler(local); sampler.start()
+        lat, samples_out = [], 0
+        l0 = eng.launch_count()
+        t_all = time.perf_counter()
+        for _ in range(args.steps * args.calls):
+            t0 = time.perf_counter()
+            out = sess.run(None, feed)[0]                    # host ids -> host float32 [1,1,1,T]; exactly voice.py:374-377
+            lat.append(time.perf_counter() - t0)
+            samples_out += out.shape[-1]
+        t_all = time.perf_counter() - t_all
+        launches = eng.launch_count() - l0
+        # device-resident rate of the same call (events on the engine's stream)
+        eng.timer_start()
+        fr = 0
+        for _ in range(args.steps * args.calls):
+            fr += device_step([feed])
+        dev_ms = eng.timer_stop()
+        stage = eng.stage_ms()
+        clocks = sampler.stop()
+        lat_ms = np.asarray(lat) * 1e3
+        ncalls = args.steps * args.calls
+        audio_s = samples_out / arch.sample_rate
+        value = (fr * arch.hop / arch.sample_rate) / (dev_ms * 1e-3)
+        dec_tf = 2.0 * arch.dec_mac_per_frame() * fr / (stage["dec"] * 1e-3) / 1e12 if stage["dec"] > 0 else 0.0
+        line = {"metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": workload, "precision": args.precision, "calls_per_step": args.calls,
+                           "l2_policy": "one utterance: the working set is far below L2 by construction; latency is quoted warm, as a serving loop sees it",
+                           "frames_per_call": fr // ncalls},
+                "latency_ms": {"p50": float(np.percentile(lat_ms, 50)), "p90": float(np.percentile(lat_ms, 90)), "p99": float(np.percentile(lat_ms, 99)),
+                               "mean": float(lat_ms.mean()), "min": float(lat_ms.min()), "calls": ncalls, "launches_per_call": launches / ncalls,
+                               "device_ms_per_call": dev_ms / ncalls, "what": "B200Session.run(None, feed): host int64 ids -> host float32 audio, one 128-id utterance"},
+                "clocks": clocks,
+                "e2e": {"value": audio_s / t_all, "unit": "audio-s/s", "h2d_bytes_per_step": args.calls * (128 * 8 + 8 + 12),
+                        "d2h_bytes_per_step": int(samples_out * 4 // args.steps), "note": "serial run() calls, wall clock"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "achieved": dec_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dec_tf / peak_tf, "traffic": None,
+                             "kernel": "HiFi-GAN decoder launches of a single ~450-frame utterance: latency-bound (3 tiles for 148 SMs), quoted for completeness",
+                             "dec_ms": stage["dec"], "flow_ms": stage["flow"], "text_ms": stage["text"], "peak_source": peak_src}}
+        if not args.no_cpu_baseline and world == 1:
+            pool = ReferencePool(path, n_threads)
+            a_s, dt = pool.run([utts[0]] * (4 * pool.procs), None)
+            line["cpu_baseline"] = dict(pool.describe(f"{4 * pool.procs} calls of the same utterance"), value=a_s / dt, unit="audio-s/s")
+            # the latency a reference user sees: ONE process, all threads, one call at a time
+            pool.close()
+            line["spot_check"] = spot_check(sess, path, utts, sids, [0])
+        if rank == 0:
+            print(json.dumps(line))
+        if use_dist:
+            dist.destroy_process_group()
+        return
+
+    # ================================================================== C2-C5: throughput
+    # settle phase (untimed, before the W warm-up steps): one end-to-end pass and one device pass so that every buffer has its
+    # final size, every kernel module is loaded and the page-locked result pool exists before anything is counted
+    for _ in sess.synthesize_many(feeds, out="f32"):
+        pass
+    device_step(feeds)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        device_step(feeds)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = eng.launch_count()
+    eng.timer_start()
+    frames = 0
+    for _ in range(args.steps):
+        frames += device_step(feeds)
+    dev_ms = eng.timer_stop()
+    barrier()
+    launches = eng.launch_count() - launches0
+    stage = eng.stage_ms()
+    kern = [eng.kernel_ms(0), eng.kernel_ms(1)]       # (ms, launches, algorithmic MACs) of the two fused decoder kernels
+    clocks = sampler.stop()
+
+    # ---- end to end, three passes, the MEDIAN reported (r01 reported the faster of two)
+    gather = None
+    if strong:
+        shm_name = f"vits_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if use_dist else os.getpid()}"
+        est = int(frames / args.steps * arch.hop * (world if use_dist else 1) * 1.3) + (1 << 20)
+        if rank == 0:
+            gather = HostGather(shm_name, world, rank, cfg["utts"], est, create=True)
+        barrier()
+        if rank != 0:
+            gather = HostGather(shm_name, world, rank, cfg["utts"], est, create=False)
+        barrier()
+    gstep = [0]
+
+    def e2e_timed(nsteps):
+        if not strong:
+            return e2e_pass(feeds, nsteps)
+        # strong: per step, synthesize this rank's share, then place it in the job-wide host buffer in original order
+        frames = nbytes = 0
+        for _ in range(nsteps):
+            res = []
+            for bidx, (audio, alen) in zip(batches, sess.synthesize_many(feeds, out="f32")):
+                res.append((bidx, audio, alen))
+                frames += int(alen.sum()) // arch.hop
+                nbytes += audio.nbytes
+            gstep[0] += 1
+            total = gather.gather(gstep[0], arch.hop, res)
+            if rank == 0:
+                head = gather.audio[:1 << 20]
+                tail = gather.audio[max(0, total - (1 << 20)):total]
+                if not (np.isfinite(head).all() and np.isfinite(tail).all() and float(np.abs(tail).max()) <= 1.0 and float(np.abs(tail).max()) > 0.0):
+                    raise SystemExit("bench.py: gathered audio is not finite / not tanh-bounded / empty")
+        return frames, nbytes
+
+    e2e_timed(args.steps)        # untimed: the same K-step stream once, so the page-locked result pool has every block the stream needs
+    passes = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e_frames, d2h = e2e_timed(args.steps)
+        torch.cuda.synchronize()
+        passes.append((time.perf_counter() - t0, e_frames, d2h))
+    barrier()
+
+    audio_s = frames * arch.hop / arch.sample_rate
+    e_audio_s = passes[0][1] * arch.hop / arch.sample_rate
+    d2h = passes[0][2]
+    pass_s = [p[0] for p in passes]
+    if use_dist:
+        t = torch.tensor([dev_ms] + pass_s, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([audio_s, e_audio_s, float(frames), float(launches), float(d2h)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        dev_ms, *pass_s = t.tolist()
+        audio_s, e_audio_s, frames_all, launches_all, d2h_all = s.tolist()
+    else:
+        frames_all, launches_all, d2h_all = float(frames), float(launches), float(d2h)
+    e2e_s = float(np.median(pass_s))            # each pass: slowest rank; then the median pass
+
+    # ---- the default C5 line also carries the strong-scaling figures of the same box (rank 0 alone = the N=1 time of the ONE job)
+    strong_sec = None
+    if args.config == "C5" and not strong and not args.no_strong:
+        g_utts, g_len = make_workload(cfg["utts"], seed=cfg["seed"], n_vocab=arch.n_vocab, lo=cfg["lo"], hi=cfg["hi"])
+
+        def feeds_for(w, r):
+            out = []
+            for bidx in scheduler.plan(g_len, w, r, max_ids=args.max_ids, max_utts=args.max_utts):
+                x, lens = scheduler.pad_batch([g_utts[i] for i in bidx])
+                out.append({"input": x, "input_lengths": lens, "scales": np.asarray(SCALES, np.float32)})
+            return out
+
+        def timed(fs):
+            for _ in sess.synthesize_many(fs, out="f32"):
+                pass
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fr, _ = e2e_pass(fs, 1)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts)), fr
+
+        t1 = fr1 = None
+        if use_dist:
+            if rank == 0:
+                t1, fr1 = timed(feeds_for(1, 0))
+            barrier()
+        mine = feeds_for(world, rank)
+        barrier()
+        tn, frn = timed(mine)
+        if use_dist:
+            tt = torch.tensor([tn], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ff = torch.tensor([float(frn)], device="cuda", dtype=torch.float64); dist.all_reduce(ff, op=dist.ReduceOp.SUM)
+            tn, frn = tt.item(), ff.item()
+        else:
+            t1, fr1 = tn, frn
+        if rank == 0:
+            strong_sec = {"what": f"the ONE {cfg['utts']}-utterance list (seed {cfg['seed']}) dealt to {world} rank(s) by scheduler.plan; host ids -> host audio per rank, "
+                                  "no job-wide gather in this section (see --scaling strong for the gathered number)",
+                          "e2e_audio_s_per_s": frn * arch.hop / arch.sample_rate / tn, "seconds": tn, "seconds_one_gpu_same_box": t1,
+                          "efficiency_vs_one_gpu": (t1 / (world * tn)) if t1 else None}
+
+    if rank != 0:
+        if gather is not None:
+            barrier()
+            gather.close(False)
+        if use_dist:
+            dist.destroy_process_group()
+        return
+    if gather is not None:
+        if use_dist:
+            barrier()
+        gather.close(True)
+
     dec_flops = 2.0 * arch.dec_mac_per_frame() * frames            # this rank
     dec_tflops = dec_flops / (stage["dec"] * 1e-3) / 1e12 if stage["dec"] > 0 else 0.0
     value = audio_s / (dev_ms * 1e-3)
-    e2e_passes_max = [round(x, 4) for x in e2e_passes]
-    # the two fused decoder kernels on their own (events around each launch; algorithmic FLOPs = no halo, no padding)
     kernels = []
     for (ms, n, mac), nm in zip(kern, ("k_mrf3_tc<32>: last stage = ConvTranspose1d + 3 ResBlock2 + lrelu/conv_post/tanh in one kernel (dominant kernel)",
                                        "k_mrf3_tc<64>: other fused multi-receptive-field stages")):
         if n > 0 and ms > 0:
             tf = 2.0 * mac / (ms * 1e-3) / 1e12
+            fpl = frames / n if n else 0.0
+            tr = KERNEL_TRAFFIC.get(nm[:13])
+            traffic = None if tr is None else {"bytes_per_launch": tr["bytes_per_frame"] * fpl, "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_frame"] * fpl,
+                                               "frames_per_launch": fpl, "source": tr["source"] + " (bytes per frame of the ncu capture x the frames per launch measured here)"}
             kernels.append({"name": nm, "launches": n, "ms_per_launch": ms / n, "achieved": tf, "frac": tf / peak_tf,
-                            "algorithmic_flops_per_launch": 2.0 * mac / n,
-                            "traffic": KERNEL_TRAFFIC.get(nm[:13])})
+                            "algorithmic_flops_per_launch": 2.0 * mac / n, "traffic": traffic})
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
         "data": "synthetic",
-        "config": {"workload": workload, "precision": args.precision, "l2_policy": "inputs larger than L2 (per-step activations >> 126 MB)",
-                   "frames_per_step_per_gpu": frames // args.steps, "ids_per_step_per_gpu": int(lengths.sum()),
+        "config": {"workload": workload, "precision": args.precision,
+                   "l2_policy": "inputs larger than L2 (per-step activations >> 126 MB)" if frames // args.steps > 4096 else
+                                "per-step activations of this small batch are of the order of L2; W warm-up steps, steps back to back",
+                   "frames_per_step_per_gpu": frames // args.steps, "ids_per_step_per_gpu": int(sum(int(f["input_lengths"].sum()) for f in feeds)),
                    "device_batches": len(feeds), "chunk_frames": args.chunk_frames, "x_realtime": value,
                    "device_busy_ms_per_step": (stage["text"] + stage["flow"] + stage["dec"]) / args.steps},
         "clocks": clocks,
-        "e2e": {"value": e_audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // args.steps,
-                "passes_s": e2e_passes_max, "note": "two K-step passes, the faster one reported; max over ranks each"},
+        "e2e": {"value": e_audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d * (world if use_dist else 1) if strong else h2d,
+                "d2h_bytes_per_step": int(d2h_all if strong else d2h) // args.steps,
+                "passes_s": [round(x, 4) for x in pass_s], "note": "three K-step passes, the MEDIAN reported; each pass is its slowest rank"
+                + ("; includes the host gather of every rank's audio into one buffer in original utterance order (shared memory, rank 0)" if strong else "")},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": dec_tflops / peak_tf, "traffic": DEC_TRAFFIC["bytes"],
-                     "traffic_note": DEC_TRAFFIC["note"],
+                     "frac": dec_tflops / peak_tf, "traffic": None,
+                     "traffic_note": "per-kernel DRAM traffic of the two fused kernels is under roofline.kernels[].traffic; the decoder as a whole is a "
+                                     "launch family, see profiles/README.md for the per-launch dram bytes of every member",
                      "kernel": "HiFi-GAN decoder = BASELINE.json's 'decoder % of tensor-core peak': every launch between conv_pre and the "
                                "tanh output (k_conv_tc<...> + k_mrf3_tc<64> + k_mrf3_tc<32>), rank 0, CUDA events on the engine's stream",
                      "algorithmic_flops_per_frame": 2 * arch.dec_mac_per_frame(), "dec_ms": stage["dec"],
                      "flow_ms": stage["flow"], "text_ms": stage["text"], "peak_source": peak_src,
                      "kernels": kernels},
     }
+    if strong_sec is not None:
+        line["strong_scaling"] = strong_sec
+    if strong:
+        line["config"]["sharding"] = f"scheduler.plan(lengths, {world}, rank): whole length buckets dealt to ranks by estimated cost"
     if not args.no_cpu_baseline and world == 1:
-        a_s, dt, _ = cpu_baseline(path, utts, sample_idx, n_threads)
-        line["cpu_baseline"] = {"value": a_s / dt, "unit": "audio-s/s", "cores": n_threads, "kind": "port",
-                                "sample": f"{len(sample_idx)} of the {args.utts} utterances, B=1 loop (voice.py:265-269), "
-                                          "oracle/vits_oracle.py on torch-CPU (onnxruntime absent offline)"}
+        pool = ReferencePool(path, n_threads)
+        su = [utts[i] for i in sample_idx]
+        ss = None if sids is None else [sids[i] for i in sample_idx]
+        a_s, dt = pool.run(su, ss)
+        line["cpu_baseline"] = dict(pool.describe(f"{len(su)} of the {cfg['utts']} utterances"), value=a_s / dt, unit="audio-s/s")
+        pool.close()
+        rs = np.random.RandomState(0)
+        line["spot_check"] = spot_check(sess, path, utts, sids, sorted(rs.choice(cfg["utts"], size=min(3, cfg["utts"]), replace=False).tolist()))
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()

@@ -83,13 +83,38 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+// TC_WAIT_POLL (round 2, default): poll with the non-blocking test_wait and a short back-off.  The try_wait form with a
+// suspend-time hint compiles to SYNCS...TRYWAIT + NANOSLEEP.SYNCS; the r02c timeline of the fused MRF kernel showed the sleeping
+// warp resuming ~1000 cycles AFTER the last arrival on the barrier (x1 staged at 31 868, the MMA warp past its wait at 32 938) --
+// at eight such hand-offs per 19k-cycle tile that is the tensor pipe's idle time.  A poll costs one SYNCS.PHASECHK per ~100 cycles
+// per waiting warp: noise next to the epilogue warps' own instruction stream.
+#ifndef TC_WAIT_POLL
+#define TC_WAIT_POLL 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
+#if TC_WAIT_POLL
+    while (!mbar_test(bar, parity)) {
+#if TC_WAIT_POLL == 1
+        if (++spins > (1u << 20)) __nanosleep(256);       // ~50 ms of pure polling first: __nanosleep's real granularity is of the order of a microsecond
+#else
+        if (++spins > 4u) __nanosleep(20);
+#endif
+        if (spins > (TC_SPIN_LIMIT << 2)) __trap();
+    }
+#else
     while (!mbar_try(bar, parity)) {
         if (++spins > 64u) __nanosleep(spins > 4096u ? 256 : 32);
         if (spins > TC_SPIN_LIMIT) __trap();
     }
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

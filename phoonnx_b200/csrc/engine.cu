@@ -938,6 +938,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 Mrf3Args& m3 = mrf3_args[i + 1];
                 memset(&m3, 0, sizeof m3);
                 m3.C = co; m3.nrb = A.n_rbk; m3.out_div = (float)A.n_rbk; m3.slope = 0.1f;
+                m3.interleave = h->opts.count("mrf_interleave") ? (int)h->opts["mrf_interleave"] : 0;
                 for (int j = 0; j < A.n_rbk; j++) {
                     m3.k[j] = m.k[j]; m3.d1[j] = m.d1[j]; m3.d2[j] = m.d2[j];
                     m3.w[j][0] = m.w[j][0]; m3.w[j][1] = m.w[j][1]; m3.b[j][0] = m.b[j][0]; m3.b[j][1] = m.b[j][1];
@@ -968,10 +969,15 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         std::vector<int> rb_bf16(A.n_ups + 2, 0);
         for (int i = 0; i < A.n_ups; i++) {
             const int co = chans[i + 1];
-            bool ok = h->precision == 1 && A.resblock_type == 2 && mrf_on[i + 1] == 0 && h->opts["no_stage_bf16"] == 0 && co % 16 == 0 &&
+            // (ResBlock1 stages too, round 2: `high` ran conv by conv on fp32 rows -- 12 B per value per conv through HBM and an fp32 ->
+            // bf16 conversion pass in every loader; C4 decoder 0.25 of tensor peak, profiles/r02e)
+            bool ok = h->precision == 1 && mrf_on[i + 1] == 0 && h->opts["no_stage_bf16"] == 0 && co % 16 == 0 &&
                       h->ups[i].A.wtc && h->ups[i].B.wtc && (h->ups[i].rate * co) % 8 == 0;
             for (int j = 0; j < A.n_rbk && ok; j++)
-                for (int c2 = 0; c2 < A.rb_ndil[j]; c2++) if (!h->rb_c1[i * A.n_rbk + j][c2].wtc) ok = false;
+                for (int c2 = 0; c2 < A.rb_ndil[j]; c2++) {
+                    if (!h->rb_c1[i * A.n_rbk + j][c2].wtc) ok = false;
+                    if (A.resblock_type == 1 && !h->rb_c2[i * A.n_rbk + j][c2].wtc) ok = false;
+                }
             rb_bf16[i + 1] = ok;
         }
         // ... of which: stages whose second convs run as one summed launch (needs a consumer that takes bf16 rows or fp32)
@@ -1212,6 +1218,21 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                         if (fin) { a.accumulate = !first; if (last) a.out_div = (float)A.n_rbk; }
                         if ((rc = launch_conv(h, a, Tout, true))) return rc;
                         in = dst;
+                    } else if (rb_bf16[i + 1]) {
+                        // modules.py:301-314 on bf16 operand rows: xt = c1(lrelu x) leaves as bf16 lrelu(xt) -- exactly c2's MMA operand;
+                        // c2 adds the residual x recovered from ITS operand rows (lrelu is invertible) and writes the next x the same
+                        // way; only the per-resblock result accumulates in fp32.  2 B per value per conv instead of 12, no conversion pass.
+                        __nv_bfloat16* inb = (c == 0) ? Xb : reinterpret_cast<__nv_bfloat16*>((c & 1) ? Ya : Yb);
+                        __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(T1b);
+                        a = base_args(h->rb_c1[n][c], nullptr, 0, 0, T1b, co, 0);
+                        a.xb = inb; a.ldxb = co; a.outb = tb; a.outb_slope = 0.1f;
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
+                        float* dstf = (c & 1) ? Yb : Ya;
+                        a = base_args(h->rb_c2[n][c], nullptr, 0, 0, fin ? XS : dstf, co, 0);
+                        a.xb = tb; a.ldxb = co; a.resb = inb; a.ldresb = co; a.resb_slope = 0.1f;
+                        if (fin) { a.accumulate = !first; if (last) a.out_div = (float)A.n_rbk; }
+                        else { a.outb = reinterpret_cast<__nv_bfloat16*>(dstf); a.outb_slope = 0.1f; }
+                        if ((rc = launch_conv(h, a, Tout, true))) return rc;
                     } else {
                         // modules.py:301-314: xt = c1(lrelu(x)); xt = c2(lrelu(xt)); x = xt + x
                         a = base_args(h->rb_c1[n][c], in, co, 0, T1b, co, 0); a.in_act = 1; a.in_slope = 0.1f;

@@ -54,7 +54,7 @@ struct Mrf3Args {
     const __nv_bfloat16* w[MRF3_MAX_RB][2];  const float* b[MRF3_MAX_RB][2];
     const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
     const int4* tdesc;                                           // per tile {first row of the utterance, its rows, o0, -}
-    float out_div;  float slope;
+    float out_div;  float slope;  int interleave;                // issue order of the convs (mrf3_step)
     float* out;                                                  // fp32 [rows, C]                       (or null)
     __nv_bfloat16* outb;  float outb_slope;                      // bf16 lrelu_{outb_slope}(out) [rows, C] (or null)
     const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
@@ -92,8 +92,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // x1 operand tile each conv2 -> stage x1(r+1) -> conv2 hand-off then idled the tensor pipe (r02a timeline: 0.4-1.0k cycles each, ~3.5k
 // of a 19k-cycle tile).  Interleaved -- C1(0) C1(1) C2(0) C1(2) C2(1) ... C2(n_r - 1) -- conv1(r+1) runs while the epilogue warps turn
 // conv1(r) into x1(r), and conv2(r-1) while they work on conv1(r): every conv2 finds its operand staged and the x1 tile free.
-__device__ __forceinline__ void mrf3_step(int step, int nrb, int& cv, int& r) {
-    if (step == 0) { cv = 0; r = 0; }
+__device__ __forceinline__ void mrf3_step(int step, int nrb, int interleave, int& cv, int& r) {
+    if (!interleave) { cv = step >= nrb; r = cv ? step - nrb : step; }
+    else if (step == 0) { cv = 0; r = 0; }
     else if (step == 2 * nrb - 1) { cv = 1; r = nrb - 1; }
     else { const int j = step - 1; cv = j & 1; r = cv ? (j >> 1) : (j >> 1) + 1; }
 }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 // same order as the MMA warps issue the convs (mrf3_step): C1(0) C1(1) C2(0) C1(2) C2(1) C2(2)
                 for (int step = 0; step < 2 * a.nrb; step++) {
                         int cv, r;
-                        mrf3_step(step, a.nrb, cv, r);
+                        mrf3_step(step, a.nrb, a.interleave, cv, r);
                         const __nv_bfloat16* wsrc = a.w[r][cv];
                         for (int tap = 0; tap < a.k[r]; tap++) {
                             if (!c.resident) tc::mbar_wait(bar_empty0 + 8u * s, ph);
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 for (int step = 0; step < 2 * a.nrb; step++) {
                     {
                         int cv, r;
-                        mrf3_step(step, a.nrb, cv, r);
+                        mrf3_step(step, a.nrb, a.interleave, cv, r);
                         if (cv == 1) {
                             // the next tile's ConvTranspose goes in before the last conv2: its accumulators (conv1 buffers 0..) were
                             // drained when x1(n_r - 2) was staged, and E0 of the next tile then runs under conv2(n_r - 1)

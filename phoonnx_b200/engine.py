@@ -83,7 +83,7 @@ def load_library(path: Optional[str] = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("VITS_B200_LIB") or LIB_PATH      # the env override exists for A/B runs of two builds on one box
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")

@@ -545,3 +545,25 @@ def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
         outs.append((a.copy(), alen.copy()))
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.isfinite(outs[1][0]).all() and np.array_equal(outs[0][0], outs[1][0])
+
+
+def test_resblock1_stages_on_bf16_rows_match_fp32_rows(lib, tmp_path_factory):
+    """ResBlock1 (`high`, modules.py:301-314) conv by conv: bf16 operand rows between the convs (default) vs fp32 rows with a
+    conversion pass per launch (`no_stage_bf16`): same MMAs, the residual stream rounds to bf16 once per conv pair."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, "high", 1)
+    rs = np.random.RandomState(12)
+    lens = np.array([97, 3, 160, 41, 1], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
+    outs = []
+    for opt in (0, 1):
+        sess = B200Session(p, precision="bf16")
+        sess.engine.set_option("no_stage_bf16", opt)
+        a, alen = sess.synthesize_packed(feed)
+        outs.append((np.array(a), np.array(alen)))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert snr_db(outs[1][0], outs[0][0]) > 45.0, snr_db(outs[1][0], outs[0][0])
