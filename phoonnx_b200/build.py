@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
 OUT = os.path.join(HERE, "libvits_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "kernels_f32.cuh", "attention.cuh", "conv_tc.cuh", "mrf_tc.cuh", "mrf2_tc.cuh", "mrf3_tc.cuh", "probe_tc.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "kernels_f32.cuh", "attention.cuh", "conv_tc.cuh", "mrf_tiles.cuh", "mrf3_tc.cuh", "probe_tc.cuh")] + \
        [os.path.join(os.path.dirname(HERE), "include", f) for f in ("vits_b200.h", "vits_b200_test.h")]
 
 

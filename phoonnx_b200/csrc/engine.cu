@@ -14,8 +14,6 @@
 #include "kernels_f32.cuh"
 #include "attention.cuh"
 #include "conv_tc.cuh"
-#include "mrf_tc.cuh"
-#include "mrf2_tc.cuh"
 #include "mrf3_tc.cuh"
 #include "probe_tc.cuh"
 
@@ -901,69 +899,44 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         h->last_nchunks++;
         std::vector<int> cu_local(nB + 1);
         for (int i = 0; i <= nB; i++) cu_local[i] = h->h_cu_y[b_lo + i] - f_lo;
-        // fused MRF stage kernel (mrf3_tc.cuh; mrf2_tc.cuh / mrf_tc.cuh with options mrf_v2 / mrf_v1, kept as test references) where the stage qualifies: bf16 mode,
-        // ResBlock2, 32/64 channels.  The last stage also absorbs lrelu -> conv_post -> tanh.
-        std::vector<MrfArgs> mrf_args(A.n_ups + 1);
-        std::vector<MrfCfg> mrf_cfg(A.n_ups + 1);
-        std::vector<Mrf2Args> mrf2_args(A.n_ups + 1);
-        std::vector<Mrf2Cfg> mrf2_cfg(A.n_ups + 1);
+        // fused MRF stage kernel (mrf3_tc.cuh) where the stage qualifies: bf16 mode, ResBlock2, 32 / 64 channels.  The last stage also
+        // absorbs its ConvTranspose1d and lrelu -> conv_post -> tanh.  Stages that do not qualify run conv by conv on bf16 operand rows
+        // (below) -- which is also the reference the fused kernel is tested against (option no_fused_mrf).
         std::vector<Mrf3Args> mrf3_args(A.n_ups + 1);
         std::vector<Mrf3Cfg> mrf3_cfg(A.n_ups + 1);
-        std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: unfused, 1: v1, 2: v2, 3: v3 (bf16 inter-stage rows, optional fused ConvTranspose)
-        std::vector<int> up_fused(A.n_ups + 2, 0);    // stage's ConvTranspose runs inside its v3 kernel
+        std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: conv by conv, 3: fused (bf16 inter-stage rows, optional fused ConvTranspose)
+        std::vector<int> up_fused(A.n_ups + 2, 0);    // stage's ConvTranspose runs inside its fused kernel
         bool post_fused = false;
-        const bool use_v1 = h->opts["mrf_v1"] != 0;
-        const bool use_v2 = h->opts["mrf_v2"] != 0;
         for (int i = 0; i < A.n_ups; i++) {
             const int co = chans[i + 1];
             if (h->precision != 1 || A.resblock_type != 2 || A.n_rbk > MRF_MAX_RB || h->opts["no_fused_mrf"] != 0) continue;
-            MrfArgs& m = mrf_args[i + 1];
-            Mrf2Args& m2 = mrf2_args[i + 1];
-            memset(&m, 0, sizeof m); memset(&m2, 0, sizeof m2);
-            m.C = co; m.nrb = A.n_rbk; m.out_div = (float)A.n_rbk; m.slope = 0.1f;
-            m2.C = co; m2.nrb = A.n_rbk; m2.out_div = (float)A.n_rbk; m2.slope = 0.1f;
+            // the stage's input arrives as bf16 lrelu rows; when the previous stage is fused as well and the geometry allows (u = 4),
+            // the ConvTranspose runs inside the kernel on the previous stage's bf16 output
+            Mrf3Args& m3 = mrf3_args[i + 1];
+            memset(&m3, 0, sizeof m3);
+            m3.C = co; m3.nrb = A.n_rbk; m3.out_div = (float)A.n_rbk; m3.slope = 0.1f;
+            m3.interleave = h->opts.count("mrf_interleave") ? (int)h->opts["mrf_interleave"] : 0;
             bool ok = true;
             for (int j = 0; j < A.n_rbk; j++) {
                 const auto& cv = h->rb_c1[i * A.n_rbk + j];
                 if (A.rb_ndil[j] != 2 || !cv[0].wtc || !cv[1].wtc) { ok = false; break; }
-                m.k[j] = A.rb_kernels[j]; m.d1[j] = A.rb_dilations[j][0]; m.d2[j] = A.rb_dilations[j][1];
-                m.w[j][0] = cv[0].wtc; m.w[j][1] = cv[1].wtc; m.b[j][0] = cv[0].b; m.b[j][1] = cv[1].b;
-                m2.k[j] = m.k[j]; m2.d1[j] = m.d1[j]; m2.d2[j] = m.d2[j];
-                m2.w[j][0] = m.w[j][0]; m2.w[j][1] = m.w[j][1]; m2.b[j][0] = m.b[j][0]; m2.b[j][1] = m.b[j][1];
+                m3.k[j] = A.rb_kernels[j]; m3.d1[j] = A.rb_dilations[j][0]; m3.d2[j] = A.rb_dilations[j][1];
+                m3.w[j][0] = cv[0].wtc; m3.w[j][1] = cv[1].wtc; m3.b[j][0] = cv[0].b; m3.b[j][1] = cv[1].b;
             }
             if (!ok) continue;
-            if (!use_v1 && !use_v2) {
-                // v3: the stage's input arrives as bf16 lrelu rows; when the previous stage is v3 as well and the geometry
-                // allows (u = 4), the ConvTranspose runs inside the kernel on the previous stage's bf16 output
-                Mrf3Args& m3 = mrf3_args[i + 1];
-                memset(&m3, 0, sizeof m3);
-                m3.C = co; m3.nrb = A.n_rbk; m3.out_div = (float)A.n_rbk; m3.slope = 0.1f;
-                m3.interleave = h->opts.count("mrf_interleave") ? (int)h->opts["mrf_interleave"] : 0;
-                for (int j = 0; j < A.n_rbk; j++) {
-                    m3.k[j] = m.k[j]; m3.d1[j] = m.d1[j]; m3.d2[j] = m.d2[j];
-                    m3.w[j][0] = m.w[j][0]; m3.w[j][1] = m.w[j][1]; m3.b[j][0] = m.b[j][0]; m3.b[j][1] = m.b[j][1];
-                }
-                const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
-                const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
-                const auto& U = h->ups[i];
-                const bool can_up = i >= 1 && mrf_on[i] == 3 && U.rate == 4 && U.A.wtc && U.B.wtc && h->opts["no_fused_ups"] == 0;
-                bool done = false;
-                for (int tryu = can_up ? 1 : 0; tryu >= 0 && !done; tryu--) {
-                    m3.up_u = tryu ? U.rate : 0; m3.up_cin = tryu ? U.A.cin : 0;
-                    for (int tryp = want_post ? 1 : 0; tryp >= 0 && !done; tryp--)
-                        if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0)) {
-                            mrf_on[i + 1] = 3; up_fused[i + 1] = tryu; if (tryp) post_fused = true; done = true;
-                        }
-                }
-                if (!done) { m3.up_u = 0; m3.up_cin = 0; }
+            const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
+            const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
+            const auto& U = h->ups[i];
+            const bool can_up = i >= 1 && mrf_on[i] == 3 && U.rate == 4 && U.A.wtc && U.B.wtc && h->opts["no_fused_ups"] == 0;
+            bool done = false;
+            for (int tryu = can_up ? 1 : 0; tryu >= 0 && !done; tryu--) {
+                m3.up_u = tryu ? U.rate : 0; m3.up_cin = tryu ? U.A.cin : 0;
+                for (int tryp = want_post ? 1 : 0; tryp >= 0 && !done; tryp--)
+                    if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0)) {
+                        mrf_on[i + 1] = 3; up_fused[i + 1] = tryu; if (tryp) post_fused = true; done = true;
+                    }
             }
-            if (!mrf_on[i + 1] && !use_v1) {
-                const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
-                const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
-                if (want_post && mrf2_plan(m2, mrf2_cfg[i + 1], nbp, true)) { mrf_on[i + 1] = 2; post_fused = true; }
-                else if (mrf2_plan(m2, mrf2_cfg[i + 1], nbp, false)) mrf_on[i + 1] = 2;
-            }
-            if (!mrf_on[i + 1] && mrf_tc_plan(m, mrf_cfg[i + 1], (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : 2))) mrf_on[i + 1] = 1;
+            if (!done) { m3.up_u = 0; m3.up_cin = 0; }
         }
         // unfused ResBlock2 stages (e.g. the 128-channel first stage) in bf16 mode: bf16 operand rows between the convs
         std::vector<int> rb_bf16(A.n_ups + 2, 0);
@@ -990,7 +963,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
         for (int i = 0; i <= A.n_ups; i++)
-            tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (mrf_on[i] == 2 ? mrf2_cfg[i].t_step : (mrf_on[i] ? mrf_cfg[i].t_out : 0)));
+            tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : 0);
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
             (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) || (rc = ensure(h, h->fpos, (size_t)Fr * 8)) ||
@@ -1139,31 +1112,6 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                     cudaError_t e = mrf3_launch_timed(h, m, mrf3_cfg[i + 1], 3 + kw);
                     if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf3 launch: %s", cudaGetErrorString(e));
                     h->launches += 2;
-                }
-            } else if (mrf_on[i + 1] == 2) {
-                Mrf2Args& m = mrf2_args[i + 1];
-                m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
-                if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
-                m.dbg = nullptr;
-                if (h->opts.count("mrf_dbg") && (int)h->opts["mrf_dbg"] == i + 1) {
-                    if ((rc = ensure(h, h->mrf_dbg, (size_t)MRF2_DBG_TILES * 48 * 8))) return rc;
-                    CK(h, cudaMemsetAsync(h->mrf_dbg.p, 0, (size_t)MRF2_DBG_TILES * 48 * 8, st));
-                    m.dbg = ptr<unsigned long long>(h->mrf_dbg);
-                }
-                if (m.ntiles > 0) {
-                    if ((rc = ensure(h, h->tdesc, (size_t)m.ntiles * sizeof(int4)))) return rc;
-                    m.tdesc = ptr<int4>(h->tdesc);
-                    cudaError_t e = mrf2_launch(m, mrf2_cfg[i + 1], h->num_sms, st);
-                    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf2 launch: %s", cudaGetErrorString(e));
-                    h->launches += 2;
-                }
-            } else if (mrf_on[i + 1]) {
-                MrfArgs& m = mrf_args[i + 1];
-                m.x = X; m.out = XS; m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
-                if (m.ntiles > 0) {
-                    cudaError_t e = mrf_tc_launch(m, mrf_cfg[i + 1], h->num_sms, st);
-                    if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "mrf_tc launch: %s", cudaGetErrorString(e));
-                    h->launches++;
                 }
             } else if (stage_sum2[i + 1]) {
                 // ResBlock2 stage (modules.py:355-364) in n_r + 1 launches: x1_r = x + conv_{k_r,d_r1}(lrelu x) for every resblock, written
@@ -1319,7 +1267,7 @@ int64_t vits_fetch(vits_handle* h, const char* name, void* out, int64_t capacity
         else { src = h->P.p; n = Fr * A.inter; }
     }
     else if (k == "conv_dbg") { src = h->conv_dbg.p; n = h->conv_dbg.p ? TC_DBG_TILES * 16 * 2 : 0; }
-    else if (k == "mrf_dbg") { src = h->mrf_dbg.p; n = h->mrf_dbg.p ? MRF2_DBG_TILES * 48 * 2 : 0; }
+    else if (k == "mrf_dbg") { src = h->mrf_dbg.p; n = h->mrf_dbg.p ? MRF3_DBG_TILES * 48 * 2 : 0; }
     else return fail(h, VITS_E_INVALID, "unknown stage tensor '%s'", name);
     if (!src || n == 0) return fail(h, VITS_E_STATE, "stage tensor '%s' is not available", name);
     if (n > capacity_elems) return fail(h, VITS_E_INVALID, "fetch '%s': capacity %lld < %lld", name, (long long)capacity_elems, (long long)n);

@@ -33,7 +33,7 @@
 // Warp roles (640 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
 // elected lane = weight producer (+ TMEM allocation), warps 17 and 19 elected lane = MMA issuers, warp 18 = input-row loader.
 #pragma once
-#include "mrf2_tc.cuh"
+#include "mrf_tiles.cuh"
 
 #define MRF3_THREADS 640
 #define MRF3_EPI_THREADS 512
@@ -722,7 +722,7 @@ static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int
 // the per-tile descriptors the kernel reads (launched separately so that the kernel proper can be timed alone)
 static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c, cudaStream_t st) {
     if (a.ntiles < 1) return cudaSuccess;
-    k_mrf2_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
+    k_mrf_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
                                                          const_cast<int4*>(a.tdesc));
     return cudaGetLastError();
 }
