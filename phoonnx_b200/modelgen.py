@@ -211,7 +211,7 @@ def conv_attr_table(a: VitsArch) -> Dict[str, dict]:
 
 
 def write_onnx(W: Dict[str, np.ndarray], a: VitsArch, path: str, dedup_identity: bool = True,
-               phoneme_id_map: Optional[dict] = None) -> None:
+               phoneme_id_map: Optional[dict] = None, graph_inputs: Optional[List[str]] = None) -> None:
     """Serialise canonical tensors the way export_onnx.py's torch.onnx.export does."""
     attrs = conv_attr_table(a)
     inits: Dict[str, np.ndarray] = {}
@@ -265,7 +265,8 @@ def write_onnx(W: Dict[str, np.ndarray], a: VitsArch, path: str, dedup_identity:
         nm = anon_name("Exp")
         inits[nm] = (-np.asarray(W["dp.flows.0.logs"], dtype=np.float32))
         nodes.append(pb.encode_node("Exp", "/dp/flows.0/Exp", [nm], ["/dp/flows.0/Exp_output_0"]))
-    inputs = ["input", "input_lengths", "scales"] + (["sid"] if a.n_speakers > 1 else [])
+    # `graph_inputs`: other exporters of the same model declare other input lists (no `scales`: voice.py:358; a `langid`: voice.py:369)
+    inputs = list(graph_inputs) if graph_inputs else ["input", "input_lengths", "scales"] + (["sid"] if a.n_speakers > 1 else [])
     meta = {   # export_onnx.py:335-345
         "model_type": "vits", "n_speakers": a.n_speakers, "n_vocab": a.n_vocab,
         "sample_rate": a.sample_rate, "alphabet": "ipa", "phoneme_type": "raw",

@@ -38,7 +38,7 @@ class B200Session:
 
     def __init__(self, path_or_bytes, sess_options=None, providers=None, provider_options=None, *,
                  device: int = 0, precision: str = "fp32", sample_rate: Optional[int] = None,
-                 max_chunk_frames: Optional[int] = None, seed: int = 0):
+                 max_chunk_frames: Optional[int] = None, seed: int = 0, default_scales=None):
         self._path = str(path_or_bytes)
         W, arch, hdr = load_model(self._path, sample_rate)
         self.arch = arch
@@ -47,11 +47,20 @@ class B200Session:
         self.engine = Engine(arch, blobs, opts, device=device, precision=precision)
         if max_chunk_frames:
             self.engine.set_option("max_chunk_frames", max_chunk_frames)
-        self._inputs = [NodeArg("input", "tensor(int64)", ["batch_size", "phonemes"]),
-                        NodeArg("input_lengths", "tensor(int64)", ["batch_size"]),
-                        NodeArg("scales", "tensor(float)", [3])]
-        if arch.n_speakers > 1:
-            self._inputs.append(NodeArg("sid", "tensor(int64)", ["batch_size"]))
+        # the inputs THIS file's graph declares, in its order (voice.py:347 reads exactly this list and filters its feed by it,
+        # voice.py:358-373): voices exported without a `scales` input get none (their scales are constants of the graph: the
+        # session then uses `default_scales`), single-language voices that still declare `langid` get it accepted and ignored
+        known = {"input": ("tensor(int64)", ["batch_size", "phonemes"]), "input_lengths": ("tensor(int64)", ["batch_size"]),
+                 "scales": ("tensor(float)", [3]), "sid": ("tensor(int64)", ["batch_size"]), "langid": ("tensor(int64)", ["batch_size"])}
+        declared = [n for n in (hdr.inputs or []) if n in known] or ["input", "input_lengths", "scales"]
+        for must in ("input", "input_lengths"):
+            if must not in declared:
+                raise ValueError(f"voice file declares no '{must}' input: not a VITS voice this engine can run")
+        if arch.n_speakers > 1 and "sid" not in declared:
+            declared.append("sid")
+        self._inputs = [NodeArg(n, known[n][0], known[n][1]) for n in declared if n != "sid" or arch.n_speakers > 1]
+        self._has_scales = "scales" in declared
+        self.default_scales = np.asarray(default_scales if default_scales is not None else (0.667, 1.0, 0.8), np.float32)   # config.py:9-11
         self._outputs = [NodeArg("output", "tensor(float)", ["batch_size", 1, 1, "time"])]
         self._seed = int(seed)
         self._calls = 0
@@ -88,7 +97,7 @@ class B200Session:
             if k not in known:
                 raise ValueError(f"Invalid input name: {k}")
         for a in self._inputs:
-            if a.name not in feed:
+            if a.name not in feed and a.name != "langid":
                 raise ValueError(f"Required input '{a.name}' is missing from the feed")
         x = np.asarray(feed["input"])
         lens = np.asarray(feed["input_lengths"])
@@ -100,9 +109,16 @@ class B200Session:
             raise ValueError("empty batch / empty phoneme sequence")
         if lens.min() < 1 or lens.max() > x.shape[1]:
             raise ValueError("input_lengths must lie in [1, T]")
-        scales = np.asarray(feed["scales"])
-        if scales.dtype != np.float32 or scales.shape != (3,):
-            raise ValueError("'scales' must be float32 [3] = [noise_scale, length_scale, noise_w] (voice.py:364-367)")
+        if self._has_scales:
+            scales = np.asarray(feed["scales"])
+            if scales.dtype != np.float32 or scales.shape != (3,):
+                raise ValueError("'scales' must be float32 [3] = [noise_scale, length_scale, noise_w] (voice.py:364-367)")
+        else:
+            scales = self.default_scales                 # the graph has no such input (voice.py:358): its scales are fixed
+        if "langid" in feed:
+            lg = np.asarray(feed["langid"])              # single-language voice: accepted (voice.py:369), nothing to select
+            if lg.dtype != np.int64 or lg.shape != (x.shape[0],) or (lg != 0).any():
+                raise ValueError("'langid' must be int64 [B] of zeros: this voice has one language")
         sid = None
         if self.arch.n_speakers > 1:
             sid = np.asarray(feed["sid"])

@@ -317,6 +317,9 @@ def load_model(path: str, sample_rate: Optional[int] = None) -> Tuple[Dict[str, 
     has_sid = "sid" in model.inputs
     if has_sid != (arch.n_speakers > 1):
         raise ValueError("graph inputs and emb_g disagree about multi-speaker support")
+    if any(k.startswith("emb_l.") or k.startswith("emb_lang.") for k in W):
+        # multi-lingual voices (a language embedding selected by `langid`, voice.py:369) condition the text encoder: not built
+        raise NotImplementedError("this voice carries a language embedding (multi-lingual VITS): not supported by the B200 engine")
     return W, arch, model
 
 
@@ -325,25 +328,48 @@ def load_checkpoint(path: str, sample_rate: Optional[int] = None):
     import pickle
     import torch
 
-    class _Stub:  # pytorch_lightning.utilities.parsing.AttributeDict and friends
+    class _Stub:  # pytorch_lightning.utilities.parsing.AttributeDict, callbacks, loggers, ...: inert placeholders
         def __init__(self, *a, **k):
             pass
 
         def __setstate__(self, s):
             self.__dict__.update(s if isinstance(s, dict) else {})
 
+        def __call__(self, *a, **k):
+            return _Stub()
+
+    # A voice checkpoint is a pickle: unpickling an untrusted one with the stock Unpickler executes whatever callable it names.
+    # Only tensor reconstruction and plain containers resolve to real objects here; every other global becomes an inert stub, so a
+    # hostile file can at worst fail to load.  (First choice is torch's own weights_only loader, which needs no pickle globals at all.)
+    _ALLOWED = {
+        ("collections", "OrderedDict"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"),
+        ("builtins", "int"), ("builtins", "float"), ("builtins", "str"), ("builtins", "bool"), ("builtins", "bytes"),
+        ("builtins", "slice"), ("builtins", "complex"), ("builtins", "frozenset"),
+        ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"), ("torch._utils", "_rebuild_tensor"),
+        ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    }
+    _STORAGES = {"FloatStorage", "DoubleStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage", "ShortStorage",
+                 "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage"}
+
     class _Unpickler(pickle.Unpickler):
         def find_class(self, module, name):
-            if module.startswith("pytorch_lightning") or module.startswith("lightning"):
-                return dict if name == "AttributeDict" else _Stub
-            return super().find_class(module, name)
+            if (module, name) in _ALLOWED or (module in ("torch", "torch.storage") and name in _STORAGES):
+                return super().find_class(module, name)
+            if name == "AttributeDict":
+                return dict
+            return _Stub
 
     class _P:
         Unpickler = _Unpickler
         __name__ = "pickle"
         load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
 
-    ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_P)
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_P)
     sd = ck.get("state_dict", ck)
     W = canonical_from_state_dict(sd)
     arch = infer_arch(W, None, None, sample_rate)

@@ -202,3 +202,47 @@ def test_synthesize_batch_equals_per_sentence_runs(built_lib, tmp_path_factory):
                 one = np.clip(one / m if m >= 1e-8 else np.zeros_like(one), -1.0, 1.0).astype(np.float32)
             assert a.shape == one.shape and np.array_equal(np.asarray(a), one)
     assert n_batch < (sess.engine.launch_count() - n0) / 3      # one pass over the kernels instead of one per sentence
+
+
+def test_other_voice_formats_on_the_gpu(built_lib, tmp_path_factory):
+    """SURVEY.md 8f-3 on the device: (a) a Lightning-style .ckpt (model_g.* keys, weight_g / weight_v pairs, extra pickled
+    objects) loads straight into the engine and synthesises exactly what the exported .onnx of the same weights does;
+    (b) a voice whose graph declares no `scales` input (voice.py:358) runs at the session's default scales; (c) a single-language
+    voice that declares `langid` (voice.py:369) accepts it."""
+    import torch
+    from phoonnx_b200 import modelgen
+    from phoonnx_b200.session import B200Session
+    d = tmp_path_factory.mktemp("fmt")
+    a = modelgen.make_arch("tiny", 1)
+    W = modelgen.synth_weights(a, 7)
+    onnx_p = str(d / "v.onnx")
+    modelgen.write_onnx(W, a, onnx_p)
+    rs = np.random.RandomState(0)
+    sd = {}
+    for k, v in W.items():
+        if k.startswith("flow.flows.") and ".enc." in k and k.endswith(".weight"):
+            # un-fold the weight norm the way a training checkpoint stores it: w = g * v / ||v||
+            g = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+            sd["model_g." + k[:-len("weight")] + "weight_g"] = torch.from_numpy(g)
+            sd["model_g." + k[:-len("weight")] + "weight_v"] = torch.from_numpy(v.copy())
+        else:
+            sd["model_g." + k] = torch.from_numpy(v.copy())
+    sd["model_d.discriminators.0.weight"] = torch.zeros(3)
+    ck_p = str(d / "v.ckpt")
+    torch.save({"state_dict": sd, "epoch": 3, "hyper_parameters": {"sample_rate": a.sample_rate}}, ck_p)
+    ids = rs.randint(0, a.n_vocab, (3, 40)).astype(np.int64)
+    lens = np.array([40, 7, 23], np.int64)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES}
+    want, wlen = B200Session(onnx_p, precision="fp32", seed=4).synthesize_packed(feed)
+    got, glen = B200Session(ck_p, precision="fp32", seed=4, sample_rate=a.sample_rate).synthesize_packed(feed)
+    assert np.array_equal(wlen, glen) and np.abs(np.array(want) - np.array(got)).max() < 2e-6      # weight-norm fold: fp32 rounding only
+    # (b), (c)
+    alt_p = str(d / "noscales.onnx")
+    modelgen.write_onnx(W, a, alt_p, graph_inputs=["input", "input_lengths", "langid"])
+    alt = B200Session(alt_p, precision="fp32", seed=4, default_scales=SCALES)
+    assert [i.name for i in alt.get_inputs()] == ["input", "input_lengths", "langid"]
+    out = alt.run(None, {"input": ids, "input_lengths": lens, "langid": np.zeros(3, np.int64)})[0]
+    ref = B200Session(onnx_p, precision="fp32", seed=4).run(None, feed)[0]
+    assert np.array_equal(out, ref)
+    with pytest.raises(ValueError):
+        alt.run(None, feed)                                          # `scales` is not an input of that graph

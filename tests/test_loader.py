@@ -94,3 +94,53 @@ def test_gzip_and_plain_are_equivalent(tmp_path, golden_dir):
     W1, a1, _ = load_model(gz)
     W2, a2, _ = load_model(plain)
     assert a1 == a2 and all(np.array_equal(W1[k], W2[k]) for k in W1)
+
+
+def test_checkpoint_loader_never_runs_pickled_callables(tmp_path):
+    """a voice checkpoint is a pickle; only tensor reconstruction and plain containers may resolve to real objects."""
+    import builtins
+    import torch
+    from phoonnx_b200.weights import load_checkpoint
+    a = modelgen.make_arch("tiny")
+    W = modelgen.synth_weights(a, 3)
+
+    class Evil:
+        def __reduce__(self):
+            return (exec, ("import builtins; builtins.PWNED_BY_CHECKPOINT = 1",))
+
+    p = str(tmp_path / "evil.ckpt")
+    torch.save({"state_dict": {"model_g." + k: torch.from_numpy(v.copy()) for k, v in W.items()}, "callbacks": Evil(),
+                "hyper_parameters": {"x": Evil()}}, p)
+    W2, a2, hdr = load_checkpoint(p)
+    assert not hasattr(builtins, "PWNED_BY_CHECKPOINT")
+    assert a2 == a and set(W2) == set(W) and all(np.array_equal(W[k], W2[k]) for k in W)
+    assert hdr.inputs[:3] == ["input", "input_lengths", "scales"]
+
+
+def test_multilingual_voices_are_refused(tmp_path):
+    a = modelgen.make_arch("tiny")
+    W = modelgen.synth_weights(a, 1)
+    W["emb_l.weight"] = np.zeros((2, 4), np.float32)
+    p = str(tmp_path / "ml.onnx")
+    modelgen.write_onnx(W, a, p, graph_inputs=["input", "input_lengths", "scales", "langid"])
+    with pytest.raises(NotImplementedError):
+        load_model(p)
+
+
+def test_session_feed_follows_the_graph_inputs():
+    """voice.py:347-373: the caller filters its feed by session.get_inputs(); a voice exported without `scales` gets none and runs
+    at the session's default scales, a single-language voice that declares `langid` accepts (and ignores) it."""
+    from phoonnx_b200.session import B200Session, NodeArg
+    s = B200Session.__new__(B200Session)
+    s.arch = modelgen.make_arch("tiny", 1)
+    s._inputs = [NodeArg("input", "tensor(int64)", None), NodeArg("input_lengths", "tensor(int64)", None), NodeArg("langid", "tensor(int64)", None)]
+    s._has_scales = False
+    s.default_scales = np.asarray((0.5, 1.1, 0.7), np.float32)
+    ids = np.array([[1, 0, 5, 0, 2]], np.int64)
+    x, lens, scales, sid = s._unpack_feed({"input": ids, "input_lengths": np.array([5], np.int64)})
+    assert np.array_equal(scales, s.default_scales) and sid is None
+    s._unpack_feed({"input": ids, "input_lengths": np.array([5], np.int64), "langid": np.array([0], np.int64)})
+    with pytest.raises(ValueError):
+        s._unpack_feed({"input": ids, "input_lengths": np.array([5], np.int64), "langid": np.array([1], np.int64)})
+    with pytest.raises(ValueError):
+        s._unpack_feed({"input": ids, "input_lengths": np.array([5], np.int64), "scales": np.zeros(3, np.float32)})   # not an input of this graph
