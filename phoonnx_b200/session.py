@@ -35,6 +35,8 @@ class NodeArg:
 
 class B200Session:
     TEST_FEEDS = ("noise_dp", "noise_z", "logw")
+    _has_scales = True                                   # the exporter's graph declares `scales` (export_onnx.py:300-304)
+    default_scales = np.asarray((0.667, 1.0, 0.8), np.float32)     # config.py:9-11
 
     def __init__(self, path_or_bytes, sess_options=None, providers=None, provider_options=None, *,
                  device: int = 0, precision: str = "fp32", sample_rate: Optional[int] = None,
