@@ -587,7 +587,11 @@ def main():
     gather = None
     if strong:
         shm_name = f"vits_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if use_dist else os.getpid()}"
-        est = int(frames / args.steps * arch.hop * (world if use_dist else 1) * 1.3) + (1 << 20)
+        # capacity every rank agrees on: the job's frames per step as just measured (durations are redrawn every step: 30 % head-room)
+        tot = torch.tensor([float(frames) / args.steps], device="cuda", dtype=torch.float64)
+        if use_dist:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        est = int(tot.item() * arch.hop * 1.3) + (1 << 20)
         if rank == 0:
             gather = HostGather(shm_name, world, rank, cfg["utts"], est, create=True)
         barrier()

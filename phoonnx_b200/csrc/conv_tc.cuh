@@ -845,7 +845,7 @@ static inline bool conv_tc_supported(const ConvArgs& a) {
     return true;
 }
 
-static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
+static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     int mn = a.toff[0], mx = a.toff[0];
     for (int i = 1; i < a.ntaps; i++) { mn = a.toff[i] < mn ? a.toff[i] : mn; mx = a.toff[i] > mx ? a.toff[i] : mx; }
     c.min_off = mn;
@@ -861,6 +861,17 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
     const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4 + 256 * 4;      // transpose buffers + this N tile's bias
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
     if (!nt) for (int cand = 256; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { nt = cand; break; }
+    // latency mode (round 2): what TTSVoice sends is ONE utterance per call (voice.py:350-351) -- a single 128-row tile, so a
+    // launch was 1-3 CTAs streaming the whole weight matrix through one SM each (C1: 1.27 ms of a 2.03 ms call on the text side,
+    // profiles/r02e_bench_C1.json).  With fewer CTAs than half the SMs the output columns are spread over more, narrower N tiles:
+    // same K order per output (bit-identical results), 1/8 of the weights per CTA.
+    if (num_sms > 0 && a.ntiles > 0)
+        while (nt > 32 && (long)a.ntiles * (a.npad16 / nt) * 2 <= (long)num_sms) {
+            int next = 0;
+            for (int cand = nt - 16; cand >= 32; cand -= 16) if (a.npad16 % cand == 0) { next = cand; break; }
+            if (!next) break;
+            nt = next;
+        }
     for (;;) {
         c.ntile = nt;
         c.slot_bytes = c.piece_ch * nt * 2;
@@ -902,7 +913,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c) {
 
 static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStream_t st, bool cluster_ok = false) {
     TcCfg c;
-    if (!conv_tc_plan(a, c)) return cudaErrorInvalidConfiguration;
+    if (!conv_tc_plan(a, c, num_sms)) return cudaErrorInvalidConfiguration;
     // epilogue variant (compile-time in the kernel)
     typedef void (*KFn)(const ConvArgs, const TcCfg);
     const bool anyacc = a.accumulate || (a.epi == EPI_SPLIT && a.accumulate2);

@@ -330,6 +330,16 @@ int launch_ln(vits_handle* h, const float* in, float* out, const LnP& ln, int ro
               const DdsP* dw, const Tiles& T) {
     if (C % 32 || C > 32 * LN_MAXV) return fail(h, VITS_E_INVALID, "LayerNorm width %d unsupported (multiple of 32, <= %d)", C, 32 * LN_MAXV);
     if (rows == 0) return 0;
+    if (C % 64 == 0 && C <= 256 && (mode != 1 || h->A.dp_kernel == 3) && h->opts["ln_scalar"] == 0) {
+        // 64-bit accesses (kernels_f32.cuh k_layernorm_v2); every exported voice's widths (192, 256) qualify, x_low's 96 does not
+#define LN2_LAUNCH(N_) k_layernorm_v2<N_><<<(rows + 3) / 4, 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, mode, dw ? dw->dw_w : nullptr, \
+                           dw ? dw->dw_b : nullptr, dw ? dw->dil : 1, ptr<int2>(h->rowpos))
+        switch (C / 64) { case 1: LN2_LAUNCH(1); break; case 2: LN2_LAUNCH(2); break; case 3: LN2_LAUNCH(3); break; default: LN2_LAUNCH(4); break; }
+#undef LN2_LAUNCH
+        h->launches++;
+        CK(h, cudaGetLastError());
+        return 0;
+    }
     const int rpw = h->opts.count("ln_rpw") ? (int)h->opts["ln_rpw"] : 1;
 #define LN_LAUNCH(R_) k_layernorm<R_><<<(rows + 4 * R_ - 1) / (4 * R_), 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, C, mode, \
                           dw ? dw->dw_w : nullptr, dw ? dw->dw_b : nullptr, h->A.dp_kernel, dw ? dw->dil : 1, ptr<int2>(h->rowpos))

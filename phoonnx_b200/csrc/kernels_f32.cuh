@@ -358,6 +358,68 @@ __global__ void __launch_bounds__(128, 10) k_layernorm(const float* __restrict__
     }
 }
 
+// 64-bit accesses (round 2): C = 64 * NV2, lane l owns channels 64 m + 2 l + {0, 1}.  The ncu pass over the benched shape put the
+// scalar kernel above at 2.8 TB/s = 0.43 of the measured HBM peak (profiles/r02f_membound.txt) -- half the load / store instructions
+// for the same bytes.  Same arithmetic per element; the reduction order over lanes differs (fp32 re-association only).
+template <int NV2>
+__global__ void __launch_bounds__(128, 8) k_layernorm_v2(const float* __restrict__ in, float* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int rows, int mode, const float* __restrict__ dw_w,
+                                                        const float* __restrict__ dw_b, int dw_dil, const int2* __restrict__ rowpos) {
+    constexpr int C = 64 * NV2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + warp;
+    if (row >= rows) return;
+    float2 v[NV2], prev[NV2];
+    const float2* pc = reinterpret_cast<const float2*>(in + (long)row * C) + lane;
+    if (mode == 1) {
+        // depthwise k = 3 (modules.py:121-123) with zero padding at utterance edges; all three taps' loads before the first FMA
+        const int2 rp = __ldg(rowpos + row);
+        const bool vl = rp.x - dw_dil >= 0, vr = rp.x + dw_dil < rp.y;
+        const float2* pl = reinterpret_cast<const float2*>(in + (long)(vl ? row - dw_dil : row) * C) + lane;
+        const float2* pr = reinterpret_cast<const float2*>(in + (long)(vr ? row + dw_dil : row) * C) + lane;
+        float2 xl[NV2], xc[NV2], xr[NV2];
+#pragma unroll
+        for (int m = 0; m < NV2; m++) { xl[m] = pl[32 * m]; xc[m] = pc[32 * m]; xr[m] = pr[32 * m]; }
+#pragma unroll
+        for (int m = 0; m < NV2; m++) {
+            const int c2 = 32 * m + lane;
+            const float2 w0 = __ldg(reinterpret_cast<const float2*>(dw_w) + c2), w1 = __ldg(reinterpret_cast<const float2*>(dw_w + C) + c2),
+                         w2 = __ldg(reinterpret_cast<const float2*>(dw_w + 2 * C) + c2);
+            float2 acc = __ldg(reinterpret_cast<const float2*>(dw_b) + c2);
+            if (vl) { acc.x = fmaf(w0.x, xl[m].x, acc.x); acc.y = fmaf(w0.y, xl[m].y, acc.y); }
+            acc.x = fmaf(w1.x, xc[m].x, acc.x); acc.y = fmaf(w1.y, xc[m].y, acc.y);
+            if (vr) { acc.x = fmaf(w2.x, xr[m].x, acc.x); acc.y = fmaf(w2.y, xr[m].y, acc.y); }
+            v[m] = acc;
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < NV2; m++) {
+            v[m] = pc[32 * m];
+            if (mode == 2) prev[m] = reinterpret_cast<const float2*>(out + (long)row * C)[32 * m + lane];
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int m = 0; m < NV2; m++) s += v[m].x + v[m].y;
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int m = 0; m < NV2; m++) { const float dx = v[m].x - mean, dy = v[m].y - mean; q = fmaf(dx, dx, q); q = fmaf(dy, dy, q); }
+    q = warp_sum(q);
+    const float rstd = 1.f / sqrtf(q / (float)C + 1e-5f);
+#pragma unroll
+    for (int m = 0; m < NV2; m++) {
+        const int c2 = 32 * m + lane;
+        const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma) + c2), bt = __ldg(reinterpret_cast<const float2*>(beta) + c2);
+        float2 y = make_float2((v[m].x - mean) * rstd * gm.x + bt.x, (v[m].y - mean) * rstd * gm.y + bt.y);
+        if (mode != 0) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); }
+        if (mode == 2) { y.x += prev[m].x; y.y += prev[m].y; }
+        reinterpret_cast<float2*>(out + (long)row * C)[c2] = y;
+    }
+}
+
 // x[t, c] += tab[idx[b]][c]   (DurationPredictor speaker conditioning, models.py:153-155)
 __global__ void k_add_rowbias(float* __restrict__ x, const float* __restrict__ tab, const int* __restrict__ idx,
                               const int* __restrict__ cu, int B, int rows, int C) {

@@ -81,3 +81,55 @@ def test_plan_partitions_and_balances(world):
             assert int(lengths[b].sum()) <= 32768
     assert (seen == 1).all()
     assert (max(loads) - min(loads)) / max(loads) < 0.04
+
+
+def _gather_worker(rank, world, name, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rs = np.random.RandomState(2)
+    n_utts, hop = 200, 256
+    lengths = rs.randint(64, 257, size=(n_utts,)).astype(np.int64)
+    frames_of = lambda g: 1 + (int(lengths[g]) * 7 + 3 * g) % 11            # "durations": any deterministic function both ranks agree on
+    g = bench.HostGather(name, world, rank, n_utts, 1 << 22, create=False)
+    try:
+        for step in (1, 2):
+            results = []
+            for bidx in scheduler.plan(lengths, world, rank, max_ids=4096):
+                alen = np.asarray([frames_of(int(i)) * hop for i in bidx], np.int64)
+                audio = np.concatenate([np.full((int(n),), float(i) + 0.5 * step, np.float32) for i, n in zip(bidx, alen)])
+                results.append((bidx, audio, alen))
+            total = g.gather(step, hop, results)
+        if rank == 0:
+            offs = np.concatenate([[0], np.cumsum([frames_of(i) * hop for i in range(n_utts)])])
+            ok = total == int(offs[-1]) and all((g.audio[offs[i]:offs[i + 1]] == float(i) + 1.0).all() for i in range(n_utts))
+            q.put(("ok", bool(ok), total))
+        else:
+            q.put(("done", True, total))
+    finally:
+        g.close(False)
+
+
+def test_host_gather_two_ranks_original_order():
+    """bench.py --scaling strong ("only the host gathers the audio"): two processes place their shards' audio into
+    ONE shared host buffer in original utterance order, hand-shaking through flags in the same segment -- no collective."""
+    import multiprocessing as mp
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    name = f"vits_test_gather_{os.getpid()}"
+    owner = bench.HostGather(name, 2, 0, 200, 1 << 22, create=True)
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        ps = [ctx.Process(target=_gather_worker, args=(r, 2, name, q)) for r in range(2)]
+        for p in ps:
+            p.start()
+        got = [q.get(timeout=120) for _ in ps]
+        for p in ps:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert sorted(x[0] for x in got) == ["done", "ok"] and all(x[1] for x in got)
+        assert got[0][2] == got[1][2] > 0
+    finally:
+        owner.close(True)

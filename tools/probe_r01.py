@@ -58,6 +58,12 @@ def timeline(sess, stage, arch):
         base = ev[0][0]
         for t, nm in ev:
             print(f"   {t - base:8d}  {nm}")
+    # one merged, absolute listing of three consecutive tiles: the hand-over between tiles is where the single-tile views are blind
+    ev = sorted((int(st[it, s]) - int(t0), f"[{it}] " + names.get(s, str(s))) for it in (3, 4, 5) for s in range(48) if st[it, s])
+    print("merged tiles 3-5 (absolute cycles since tile 0's first stamp):")
+    for t, nm in ev:
+        if nm[4] in "ME":
+            print(f"   {t:8d}  {nm}")
     starts = st[:, 0]
     print("tile period (E top to E top):", np.diff(starts[starts > 0])[:20])
     eng.set_option("mrf_dbg", 0)
