@@ -58,6 +58,9 @@ struct TcCfg {
     int nabuf;        // activation tile buffers (1 or 2)
     int naccbuf;      // TMEM accumulator buffers (1 or 2)
     int epi_off;      // byte offset of the epilogue transpose buffers (4 warps x 32 x TC_EPI_PITCH floats)
+    int nepi;         // epilogue warps: 8, or 12 when the loader is the cp.async one (bf16 operand rows: 2 loader warps suffice)
+    int nload;        // loader warps = 14 - nepi
+    int gw;           // accumulator columns per epilogue work item (32, or 16 when that spreads the items better over the warps)
     int cluster;      // 2: CTA pairs (cluster 2x1x1) share every weight piece -- each CTA fetches every other piece and multicasts it to both
                       //    (the ring-mode launches are bound by L2 -> SM weight traffic: a 128-row tile re-streams all taps); 1: off
 };
@@ -314,9 +317,10 @@ template <int EPI, int RESK, int ACC>
 __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, uint8_t* smem, uint32_t tmem_base,
                                             uint32_t bar_accfull0, uint32_t bar_accempty0, int warp, int lane, bool dbg_on) {
     const int q = warp & 3, hh = warp >> 2, ny = blockIdx.y;
+    const int nhh = c.nepi >> 2;                       // warps per TMEM lane quadrant: they take the column groups round-robin
     float* sE = reinterpret_cast<float*>(smem + c.epi_off) + warp * (32 * TC_EPI_PITCH);
     float* srow = sE + lane * TC_EPI_PITCH;
-    const int ngroups = (c.ntile + 31) >> 5;
+    const int ngroups = (c.ntile + c.gw - 1) / c.gw;
     const float inv_div = 1.f / a.out_div;
     constexpr bool has_res = (RESK == 1), has_resb = (RESK == 2 || RESK == 3);
     constexpr int NRB = (RESK == 3) ? 3 : 1;          // bf16 residual row groups summed (RESK 3: up to three, a.nresb)
@@ -325,7 +329,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     const bool scaled = a.out_div != 1.f;
     // gate outputs straight to bf16 operand rows (lrelu slope 1 = identity; 16-byte aligned rows)
     const bool gate_direct = (EPI == EPI_GATE) && a.outb != nullptr && a.outb_slope == 1.f && (a.ldo % 8 == 0) && (a.ocol % 8 == 0);
-    const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);   // this N tile's bias
+    const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + c.nepi * (32 * TC_EPI_PITCH);   // this N tile's bias
     uint32_t it = 0;
     int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
@@ -346,11 +350,11 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
         long long ph1 = 0, ph2 = 0, tq = 0, ph1a = 0, ph1b = 0;
         if (nrows > 0) {                                  // warp-uniform
-            for (int g = hh; g < ngroups; g += 2) {
+            for (int g = hh; g < ngroups; g += nhh) {
                 if (dbg_on) tq = clock64();
-                const int n0 = g * 32;
-                const int ng = ny * c.ntile + n0;         // global accumulator column of this 32-wide group
-                const int ncols = min(32, c.ntile - n0);  // 16 or 32
+                const int n0 = g * c.gw;
+                const int ng = ny * c.ntile + n0;         // global accumulator column of this group
+                const int ncols = min(c.gw, c.ntile - n0);  // 16 or 32
                 // phase-2 mapping: `lpr` lanes cover one staged row (128-bit each), 32 / lpr rows per warp instruction
                 const int ocols = (EPI == EPI_GATE) ? (ncols >> 1) : ncols;      // 8, 16 or 32 staged output columns
                 const int og = (EPI == EPI_GATE) ? (ng >> 1) : ng;               // first output column
@@ -518,6 +522,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
 __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCfg& c, uint32_t tmem_base, uint32_t bar_accfull0,
                                                    uint32_t bar_accempty0, int warp, int lane) {
     const int q = warp & 3, hh = warp >> 2, ny = blockIdx.y;
+    const int nhh = c.nepi >> 2;
     const int ngroups = (c.ntile + 15) >> 4;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
@@ -529,7 +534,7 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
         tc::tc_fence_after();
         const int t = t0 + q * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * (uint32_t)c.ntile;
-        for (int g = hh; g < ngroups; g += 2) {
+        for (int g = hh; g < ngroups; g += nhh) {
             float v[16];
             tc::tmem_ld16(trow + (uint32_t)(g * 16), v);
             if (t < len) {
@@ -577,21 +582,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     const int ny = blockIdx.y;
     const bool dbg_on_cta = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     const bool dbg_on = dbg_on_cta && lane == 0 &&
-                        (warp == 0 || warp == TC_EPI_WARPS || warp >= TC_EPI_WARPS + TC_LOAD_WARPS);
+                        (warp == 0 || warp == c.nepi || warp >= TC_EPI_WARPS + TC_LOAD_WARPS);
     if (dbg_on && warp == 0) a.dbg[15] = (unsigned long long)clock64();
 
     if (tid == 0) {
         for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, (uint32_t)c.cluster); }
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(bar_afull0 + 8u * i, TC_LOAD_THREADS);
+            tc::mbar_init(bar_afull0 + 8u * i, (uint32_t)c.nload * 32u);
             tc::mbar_init(bar_aempty0 + 8u * i, 1);
             tc::mbar_init(bar_accfull0 + 8u * i, 1);
-            tc::mbar_init(bar_accempty0 + 8u * i, TC_EPI_WARPS * 32);
+            tc::mbar_init(bar_accempty0 + 8u * i, (uint32_t)c.nepi * 32u);
         }
         tc::fence_mbar_init();
     }
     {
-        float* sBias = reinterpret_cast<float*>(smem + c.epi_off) + TC_EPI_WARPS * (32 * TC_EPI_PITCH);
+        float* sBias = reinterpret_cast<float*>(smem + c.epi_off) + c.nepi * (32 * TC_EPI_PITCH);
         for (int i = tid; i < c.ntile; i += TC_THREADS) sBias[i] = a.bias ? __ldg(a.bias + ny * c.ntile + i) : 0.f;
     }
     if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) tc::tmem_alloc(tc::smem_u32(tmem_slot), (uint32_t)c.tmem_cols);
@@ -613,16 +618,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     const uint32_t lbo_a = (uint32_t)c.rows_a * 16u;
     const uint32_t lbo_b = (uint32_t)c.ntile * 16u;
 
-    if (warp < TC_EPI_WARPS) {
-        // ================= epilogue (256 threads) =================
+    if (warp < c.nepi) {
+        // ================= epilogue (8 warps; 12 when the loader is the cp.async one) =================
         if constexpr (EPI < 0) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
         else tc_epilogue<EPI, RESK, ACC>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
     } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
-        // ================= activation loaders (192 threads) =================
-        const int lt = tid - TC_EPI_WARPS * 32;
+        // ================= activation loaders (the warps between the epilogue warps and warp 14) =================
+        const int lt = tid - c.nepi * 32;
+        const int nlt = c.nload * 32;                   // loader threads
         uint32_t it = 0;
         const int items = c.rows_a * kc_total;
-        const int dr = TC_LOAD_THREADS / kc_total, dk = TC_LOAD_THREADS - dr * kc_total;   // advance of (r, kc) per TC_LOAD_THREADS items
+        const int dr = nlt / kc_total, dk = nlt - dr * kc_total;   // advance of (r, kc) per nlt items
         int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
         const int lr0 = lt / kc_total, lk0 = lt - lr0 * kc_total;          // this thread's first (row, chunk) item
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                 const __nv_bfloat16* xbb = a.xb + (row0 + t0 + c.min_off) * (long)a.ldxb + a.xcol + ks * a.cin;
                 const uint32_t dA = tc::smem_u32(dstA);
                 int r2 = lr0, kc2 = lk0;
-                for (int i = lt; i < items; i += TC_LOAD_THREADS) {
+                for (int i = lt; i < items; i += nlt) {
                     const bool okr = (r2 >= tlo) && (r2 < thi);
                     const __nv_bfloat16* src = xbb + (okr ? (long)r2 * a.ldxb : 0) + kc2 * 8;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dA + (uint32_t)(kc2 * c.rows_a + r2) * 16u), "l"(okr ? src : a.xb), "r"(okr ? 16u : 0u) : "memory");
@@ -661,14 +667,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             // 16-byte (8-channel) chunks, kc fastest so global reads are contiguous; TC_LOAD_BATCH items (2 x LDG.128 each) in
             // flight per thread before any conversion so the load latency is paid once per batch
             int r = lr0, kc = lk0;
-            for (int base = lt; base < items; base += TC_LOAD_BATCH * TC_LOAD_THREADS) {
+            for (int base = lt; base < items; base += TC_LOAD_BATCH * nlt) {
                 float4 v0[TC_LOAD_BATCH], v1[TC_LOAD_BATCH];
                 int rr[TC_LOAD_BATCH], kk[TC_LOAD_BATCH];
                 bool ok[TC_LOAD_BATCH];
 #pragma unroll
                 for (int u = 0; u < TC_LOAD_BATCH; u++) {
                     rr[u] = r; kk[u] = kc;
-                    ok[u] = (base + u * TC_LOAD_THREADS < items);
+                    ok[u] = (base + u * nlt < items);
                     v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
                     if (ok[u] && r >= tlo && r < thi) {
                         const float4* src = reinterpret_cast<const float4*>(xbase + (long)r * a.ldx + kc * 8);
@@ -845,6 +851,10 @@ static inline bool conv_tc_supported(const ConvArgs& a) {
     return true;
 }
 
+// Epilogue warps when the loader is the cp.async one.  12 (two loader warps) was measured NEUTRAL to slightly worse against 8
+// (profiles/r02m_ab_conv_nepi.log: medium decoder 181-185 vs 184-186 ms, flow 53.5 vs 56 ms, `high` 203.5 vs 206.3 ms): the
+// epilogue is not short of warps -- the small-channel launches move ~1.3 GB per conv and sit at 50-67 % of HBM bandwidth.
+static int g_tc_nepi_xb = 8;         // engine option "conv_nepi" (8 or 12), process-wide
 static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     int mn = a.toff[0], mx = a.toff[0];
     for (int i = 1; i < a.ntaps; i++) { mn = a.toff[i] < mn ? a.toff[i] : mn; mx = a.toff[i] > mx ? a.toff[i] : mx; }
@@ -858,7 +868,11 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     c.cpt = (a.cin + c.piece_ch - 1) / c.piece_ch;
     c.npieces = (a.ntaps_ks[0] ? a.ntaps : a.ntaps * (a.nks > 0 ? a.nks : 1)) * nseg * c.cpt;
     const int limit = 222 * 1024;
-    const int epi_bytes = TC_EPI_WARPS * 32 * TC_EPI_PITCH * 4 + 256 * 4;      // transpose buffers + this N tile's bias
+    // epilogue-bound launches (every conv of <= 256 channels, r01/r02 timelines) get 12 epilogue warps when the activations arrive as
+    // bf16 operand rows: the cp.async loader needs two warps, not six
+    c.nepi = (a.xb && !a.split3) ? g_tc_nepi_xb : TC_EPI_WARPS;
+    c.nload = TC_EPI_WARPS + TC_LOAD_WARPS - c.nepi;
+    const int epi_bytes = c.nepi * 32 * TC_EPI_PITCH * 4 + 256 * 4;      // transpose buffers + this N tile's bias
     int nt = a.npad16 <= 256 ? a.npad16 : 0;
     if (!nt) for (int cand = 256; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { nt = cand; break; }
     // latency mode (round 2): what TTSVoice sends is ONE utterance per call (voice.py:350-351) -- a single 128-row tile, so a
@@ -901,6 +915,11 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
         for (int cand = nt - 16; cand >= 16; cand -= 16) if (a.npad16 % cand == 0) { next = cand; break; }
         if (!next) return false;
         nt = next;
+    }
+    {   // column-group width of the epilogue: the one that leaves the busiest warp of a quadrant the fewest columns (32 on ties)
+        const int nhh = c.nepi / 4;
+        auto busiest = [&](int gw) { const int groups = (c.ntile + gw - 1) / gw; return ((groups + nhh - 1) / nhh) * gw; };
+        c.gw = busiest(16) < busiest(32) ? 16 : 32;
     }
     c.naccbuf = (2 * c.ntile <= 512) ? 2 : 1;
     int tc_cols = 32; while (tc_cols < c.naccbuf * c.ntile) tc_cols <<= 1;

@@ -503,6 +503,9 @@ int vits_set_option(vits_handle* h, const char* key, double value) {
     } else if (k == "num_sms") {
         if (value < 1) return fail(h, VITS_E_INVALID, "num_sms must be >= 1");
         h->num_sms = (int)value;                 // test hook: persistent grids use this many CTAs
+    } else if (k == "conv_nepi") {
+        if (value != 8 && value != 12) return fail(h, VITS_E_INVALID, "conv_nepi must be 8 or 12");
+        g_tc_nepi_xb = (int)value;               // experiment switch of conv_tc.cuh (process-wide)
     } else if (k == "max_chunk_frames") {
         if (value < 1) return fail(h, VITS_E_INVALID, "max_chunk_frames must be >= 1");
         h->max_chunk_frames = (int64_t)value;
