@@ -69,12 +69,22 @@ typedef struct vits_info {
     int32_t resblock_type, use_sdp;
     int32_t precision;                         /* 0 fp32 CUDA cores, 1 bf16 tcgen05                                      */
     int32_t device, num_sms, finalized;
-    int32_t reserved[8];
+    int32_t has_scales, has_langid;            /* inputs the voice's own graph declares (voice.py:358, :369); vits_create handles: 1, 0 */
+    int32_t reserved[6];
 } vits_info;
 int vits_describe(vits_handle* h, vits_info* info);
 
-/* Replaces InferenceSession(...) construction (voice.py:167-171): binds device `device_id`,
- * creates the stream and an empty weight table. */
+/* Replaces InferenceSession(str(model_path), ...) (voice.py:167-171) in ONE call: opens a voice file written by
+ * phoonnx_train/export_onnx.py (plain or gzip-compressed .onnx), recovers the architecture from its tensors (the file carries no
+ * hyper-parameters), packs the kernel layouts, uploads them to device `device_id` and finalizes the handle -- no host-language
+ * helper involved (csrc/voice_file.h; pinned blob for blob against the Python loader by tests/test_native_loader.py).
+ * precision: 0 fp32 CUDA cores (parity), 1 bf16 tcgen05.  On failure *out is NULL and, when `err` is given, a message of at most
+ * err_cap bytes explains why (bad file -> VITS_E_INVALID, no sm_100 device -> VITS_E_CUDA). */
+int vits_open(const char* path, int device_id, int precision, vits_handle** out, char* err, size_t err_cap);
+
+/* Lower-level construction for hosts that parse and pack the file themselves (phoonnx_b200/weights.py + packing.py do, for
+ * checkpoints and state dicts): binds device `device_id`, creates the stream and an empty weight table; then vits_upload per
+ * blob, vits_set_option, vits_finalize. */
 int vits_create(const vits_arch* arch, int device_id, vits_handle** out);
 
 /* Upload one packed weight blob (already in kernel layout; packing is done by the

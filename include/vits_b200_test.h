@@ -24,6 +24,12 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
 int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
                         double* total_cycles);
 
+/* Test hooks of the native voice loader (no GPU needed): the architecture vits_open would infer from `path`, and one packed blob
+ * by name (bytes copied to `out` when it fits; returns its size in bytes, or a negative VITS_E_*; *dtype as in vits_upload).
+ * name == NULL: returns the number of blobs; name "#<i>": copies the i-th blob's NAME into `out` instead. */
+int vits_test_file_arch(const char* path, vits_arch* arch, char* err, size_t err_cap);
+int64_t vits_test_file_blob(const char* path, const char* name, void* out, int64_t cap, int* dtype);
+
 #ifdef __cplusplus
 }
 #endif

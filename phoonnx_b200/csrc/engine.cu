@@ -16,6 +16,7 @@
 #include "conv_tc.cuh"
 #include "mrf3_tc.cuh"
 #include "probe_tc.cuh"
+#include "voice_file.h"
 
 #include <algorithm>
 #include <cmath>
@@ -96,6 +97,7 @@ struct vits_handle {
     int last_chunk_frames = 0;
     int last_nchunks = 0;             // chunks of the last vits_decode (chunk tensors can only be fetched when it was one)
     cudaStream_t own_stream = nullptr;   // the stream vits_create made (h->stream is this one unless vits_set_stream gave another)
+    int graph_has_scales = 1, graph_has_langid = 0;   // inputs the file's graph declares (vits_open)
     int64_t ticket = 0;               // number of vits_decode calls that produced host output so far
     int64_t ticket_of[2] = {0, 0};    // ticket whose transfer ev_out[i] tracks
 
@@ -476,6 +478,74 @@ int vits_create(const vits_arch* arch, int device_id, vits_handle** out) {
     for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
     *out = h;
     return VITS_OK;
+}
+
+int vits_open(const char* path, int device_id, int precision, vits_handle** out, char* err, size_t err_cap) {
+    auto say = [&](const std::string& m) { if (err && err_cap) { snprintf(err, err_cap, "%s", m.c_str()); } };
+    if (out) *out = nullptr;
+    if (!path || !out || (precision != 0 && precision != 1)) { say("vits_open: null argument or precision not 0/1"); return VITS_E_INVALID; }
+    vf::Voice v;
+    std::string e;
+    if (!vf::load_voice(path, v, e)) { say(e); return VITS_E_INVALID; }
+    vits_handle* h = nullptr;
+    int rc = vits_create(&v.arch, device_id, &h);
+    if (rc != VITS_OK) { say("vits_open: no usable sm_100 CUDA device (this engine has no CPU fallback)"); return rc; }
+    for (auto& kv : v.blobs)
+        if ((rc = vits_upload(h, kv.first.c_str(), kv.second.bytes.data(), kv.second.bytes.size(), kv.second.dtype)) != VITS_OK) break;
+    for (auto& kv : v.opts) if (rc == VITS_OK) rc = vits_set_option(h, kv.first.c_str(), kv.second);
+    if (rc == VITS_OK) rc = vits_set_option(h, "precision", (double)precision);
+    if (rc == VITS_OK) rc = vits_finalize(h);
+    if (rc != VITS_OK) { say(h->err); vits_destroy(h); return rc; }
+    auto has = [&](const char* n) { return std::find(v.model.inputs.begin(), v.model.inputs.end(), n) != v.model.inputs.end(); };
+    h->graph_has_scales = has("scales") ? 1 : 0; h->graph_has_langid = has("langid") ? 1 : 0;
+    *out = h;
+    return VITS_OK;
+}
+
+int vits_test_file_arch(const char* path, vits_arch* arch, char* err, size_t err_cap) {
+    if (!path || !arch) return VITS_E_INVALID;
+    vf::Voice v;
+    std::string e;
+    if (!vf::load_voice(path, v, e, false)) { if (err && err_cap) snprintf(err, err_cap, "%s", e.c_str()); return VITS_E_INVALID; }
+    *arch = v.arch;
+    return VITS_OK;
+}
+
+int64_t vits_test_file_blob(const char* path, const char* name, void* out, int64_t cap, int* dtype) {
+    static std::string cached_path;                      // the tests walk every blob of one file: parse and pack it once
+    static vf::Voice cached;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!path) return VITS_E_INVALID;
+    if (cached_path != path) {
+        cached = vf::Voice();
+        std::string e;
+        cached_path.clear();
+        if (!vf::load_voice(path, cached, e)) return VITS_E_INVALID;
+        cached_path = path;
+    }
+    if (!name) return (int64_t)(cached.blobs.size() + cached.opts.size());
+    if (name[0] == '#') {
+        int64_t i = atoll(name + 1);
+        std::string nm;
+        if (i < (int64_t)cached.blobs.size()) { auto it = cached.blobs.begin(); std::advance(it, i); nm = it->first; }
+        else if (i < (int64_t)(cached.blobs.size() + cached.opts.size())) { auto it = cached.opts.begin(); std::advance(it, i - (int64_t)cached.blobs.size()); nm = "opt:" + it->first; }
+        else return VITS_E_INVALID;
+        if (out && cap > (int64_t)nm.size()) memcpy(out, nm.c_str(), nm.size() + 1);
+        return (int64_t)nm.size();
+    }
+    if (!strncmp(name, "opt:", 4)) {
+        auto it = cached.opts.find(name + 4);
+        if (it == cached.opts.end()) return VITS_E_INVALID;
+        if (out && cap >= 8) memcpy(out, &it->second, 8);
+        if (dtype) *dtype = 3;
+        return 8;
+    }
+    auto it = cached.blobs.find(name);
+    if (it == cached.blobs.end()) return VITS_E_INVALID;
+    if (dtype) *dtype = it->second.dtype;
+    if (out && cap >= (int64_t)it->second.bytes.size()) memcpy(out, it->second.bytes.data(), it->second.bytes.size());
+    return (int64_t)it->second.bytes.size();
 }
 
 int vits_upload(vits_handle* h, const char* name, const void* data, size_t nbytes, int dtype) {
@@ -1400,6 +1470,7 @@ int vits_describe(vits_handle* h, vits_info* info) {
     info->hidden = A.hidden; info->inter = A.inter; info->sample_rate = A.sample_rate; info->hop = hop;
     info->resblock_type = A.resblock_type; info->use_sdp = A.use_sdp; info->precision = h->precision;
     info->device = h->device; info->num_sms = h->num_sms; info->finalized = h->finalized ? 1 : 0;
+    info->has_scales = h->graph_has_scales; info->has_langid = h->graph_has_langid;
     return VITS_OK;
 }
 

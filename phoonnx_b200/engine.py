@@ -41,8 +41,9 @@ class CArch(C.Structure):
 
 class CInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_speakers", "has_sid", "hidden", "inter", "sample_rate", "hop",
-                                         "resblock_type", "use_sdp", "precision", "device", "num_sms", "finalized")] + \
-               [("reserved", C.c_int32 * 8)]
+                                         "resblock_type", "use_sdp", "precision", "device", "num_sms", "finalized",
+                                         "has_scales", "has_langid")] + \
+               [("reserved", C.c_int32 * 6)]
 
 
 def to_c_arch(a: VitsArch) -> CArch:
@@ -91,6 +92,8 @@ def load_library(path: Optional[str] = None):
     H = C.c_void_p
     lib.vits_abi_version.restype = C.c_int
     lib.vits_create.argtypes = [C.POINTER(CArch), C.c_int, C.POINTER(H)]
+    lib.vits_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(H), C.c_char_p, C.c_size_t]
+    lib.vits_open.restype = C.c_int
     lib.vits_upload.argtypes = [H, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
     lib.vits_finalize.argtypes = [H]
     lib.vits_set_option.argtypes = [H, C.c_char_p, C.c_double]
@@ -133,10 +136,10 @@ EXPORTED_SYMBOLS = (
     "vits_abi_version", "vits_create", "vits_upload", "vits_finalize", "vits_set_option", "vits_prepare",
     "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_launch_count",
     "vits_last_error", "vits_destroy", "vits_host_alloc", "vits_host_free", "vits_wait_output",
-    "vits_describe", "vits_max_output_samples", "vits_set_stream", "vits_output_ticket", "vits_wait_ticket",
+    "vits_describe", "vits_max_output_samples", "vits_set_stream", "vits_output_ticket", "vits_wait_ticket", "vits_open",
 )
 # include/vits_b200_test.h: test-only hooks, not part of the drop-in boundary
-TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe")
+TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe", "vits_test_file_arch", "vits_test_file_blob")
 VITS_OUT_ASYNC = 0x100
 
 _DT = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.int32): 2}
@@ -235,6 +238,34 @@ class Engine:
         self._ylen = None
         self._pool = PinnedPool(self.lib)
         self.last_ticket = 0
+
+    @classmethod
+    def open(cls, path: str, device: int = 0, precision: str = "fp32") -> "Engine":
+        """The library opens the voice file by itself (vits_open: C++ reader, architecture inference and packing inside the
+        .so); this class then only needs what vits_describe reports."""
+        from .weights import VitsArch
+        lib = load_library()
+        self = cls.__new__(cls)
+        self.lib = lib
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib.vits_open(str(path).encode(), int(device), 0 if precision == "fp32" else 1, C.byref(self._h), err, 512)
+        if rc != 0 or not self._h:
+            self._h = C.c_void_p()
+            msg = err.value.decode("utf-8", "replace")
+            if rc == -1:
+                raise ValueError(msg)
+            raise RuntimeError(f"vits_open failed (code {rc}): {msg}")
+        self.precision = precision
+        self._B, self._ylen = 0, None
+        self._pool = PinnedPool(lib)
+        self.last_ticket = 0
+        info = self.describe()
+        self.info = info
+        self.hop = info["hop"]
+        self.arch = VitsArch(n_vocab=info["n_vocab"], hidden=info["hidden"], inter=info["inter"], n_speakers=info["n_speakers"],
+                             sample_rate=info["sample_rate"], use_sdp=bool(info["use_sdp"]), resblock=str(info["resblock_type"]))
+        return self
 
     # ------------------------------------------------------------------
     def _check(self, rc: int):

@@ -40,13 +40,24 @@ class B200Session:
 
     def __init__(self, path_or_bytes, sess_options=None, providers=None, provider_options=None, *,
                  device: int = 0, precision: str = "fp32", sample_rate: Optional[int] = None,
-                 max_chunk_frames: Optional[int] = None, seed: int = 0, default_scales=None):
+                 max_chunk_frames: Optional[int] = None, seed: int = 0, default_scales=None,
+                 native_loader: bool = False):
         self._path = str(path_or_bytes)
-        W, arch, hdr = load_model(self._path, sample_rate)
+        if native_loader:
+            # the library opens the file itself (vits_open); the Python loader is not involved
+            self.engine = Engine.open(self._path, device=device, precision=precision)
+            arch = self.engine.arch
+            if sample_rate:
+                arch.sample_rate = int(sample_rate)
+            info = self.engine.info
+            hdr = type("Hdr", (), {"metadata": {}, "inputs": ["input", "input_lengths"] + (["scales"] if info["has_scales"] else []) +
+                                   (["sid"] if info["has_sid"] else []) + (["langid"] if info["has_langid"] else [])})()
+        else:
+            W, arch, hdr = load_model(self._path, sample_rate)
+            blobs, opts = pack_model(W, arch)
+            self.engine = Engine(arch, blobs, opts, device=device, precision=precision)
         self.arch = arch
         self.metadata = dict(hdr.metadata)
-        blobs, opts = pack_model(W, arch)
-        self.engine = Engine(arch, blobs, opts, device=device, precision=precision)
         if max_chunk_frames:
             self.engine.set_option("max_chunk_frames", max_chunk_frames)
         # the inputs THIS file's graph declares, in its order (voice.py:347 reads exactly this list and filters its feed by it,

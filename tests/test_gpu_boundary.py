@@ -2,6 +2,7 @@
 asynchronous output with tickets, chunked int16 output, device-pointer output on a caller stream, the multi-chunk fetch guard,
 and phoonnx_b200.voice.synthesize_batch on a minimal stand-in voice object with the real engine underneath (the reference
 package is absent on the GPU box; its own TTSVoice is exercised on CPU in tests/test_voice_batch.py)."""
+import os
 import threading
 
 import numpy as np
@@ -246,3 +247,60 @@ def test_other_voice_formats_on_the_gpu(built_lib, tmp_path_factory):
     assert np.array_equal(out, ref)
     with pytest.raises(ValueError):
         alt.run(None, feed)                                          # `scales` is not an input of that graph
+
+
+def test_library_opens_a_voice_by_itself(built_lib, tmp_path_factory):
+    """vits_open (csrc/voice_file.h): the .so parses, infers and packs the exporter's file without any host-language helper --
+    the entry point SURVEY.md 8b sketched as vits_create(path, ...).  A session built on it synthesises bit for bit what the
+    Python-loader session does, for plain and gzip-compressed files, single- and multi-speaker, both precisions."""
+    import gzip
+    from phoonnx_b200.session import B200Session
+    for preset, ns in (("tiny", 1), ("tiny", 3), ("x_low", 1)):
+        p, arch = _voice_file(tmp_path_factory, preset, ns)
+        rs = np.random.RandomState(3)
+        f = _feeds(arch, rs, (4,))[0]
+        if ns > 1:
+            f["sid"] = (np.arange(4) % ns).astype(np.int64)
+        for prec in ("fp32", "bf16"):
+            want, wlen = B200Session(p, precision=prec, seed=11).synthesize_packed(f)
+            nat = B200Session(p, precision=prec, seed=11, native_loader=True)
+            assert [i.name for i in nat.get_inputs()] == ["input", "input_lengths", "scales"] + (["sid"] if ns > 1 else [])
+            got, glen = nat.synthesize_packed(f)
+            assert np.array_equal(wlen, glen) and np.array_equal(np.array(want), np.array(got)), (preset, ns, prec)
+        gz = p + ".gz"
+        with open(p, "rb") as src, gzip.open(gz, "wb") as dst:
+            dst.write(src.read())
+        got, _ = B200Session(gz, precision="bf16", seed=11, native_loader=True).synthesize_packed(f)
+        assert np.array_equal(np.array(want), np.array(got))
+    with pytest.raises(ValueError):
+        B200Session(str(tmp_path_factory.mktemp("x") / "missing.onnx"), native_loader=True)
+
+
+def test_plain_c_host_program(built_lib, tmp_path_factory):
+    """examples/synth.c: a complete host in C (gcc, no Python on its path) -- vits_open / vits_describe / vits_prepare /
+    vits_max_output_samples / vits_decode(int16) -- produces the PCM the Python session produces for the same ids and seed."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from phoonnx_b200.session import B200Session
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler on this box")
+    d = tmp_path_factory.mktemp("c_host")
+    exe = str(d / "synth")
+    libdir = os.path.dirname(built_lib)
+    r = subprocess.run(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "synth.c"), "-L" + libdir,
+                        "-lvits_b200", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p, arch = _voice_file(tmp_path_factory, "x_low", 1)
+    ids = [1, 0, 20, 0, 59, 0, 24, 0, 120, 0, 27, 0, 100, 0, 3, 0, 35, 0, 120, 0, 62, 0, 122, 0, 24, 0, 17, 0, 2]    # SURVEY 8c example
+    out = str(d / "out.pcm")
+    r = subprocess.run([exe, p, ",".join(map(str, ids)), out, "0", "1.0", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    pcm = np.fromfile(out, dtype=np.int16)
+    sess = B200Session(p, precision="bf16")
+    want, wlen = sess.synthesize_packed({"input": np.asarray([ids], np.int64), "input_lengths": np.array([len(ids)], np.int64),
+                                         "scales": np.array([0.0, 1.0, 0.0], np.float32)}, out="i16")
+    assert pcm.shape[0] == int(wlen[0]) and np.array_equal(pcm, np.array(want))
+    assert f"{len(ids)} ids" in r.stdout and f"{arch.sample_rate} Hz" in r.stdout
+    bad = subprocess.run([exe, p, "1,0,9999,2", out], capture_output=True, text=True)
+    assert bad.returncode == 1 and "outside" in bad.stderr                 # id >= n_vocab: VITS_E_INVALID with a message
