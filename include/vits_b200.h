@@ -158,6 +158,14 @@ int vits_set_stream(vits_handle* h, void* cuda_stream);
  * copy stream: with option "async_output" = 1, vits_decode(out_kind = 1) returns once the transfer is enqueued and
  * vits_wait_output() (or the second-next vits_decode on the same handle) completes it, so the transfer of one batch
  * overlaps the kernels of the next.  Without the option vits_decode() blocks until `out` is complete. */
+/* Scatter output: the NEXT vits_decode with a host output (out_kind 1 or 2) writes utterance b's samples at out + sample_offsets[b]
+ * instead of packing the utterances back to back -- one DMA per utterance, so the device's copy engine places every utterance
+ * where the caller wants it (original order of a larger job, a result buffer shared by several processes, ...).  One-shot; B must
+ * equal the prepared batch; capacity is checked per utterance.  vits_host_register page-locks memory the caller already owns
+ * (e.g. a POSIX shared-memory segment) so that those DMAs are asynchronous. */
+int vits_set_output_offsets(vits_handle* h, const int64_t* sample_offsets, int32_t B);
+int vits_host_register(void* p, size_t nbytes);
+int vits_host_unregister(void* p);
 int vits_host_alloc(size_t nbytes, void** out);
 int vits_host_free(void* p);
 int vits_wait_output(vits_handle* h, int older_only);   /* older_only: leave the most recent vits_decode's transfer in flight */

@@ -97,6 +97,7 @@ struct vits_handle {
     int last_chunk_frames = 0;
     int last_nchunks = 0;             // chunks of the last vits_decode (chunk tensors can only be fetched when it was one)
     cudaStream_t own_stream = nullptr;   // the stream vits_create made (h->stream is this one unless vits_set_stream gave another)
+    std::vector<int64_t> out_offsets;   // one-shot per-utterance destination offsets of the next host-output vits_decode (vits_set_output_offsets)
     int graph_has_scales = 1, graph_has_langid = 0;   // inputs the file's graph declares (vits_open)
     int64_t ticket = 0;               // number of vits_decode calls that produced host output so far
     int64_t ticket_of[2] = {0, 0};    // ticket whose transfer ev_out[i] tracks
@@ -931,6 +932,18 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
     const bool async_flag = (out_kind & VITS_OUT_ASYNC) != 0;
     out_kind &= ~VITS_OUT_ASYNC;
     if (out_kind < 0 || out_kind > 3) return fail(h, VITS_E_INVALID, "out_kind %d", out_kind);
+    std::vector<int64_t> offs;                           // consumed by this call whatever happens next
+    offs.swap(h->out_offsets);
+    const bool scatter = !offs.empty();
+    if (scatter) {
+        if (out_kind != 1 && out_kind != 2) return fail(h, VITS_E_INVALID, "output offsets apply to host outputs (out_kind 1 or 2)");
+        if ((int)offs.size() != B) return fail(h, VITS_E_INVALID, "output offsets given for %d utterances, the prepared batch has %d", (int)offs.size(), B);
+        if (!out) return fail(h, VITS_E_INVALID, "null output buffer");
+        for (int b = 0; b < B; b++)
+            if (offs[b] < 0 || offs[b] + (int64_t)h->h_ylen[b] * hop > out_capacity)
+                return fail(h, VITS_E_INVALID, "utterance %d: offset %lld + %lld samples exceeds the output capacity %lld", b, (long long)offs[b],
+                            (long long)h->h_ylen[b] * hop, (long long)out_capacity);
+    } else
     if (out_kind != 0 && (!out || out_capacity < total_samples)) return fail(h, VITS_E_INVALID, "output buffer too small: %lld < %lld samples", (long long)out_capacity, (long long)total_samples);
     if (noise_z) for (int b = 0; b < B; b++) if (z_stride < h->h_ylen[b]) return fail(h, VITS_E_INVALID, "noise_z stride %lld < frames %d of utterance %d", (long long)z_stride, h->h_ylen[b], b);
     CK(h, cudaSetDevice(h->device));
@@ -1304,7 +1317,15 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             // this chunk's audio leaves on the copy stream while the next chunk computes
             CK(h, cudaEventRecord(h->ev_chunk, st));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_chunk, 0));
-            if (out_kind == 1)
+            if (scatter) {
+                // every utterance of the chunk straight to ITS place in the caller's buffer (e.g. a job-wide result buffer shared by
+                // several processes, in original utterance order): the DMA engine does the gather, no host memcpy afterwards
+                for (int b = b_lo; b < b_hi; b++) {
+                    const int64_t s0 = (int64_t)h->h_cu_y[b] * hop, ns = (int64_t)h->h_ylen[b] * hop;
+                    if (out_kind == 1) CK(h, cudaMemcpyAsync(static_cast<float*>(out) + offs[b], audio + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+                    else CK(h, cudaMemcpyAsync(static_cast<int16_t*>(out) + offs[b], audio16 + s0, (size_t)ns * 2, cudaMemcpyDeviceToHost, h->copy_stream));
+                }
+            } else if (out_kind == 1)
                 CK(h, cudaMemcpyAsync(static_cast<float*>(out) + (int64_t)f_lo * hop, audio + (int64_t)f_lo * hop, (size_t)Fr * hop * 4,
                                       cudaMemcpyDeviceToHost, h->copy_stream));
             else
@@ -1523,6 +1544,25 @@ int vits_wait_output(vits_handle* h, int older_only) {
         if (older_only && i == h->audio_sel) continue;      // the most recent vits_decode keeps running
         if (h->out_pending[i]) { CK(h, cudaEventSynchronize(h->ev_out[i])); h->out_pending[i] = false; }
     }
+    return VITS_OK;
+}
+
+int vits_set_output_offsets(vits_handle* h, const int64_t* sample_offsets, int32_t B) {
+    if (!h || B < 0 || (B > 0 && !sample_offsets)) return VITS_E_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->out_offsets.assign(sample_offsets, sample_offsets + B);
+    return VITS_OK;
+}
+
+int vits_host_register(void* p, size_t nbytes) {
+    if (!p || nbytes == 0) return VITS_E_INVALID;
+    if (cudaHostRegister(p, nbytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return VITS_E_CUDA; }
+    return VITS_OK;
+}
+
+int vits_host_unregister(void* p) {
+    if (!p) return VITS_OK;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return VITS_E_CUDA; }
     return VITS_OK;
 }
 

@@ -94,6 +94,11 @@ def load_library(path: Optional[str] = None):
     lib.vits_create.argtypes = [C.POINTER(CArch), C.c_int, C.POINTER(H)]
     lib.vits_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(H), C.c_char_p, C.c_size_t]
     lib.vits_open.restype = C.c_int
+    lib.vits_set_output_offsets.argtypes = [H, C.c_void_p, C.c_int32]
+    lib.vits_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.vits_host_unregister.argtypes = [C.c_void_p]
+    for fn in ("vits_set_output_offsets", "vits_host_register", "vits_host_unregister"):
+        getattr(lib, fn).restype = C.c_int
     lib.vits_upload.argtypes = [H, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
     lib.vits_finalize.argtypes = [H]
     lib.vits_set_option.argtypes = [H, C.c_char_p, C.c_double]
@@ -137,6 +142,7 @@ EXPORTED_SYMBOLS = (
     "vits_decode", "vits_fetch", "vits_timer_start", "vits_timer_stop", "vits_stage_ms", "vits_kernel_ms", "vits_launch_count",
     "vits_last_error", "vits_destroy", "vits_host_alloc", "vits_host_free", "vits_wait_output",
     "vits_describe", "vits_max_output_samples", "vits_set_stream", "vits_output_ticket", "vits_wait_ticket", "vits_open",
+    "vits_set_output_offsets", "vits_host_register", "vits_host_unregister",
 )
 # include/vits_b200_test.h: test-only hooks, not part of the drop-in boundary
 TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe", "vits_test_file_arch", "vits_test_file_blob")
@@ -317,7 +323,8 @@ class Engine:
         return ylen
 
     def decode(self, noise_z: Optional[np.ndarray] = None, out: str = "f32", volume: float = 1.0,
-               normalize: bool = True, asynchronous: bool = False) -> Optional[np.ndarray]:
+               normalize: bool = True, asynchronous: bool = False, dest: Optional[np.ndarray] = None,
+               dest_offsets=None) -> Optional[np.ndarray]:
         """``asynchronous=True`` (host outputs only): returns as soon as the device->host transfer is enqueued; the array is
         complete after ``wait_ticket(self.last_ticket)``.  It is a per-call flag -- a blocking decode() issued while an
         asynchronous result is still in flight waits for ITS OWN buffer only and does not disturb the other one."""
@@ -337,10 +344,27 @@ class Engine:
             raise ValueError("out must be 'none', 'f32' or 'i16'")
         # page-locked result: the device->host transfer is a DMA on the copy stream, chunk by chunk
         kind = (1 if out == "f32" else 2) | (VITS_OUT_ASYNC if asynchronous else 0)
+        if dest is not None:
+            # scatter output: utterance b lands at dest[dest_offsets[b]:...] (vits_set_output_offsets); `dest` is the caller's own
+            # buffer (page-lock it with host_register() for asynchronous DMA) and is returned as is
+            offs = np.ascontiguousarray(dest_offsets, dtype=np.int64).reshape(-1)
+            if offs.shape[0] != self._B or dest.dtype != (np.float32 if out == "f32" else np.int16) or not dest.flags["C_CONTIGUOUS"]:
+                raise ValueError("dest must be a contiguous array of the output dtype and dest_offsets one sample offset per utterance")
+            self._check(self.lib.vits_set_output_offsets(self._h, _ptr(offs), self._B))
+            self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, kind, _ptr(dest), int(dest.size), volume, int(normalize)))
+            self.last_ticket = int(self.lib.vits_output_ticket(self._h))
+            return dest
         buf = self._pool.take(total, np.float32 if out == "f32" else np.int16)
         self._check(self.lib.vits_decode(self._h, _ptr(nz), stride, kind, _ptr(buf), total, volume, int(normalize)))
         self.last_ticket = int(self.lib.vits_output_ticket(self._h))
         return buf
+
+    def host_register(self, arr: np.ndarray):
+        """Page-lock memory the caller owns (e.g. a shared-memory segment) so DMAs into it are asynchronous."""
+        self._check(self.lib.vits_host_register(_ptr(arr), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self.lib.vits_host_unregister(_ptr(arr))
 
     def decode_to_device(self, dev_ptr: int, capacity: int, noise_z: Optional[np.ndarray] = None):
         """float32 audio into a caller-owned DEVICE buffer (out_kind 3): stream-ordered, no host synchronisation."""

@@ -153,6 +153,24 @@ class B200Session:
         self.last_lengths = ylen * self.engine.hop
         return audio, self.last_lengths
 
+    def prepare_feed(self, feed) -> np.ndarray:
+        """Text side only (vits_prepare): returns the samples per utterance the following ``decode_prepared`` will produce -- the
+        two-phase form a multi-process job uses to agree on every utterance's place in a shared result buffer before any audio
+        exists (bench.py --scaling strong)."""
+        x, lens, scales, sid = self._unpack_feed(feed)
+        mask = np.arange(x.shape[1])[None, :] < lens[:, None]
+        self._calls += 1
+        ylen = self.engine.prepare(x[mask], lens, scales, sid, feed.get("noise_dp"), feed.get("logw"), seed=self._seed + self._calls)
+        self.last_lengths = ylen * self.engine.hop
+        return self.last_lengths
+
+    def decode_prepared(self, feed=None, out: str = "f32", dest: Optional[np.ndarray] = None, dest_offsets=None, asynchronous: bool = False,
+                        volume: float = 1.0, normalize: bool = True):
+        """Frame side of the batch ``prepare_feed`` prepared; with ``dest`` / ``dest_offsets`` every utterance is DMA'd straight to
+        its own place in the caller's buffer."""
+        return self.engine.decode(None if feed is None else feed.get("noise_z"), out=out, volume=volume, normalize=normalize,
+                                  asynchronous=asynchronous, dest=dest, dest_offsets=dest_offsets)
+
     def synthesize_many(self, feeds, out: str = "f32", volume: float = 1.0, normalize: bool = True):
         """Batched form of the serial loop in ``TTSVoice.synthesize`` (voice.py:265-269): yields
         ``(packed audio, samples per utterance)`` per feed, in order, with the device->host transfer of batch k

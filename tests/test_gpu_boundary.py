@@ -304,3 +304,52 @@ def test_plain_c_host_program(built_lib, tmp_path_factory):
     assert f"{len(ids)} ids" in r.stdout and f"{arch.sample_rate} Hz" in r.stdout
     bad = subprocess.run([exe, p, "1,0,9999,2", out], capture_output=True, text=True)
     assert bad.returncode == 1 and "outside" in bad.stderr                 # id >= n_vocab: VITS_E_INVALID with a message
+
+
+def test_scatter_output_places_every_utterance(built_lib, tmp_path_factory):
+    """vits_set_output_offsets: the frame side's device->host DMAs write utterance b at out + offsets[b] (any order, gaps allowed)
+    into memory the caller owns and page-locked with vits_host_register -- what bench.py --scaling strong uses to let every rank's
+    copy engine fill ONE job-wide buffer in original utterance order.  Two-phase API: prepare_feed (lengths) -> decode_prepared."""
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "tiny", 1)
+    rs = np.random.RandomState(9)
+    f = dict(_feeds(arch, rs, (7,))[0], scales=np.array([0.0, 1.0, 0.0], np.float32))
+    for chunk in (None, 48):
+        sess = B200Session(p, precision="fp32", max_chunk_frames=chunk)
+        want, wlen = sess.synthesize_packed(f)
+        want = np.array(want)
+        alen = sess.prepare_feed(f)
+        assert np.array_equal(alen, wlen)
+        order = rs.permutation(7)                                   # destination order != batch order, 5-sample gaps
+        offs = np.zeros(7, np.int64)
+        pos = 3
+        for b in order:
+            offs[b] = pos
+            pos += int(alen[b]) + 5
+        dest = np.full((pos + 11,), 9.0, np.float32)
+        sess.engine.host_register(dest)
+        try:
+            got = sess.decode_prepared(f, dest=dest, dest_offsets=offs)
+            assert got is dest
+            src = np.concatenate([[0], np.cumsum(wlen)])
+            mask = np.ones(dest.shape, bool)
+            for b in range(7):
+                assert np.array_equal(dest[offs[b]:offs[b] + alen[b]], want[src[b]:src[b + 1]]), (chunk, b)
+                mask[offs[b]:offs[b] + alen[b]] = False
+            assert (dest[mask] == 9.0).all()                         # nothing written outside the utterances' own ranges
+            # int16 the same way
+            i16, _ = sess.synthesize_packed(f, out="i16")
+            sess.prepare_feed(f)
+            d16 = np.zeros((pos + 11,), np.int16)
+            sess.decode_prepared(f, out="i16", dest=d16, dest_offsets=offs)
+            for b in range(7):
+                assert np.array_equal(d16[offs[b]:offs[b] + alen[b]], np.array(i16)[src[b]:src[b + 1]])
+            # capacity is checked per utterance; the offsets are one-shot
+            sess.prepare_feed(f)
+            with pytest.raises(ValueError):
+                sess.decode_prepared(f, dest=dest[:int(offs.max())], dest_offsets=offs)
+            sess.prepare_feed(f)
+            again, _ = sess.synthesize_packed(f)
+            assert np.array_equal(np.array(again), want)
+        finally:
+            sess.engine.host_unregister(dest)
