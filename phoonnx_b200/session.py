@@ -14,6 +14,7 @@ Errors: bad shapes / ids / sid -> ValueError, CUDA problems -> RuntimeError.  No
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -21,6 +22,17 @@ import numpy as np
 from .engine import Engine
 from .packing import pack_model
 from .weights import load_model
+
+
+class _NoLock:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_LOCK = _NoLock()
 
 
 class NodeArg:
@@ -77,6 +89,7 @@ class B200Session:
         self._outputs = [NodeArg("output", "tensor(float)", ["batch_size", 1, 1, "time"])]
         self._seed = int(seed)
         self._calls = 0
+        self._lock = threading.RLock()                   # run() is re-entrant like ORT's (voice.py:374): calls on one session are serialised
         self.last_lengths: Optional[np.ndarray] = None   # samples per utterance of the last run
 
     # ---- the InferenceSession surface TTSVoice uses ---------------------------------
@@ -146,12 +159,13 @@ class B200Session:
         B, T = x.shape
         mask = np.arange(T)[None, :] < lens[:, None]
         ids = x[mask]                                    # packed, positions >= length ignored (commons.py:109-113)
-        self._calls += 1
-        ylen = self.engine.prepare(ids, lens, scales, sid, feed.get("noise_dp"), feed.get("logw"),
-                                   seed=self._seed + self._calls)
-        audio = self.engine.decode(feed.get("noise_z"), out=out, volume=volume, normalize=normalize, asynchronous=asynchronous)
-        self.last_lengths = ylen * self.engine.hop
-        return audio, self.last_lengths
+        with getattr(self, "_lock", _NO_LOCK):           # text side + frame side of ONE call must not interleave with another thread's
+            self._calls += 1
+            ylen = self.engine.prepare(ids, lens, scales, sid, feed.get("noise_dp"), feed.get("logw"),
+                                       seed=self._seed + self._calls)
+            audio = self.engine.decode(feed.get("noise_z"), out=out, volume=volume, normalize=normalize, asynchronous=asynchronous)
+            self.last_lengths = ylen * self.engine.hop
+            return audio, self.last_lengths
 
     def prepare_feed(self, feed) -> np.ndarray:
         """Text side only (vits_prepare): returns the samples per utterance the following ``decode_prepared`` will produce -- the

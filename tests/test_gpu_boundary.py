@@ -353,3 +353,27 @@ def test_scatter_output_places_every_utterance(built_lib, tmp_path_factory):
             assert np.array_equal(np.array(again), want)
         finally:
             sess.engine.host_unregister(dest)
+
+
+def test_sessions_are_thread_safe(built_lib, tmp_path_factory):
+    """ORT's run() is re-entrant (voice.py:374 is called from whatever thread the application uses): one session shared by several
+    threads serialises its calls (text side + frame side of a call never interleave with another thread's), and independent
+    sessions run concurrently on one GPU; every result equals the serial one."""
+    from concurrent.futures import ThreadPoolExecutor
+    from phoonnx_b200.session import B200Session
+    p, arch = _voice_file(tmp_path_factory, "x_low", 1)
+    rs = np.random.RandomState(10)
+    z = np.array([0.0, 1.0, 0.0], np.float32)
+    feeds = [dict(f, scales=z) for f in _feeds(arch, rs, (2, 5, 1, 3, 4, 2, 3, 1))]
+    ref = B200Session(p, precision="bf16")
+    want = [np.array(ref.run(None, f)[0]) for f in feeds]
+    shared = B200Session(p, precision="bf16")
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        got = list(pool.map(lambda f: np.array(shared.run(None, f)[0]), feeds * 3))
+    for i, g in enumerate(got):
+        assert np.array_equal(g, want[i % len(feeds)]), i
+    sessions = [B200Session(p, precision="bf16") for _ in range(3)]
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        outs = list(pool.map(lambda s: [np.array(s.run(None, f)[0]) for f in feeds], sessions))
+    for o in outs:
+        assert all(np.array_equal(a, b) for a, b in zip(o, want))
