@@ -23,6 +23,11 @@ int vits_test_conv(vits_handle* h, int use_tc, const float* x, int L, int cin, c
  * rotation, operand tile of `rows` rows).  Returns the average cycles per MMA (issue only / issue + completion). */
 int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
                         double* total_cycles);
+/* mode: 0 both operands in shared memory, K-major no-swizzle (== vits_test_mma_probe); 1 both SWIZZLE_128B; 2 A operand in tensor
+ * memory, B no-swizzle; 3 A in tensor memory, B SWIZZLE_128B; 4 = 2 with a tcgen05.cp smem->tmem of the A operand before each MMA; 5 that
+ * copy alone (csrc/probe_tc.cuh). */
+int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
+                             double* total_cycles);
 
 /* Test hooks of the native voice loader (no GPU needed): the architecture vits_open would infer from `path`, and one packed blob
  * by name (bytes copied to `out` when it fits; returns its size in bytes, or a negative VITS_E_*; *dtype as in vits_upload).

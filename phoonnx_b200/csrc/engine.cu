@@ -1580,14 +1580,29 @@ int vits_host_free(void* p) {
 }
 
 int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles, double* total_cycles) {
-    if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > 512 || rows < 128 + 3 * na || rows > 700 || nctas < 1) return VITS_E_INVALID;
+    return vits_test_mma_probe_mode(h, 0, n, iters, nd, na, rows, nctas, issue_cycles, total_cycles);
+}
+
+int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles, double* total_cycles) {
+    if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > (mode >= 2 ? 384 : 512) || rows < 128 + 8 * na || rows > 700 || nctas < 1 ||
+        mode < 0 || mode > 5) return VITS_E_INVALID;
     std::lock_guard<std::mutex> lk(h->mu);
     CK(h, cudaSetDevice(h->device));
     unsigned long long* d = nullptr;
     CK(h, cudaMalloc(&d, (size_t)nctas * 16));
-    const int smem = 8 * rows * 16 + 8 * 256 * 16;
-    CK(h, cudaFuncSetAttribute(k_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_mma_probe<<<nctas, 128, smem, h->stream>>>(n, iters, nd, na, rows, d);
+    const int smem = 8 * rows * 16 + 8 * 256 * 16 + 2048;
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        kern<<<nctas, 128, smem, h->stream>>>(n, iters, nd, na, rows, d);
+    };
+    switch (mode) {
+        case 0: go(k_mma_probe<0>); break;
+        case 1: go(k_mma_probe<1>); break;
+        case 2: go(k_mma_probe<2>); break;
+        case 3: go(k_mma_probe<3>); break;
+        case 4: go(k_mma_probe<4>); break;
+        default: go(k_mma_probe<5>); break;
+    }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { cudaFree(d); return fail(h, VITS_E_CUDA, "mma probe: %s", cudaGetErrorString(e)); }
     std::vector<unsigned long long> r(2 * (size_t)nctas);

@@ -23,6 +23,21 @@ def probe(sess):
             a, b = C.c_double(), C.c_double()
             rc = lib.vits_test_mma_probe(h, n, 4096, nd, na, rows, nctas, C.byref(a), C.byref(b))
             print(f"{n:3d} {nd:2d} {na:2d} {rows:4d} {nctas:4d} | {a.value:8.1f} {b.value:8.1f}   ({n / 2:.0f})  rc={rc}")
+    # operand placement: does the small-N cost follow the smem layout (swizzle) or the A operand's trip through shared memory at all?
+    lib.vits_test_mma_probe_mode.argtypes = [C.c_void_p, C.c_int] + lib.vits_test_mma_probe.argtypes[1:]
+    names = {0: "A,B smem no-swizzle", 1: "A,B smem SWIZZLE_128B", 2: "A tmem, B smem no-swizzle", 3: "A tmem, B smem SWIZZLE_128B",
+             4: "cp A smem->tmem + MMA A tmem", 5: "cp A smem->tmem alone"}
+    print("mode N  nd na | total cyc/MMA at 1 CTA, at 148 CTAs  (floor N/2)")
+    for mode in (0, 1, 2, 3, 4, 5):
+        for n, nd, na in ((16, 4, 7), (32, 4, 7), (64, 4, 7), (96, 4, 7), (128, 2, 5), (192, 2, 5), (256, 1, 5)):
+            if mode >= 2 and nd * n > 384:
+                nd = 384 // n
+            tot = []
+            for nctas in (1, 148):
+                a, b = C.c_double(), C.c_double()
+                rc = lib.vits_test_mma_probe_mode(h, mode, n, 4096, nd, na, 545, nctas, C.byref(a), C.byref(b))
+                tot.append(b.value if rc == 0 else float("nan"))
+            print(f"{mode} [{names[mode]:28s}] {n:3d} {nd:2d} {na:2d} | {tot[0]:8.1f} {tot[1]:8.1f}   ({n / 2:.0f})")
 
 
 def timeline(sess, stage, arch):
@@ -76,6 +91,8 @@ def main():
     sess = B200Session(path, precision="bf16")
     if '--probe' in sys.argv:
         probe(sess)
+    if '--probe-only' in sys.argv:
+        return
     timeline(sess, 3, arch)
     timeline(sess, 2, arch)
 
