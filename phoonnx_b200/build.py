@@ -7,9 +7,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
+SRC_MAS = os.path.join(HERE, "csrc", "mas.cu")          # monotonic alignment search (include/mas_b200.h), same library
 OUT = os.path.join(HERE, "libvits_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "kernels_f32.cuh", "attention.cuh", "conv_tc.cuh", "mrf_tiles.cuh", "mrf3_tc.cuh", "probe_tc.cuh", "voice_file.h")] + \
-       [os.path.join(os.path.dirname(HERE), "include", f) for f in ("vits_b200.h", "vits_b200_test.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "common.cuh", "kernels_f32.cuh", "attention.cuh", "conv_tc.cuh", "mrf_tiles.cuh", "mrf3_tc.cuh", "probe_tc.cuh", "voice_file.h", "mas.cu")] + \
+       [os.path.join(os.path.dirname(HERE), "include", f) for f in ("vits_b200.h", "vits_b200_test.h", "mas_b200.h")]
 
 
 def nvcc_path() -> str:
@@ -25,7 +26,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
         if os.path.getmtime(out) >= newest:
             return out
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, "-lz", *extra_flags]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC, SRC_MAS, "-lz", *extra_flags]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -38,6 +38,25 @@ def test_test_hooks_live_in_their_own_header(built_lib):
         assert hasattr(lib, n), n
 
 
+def test_mas_header_symbols_are_exported(built_lib):
+    """include/mas_b200.h (monotonic alignment search) lives in the same library."""
+    hdr = open(os.path.join(ROOT, "include", "mas_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(mas_[a-z0-9_]+)\s*\(", hdr)))
+    from phoonnx_b200 import monotonic_align
+    assert set(names) == set(monotonic_align.MAS_SYMBOLS)
+    lib = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_mas_refuses_cpu_tensors(built_lib):
+    import torch
+    from phoonnx_b200 import monotonic_align
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        monotonic_align.maximum_path(torch.zeros(1, 4, 2), torch.ones(1, 4, 2))
+
+
 def test_python_binding_covers_header(built_lib):
     from phoonnx_b200 import engine
     assert set(engine.EXPORTED_SYMBOLS) == set(declared_symbols())
