@@ -44,7 +44,9 @@ const char* mas_last_error(void);
 /* device time of the last mas_maximum_path on this thread, in ms (0 if timing was not requested): set MAS_TIMED in flags and the call
  * brackets its kernels with CUDA events and synchronises the stream before returning */
 #define MAS_TIMED 0x4
+#define MAS_ROW_KERNEL 0x8   /* use the general one-barrier-per-row kernel (the only one above 1024 columns) also below: for tests / A-B */
 float mas_last_ms(void);
+float mas_last_forward_ms(void);   /* the forward + backtrack launch alone; the rest of mas_last_ms() is the output pass */
 
 #ifdef __cplusplus
 }

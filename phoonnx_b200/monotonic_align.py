@@ -22,7 +22,8 @@ from . import engine
 MAS_DEVICE_PTRS = 0x1
 MAS_PATH_F32 = 0x2
 MAS_TIMED = 0x4
-MAS_SYMBOLS = ("mas_maximum_path", "mas_last_error", "mas_last_ms")
+MAS_ROW_KERNEL = 0x8
+MAS_SYMBOLS = ("mas_maximum_path", "mas_last_error", "mas_last_ms", "mas_last_forward_ms")
 
 _bound = None
 
@@ -35,6 +36,7 @@ def _lib():
         lib.mas_maximum_path.restype = C.c_int
         lib.mas_last_error.restype = C.c_char_p
         lib.mas_last_ms.restype = C.c_float
+        lib.mas_last_forward_ms.restype = C.c_float
         _bound = lib
     return _bound
 
@@ -77,7 +79,7 @@ def maximum_path(neg_cent, mask):
     return path if dtype == torch.float32 else path.to(dtype)
 
 
-def maximum_path_timed(values, t_ys, t_xs):
+def maximum_path_timed(values, t_ys, t_xs, row_kernel: bool = False):
     """Device tensors in (float32 [b, t_y, t_x], int32 [b], int32 [b]); returns (int32 path tensor, kernel milliseconds by CUDA
     events).  For tools/bench_mas.py and the tests."""
     import torch
@@ -86,7 +88,7 @@ def maximum_path_timed(values, t_ys, t_xs):
     with torch.cuda.device(values.device):
         stream = torch.cuda.current_stream().cuda_stream
         _check(_lib().mas_maximum_path(path.data_ptr(), values.data_ptr(), t_ys.data_ptr(), t_xs.data_ptr(), b, ty, tx,
-                                       MAS_DEVICE_PTRS | MAS_TIMED, C.c_void_p(stream)))
+                                       MAS_DEVICE_PTRS | MAS_TIMED | (MAS_ROW_KERNEL if row_kernel else 0), C.c_void_p(stream)))
     return path, float(_lib().mas_last_ms())
 
 

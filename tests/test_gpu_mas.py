@@ -21,9 +21,9 @@ def _oracle(values, t_ys, t_xs):
 def _random_case(rs, b, ty, tx, scale=3.0, ragged=True):
     values = (rs.randn(b, ty, tx) * scale).astype(np.float32)
     if ragged:
-        t_xs = rs.randint(1, tx + 1, size=b).astype(np.int32)
+        t_xs = rs.randint(1, min(tx, ty) + 1, size=b).astype(np.int32)
         t_ys = np.array([rs.randint(t_xs[i], ty + 1) for i in range(b)], np.int32)
-        t_xs[0], t_ys[0] = tx, ty
+        t_xs[0], t_ys[0] = min(tx, ty), ty
     else:
         t_xs = np.full(b, tx, np.int32); t_ys = np.full(b, ty, np.int32)
     return values, t_ys, t_xs
@@ -63,8 +63,11 @@ def test_golden_cases_device_tensors_and_wrapper():
 
 
 @pytest.mark.parametrize("b,ty,tx,what", [
-    (8, 700, 180, "training-sized items, one column per thread, bit matrix in shared memory"),
-    (3, 300, 1500, "two columns per thread"),
+    (8, 700, 180, "training-sized items, wavefront kernel, bit matrix in shared memory"),
+    (3, 900, 1024, "wavefront kernel at its widest: 32 warps, 32-row FIFO"),
+    (4, 130, 600, "wavefront kernel, 19 warps, short items (the boundary ring never wraps)"),
+    (2, 5, 70, "fewer rows than one hand-over block"),
+    (3, 1700, 1500, "two columns per thread"),
     (2, 3300, 3000, "four columns per thread, bit matrix in the global scratch"),
     (2, 6000, 1024, "bit matrix in global memory, 1024 threads"),
     (1, 60000, 40, "row index table in global memory"),
@@ -77,9 +80,13 @@ def test_random_cases_match_oracle(b, ty, tx, what):
     rs = np.random.RandomState(b * 1000 + tx)
     values, t_ys, t_xs = _random_case(rs, b, ty, tx)
     want = _oracle(values, t_ys, t_xs)
-    path, ms = ma.maximum_path_timed(torch.from_numpy(values).cuda(), torch.from_numpy(t_ys).cuda(), torch.from_numpy(t_xs).cuda())
+    dev = [torch.from_numpy(a).cuda() for a in (values, t_ys, t_xs)]
+    path, ms = ma.maximum_path_timed(*dev)
     assert ms > 0
     assert np.array_equal(path.cpu().numpy(), want), what
+    # the general (barrier-per-row) kernel on the same case; above 1024 columns it is what ran already
+    path, _ = ma.maximum_path_timed(*dev, row_kernel=True)
+    assert np.array_equal(path.cpu().numpy(), want), what + " [row kernel]"
 
 
 def test_ties_and_items_without_a_monotonic_path():

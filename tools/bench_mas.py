@@ -3,8 +3,8 @@ Cython/OpenMP `maximum_path_c` (oracle/_ref, else the oracle port) on the box's 
 
     python tools/bench_mas.py [--b 64] [--ty 1000] [--tx 300] [--iters 50]
 
-Prints one JSON line: alignments per second both ways, the kernel's HBM roofline (algorithmic bytes = values read once + paths
-written once = 8 bytes per cell of the padded batch) against MEASURED_PEAKS.json, and what the reference's call costs end to end
+Prints one JSON line: alignments per second both ways, the kernel's HBM roofline (algorithmic bytes = the valid cells of neg_cent read once + the padded path
+array written once) against MEASURED_PEAKS.json, and what the reference's call costs end to end
 including the two copies it needs (D2H neg_cent, H2D path: monotonic_align/__init__.py:14-21).
 """
 from __future__ import annotations
@@ -42,12 +42,12 @@ def main():
     for _ in range(5):
         path, _ = ma.maximum_path_timed(dv, dy, dx)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ms = []
+    ms, ms_fwd = [], []
     for _ in range(args.iters):
         flush.zero_()                                             # L2 flush between timed iterations
         path, t = ma.maximum_path_timed(dv, dy, dx)
-        ms.append(t)
-    ms = float(np.median(ms))
+        ms.append(t); ms_fwd.append(float(ma._lib().mas_last_forward_ms()))
+    ms = float(np.median(ms)); ms_fwd = float(np.median(ms_fwd))
     got = path.cpu().numpy()
 
     # the reference's way on this box: device tensor -> host, compiled core (OpenMP over the batch), host -> device
@@ -79,14 +79,15 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6557.0))) if isinstance(peaks, dict) else 6557.0
-    bytes_algo = 8.0 * b * ty * tx
+    # algorithmic bytes: every VALID cell of neg_cent read once (padding is never touched) + the whole padded path array written once
+    bytes_algo = 4.0 * float((t_ys.astype(np.int64) * t_xs).sum()) + 4.0 * b * ty * tx
     line = {
-        "metric": "alignments_per_s", "unit": "alignments/s", "value": b / (ms * 1e-3), "ms_per_batch": ms,
+        "metric": "alignments_per_s", "unit": "alignments/s", "value": b / (ms * 1e-3), "ms_per_batch": ms, "ms_forward_and_backtrack": ms_fwd, "ms_output_pass": ms - ms_fwd,
         "config": {"workload": f"maximum_path on b={b} items of up to {ty} frames x {tx} text positions (lengths drawn in the upper half), "
                                "float32 neg_cent resident in HBM, int32 path out", "l2_policy": "256 MiB write between timed calls"},
         "roofline": {"bound": "hbm", "achieved": bytes_algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                     "note": "t_y dependent row steps per item: latency / barrier bound by construction, HBM traffic is the algorithmic minimum"},
+                     "frac": bytes_algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": bytes_algo,
+                     "note": "the forward pass is a chain of t_y dependent row steps per item (~100 cycles each: shuffle, select, max, add): latency-bound by construction; the output pass alone runs at ~4 TB/s; DRAM traffic = algorithmic bytes (profiles/r02v_ncu_mas.txt)"},
         "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "value": b / float(np.median(core_s)), "unit": "alignments/s",
                          "ms_core": 1e3 * float(np.median(core_s)), "ms_with_copies": 1e3 * float(np.median(e2e_s)),
                          "sample": "the same batch, 5 calls, median; `ms_with_copies` adds the D2H of neg_cent and the H2D of the path the reference's wrapper performs"},
