@@ -25,7 +25,8 @@ int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int ro
                         double* total_cycles);
 /* mode: 0 both operands in shared memory, K-major no-swizzle (== vits_test_mma_probe); 1 both SWIZZLE_128B; 2 A operand in tensor
  * memory, B no-swizzle; 3 A in tensor memory, B SWIZZLE_128B; 4 = 2 with a tcgen05.cp smem->tmem of the A operand before each MMA; 5 that
- * copy alone (csrc/probe_tc.cuh). */
+ * copy alone; 6 cta_group::2 (pairs of CTAs, nctas even, n a multiple of 32), operands in shared memory; 7 = 6 with A in tensor memory
+ * (csrc/probe_tc.cuh). */
 int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles,
                              double* total_cycles);
 

@@ -1584,8 +1584,8 @@ int vits_test_mma_probe(vits_handle* h, int n, int iters, int nd, int na, int ro
 }
 
 int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd, int na, int rows, int nctas, double* issue_cycles, double* total_cycles) {
-    if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > (mode >= 2 ? 384 : 512) || rows < 128 + 8 * na || rows > 700 || nctas < 1 ||
-        mode < 0 || mode > 5) return VITS_E_INVALID;
+    if (!h || n < 16 || n > 256 || n % 16 || iters < 1 || nd < 1 || nd * n > ((mode >= 2 && mode != 6) ? 384 : 512) || rows < 128 + 8 * na || rows > 700 || nctas < 1 ||
+        mode < 0 || mode > 7 || (mode >= 6 && (n % 32 || nctas % 2))) return VITS_E_INVALID;
     std::lock_guard<std::mutex> lk(h->mu);
     CK(h, cudaSetDevice(h->device));
     unsigned long long* d = nullptr;
@@ -1601,8 +1601,11 @@ int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd,
         case 2: go(k_mma_probe<2>); break;
         case 3: go(k_mma_probe<3>); break;
         case 4: go(k_mma_probe<4>); break;
-        default: go(k_mma_probe<5>); break;
+        case 5: go(k_mma_probe<5>); break;
+        case 6: go(k_mma_probe2<0>); break;       // clusters of two CTAs (__cluster_dims__)
+        default: go(k_mma_probe2<1>); break;
     }
+    if (mode >= 6) nctas /= 2;                     // one result per pair
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { cudaFree(d); return fail(h, VITS_E_CUDA, "mma probe: %s", cudaGetErrorString(e)); }
     std::vector<unsigned long long> r(2 * (size_t)nctas);

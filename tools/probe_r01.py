@@ -26,14 +26,17 @@ def probe(sess):
     # operand placement: does the small-N cost follow the smem layout (swizzle) or the A operand's trip through shared memory at all?
     lib.vits_test_mma_probe_mode.argtypes = [C.c_void_p, C.c_int] + lib.vits_test_mma_probe.argtypes[1:]
     names = {0: "A,B smem no-swizzle", 1: "A,B smem SWIZZLE_128B", 2: "A tmem, B smem no-swizzle", 3: "A tmem, B smem SWIZZLE_128B",
-             4: "cp A smem->tmem + MMA A tmem", 5: "cp A smem->tmem alone"}
+             4: "cp A smem->tmem + MMA A tmem", 5: "cp A smem->tmem alone",
+             6: "cta_group::2, A,B smem", 7: "cta_group::2, A tmem"}
     print("mode N  nd na | total cyc/MMA at 1 CTA, at 148 CTAs  (floor N/2)")
-    for mode in (0, 1, 2, 3, 4, 5):
+    for mode in (0, 1, 2, 3, 4, 5, 6, 7):
         for n, nd, na in ((16, 4, 7), (32, 4, 7), (64, 4, 7), (96, 4, 7), (128, 2, 5), (192, 2, 5), (256, 1, 5)):
-            if mode >= 2 and nd * n > 384:
+            if mode >= 6 and n % 32:
+                continue
+            if mode >= 2 and mode != 6 and nd * n > 384:
                 nd = 384 // n
             tot = []
-            for nctas in (1, 148):
+            for nctas in ((2, 148) if mode >= 6 else (1, 148)):
                 a, b = C.c_double(), C.c_double()
                 rc = lib.vits_test_mma_probe_mode(h, mode, n, 4096, nd, na, 545, nctas, C.byref(a), C.byref(b))
                 tot.append(b.value if rc == 0 else float("nan"))
