@@ -255,6 +255,13 @@ __device__ __forceinline__ void bulk_g2s_mc_e(uint32_t dst, const void* src, uin
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n\t}"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask), "r"(el) : "memory");
 }
+// TMA tile load (cp.async.bulk.tensor, SASS UTMALDG): one box of a 2-D tensor map -> shared memory, completion counted in bytes on `bar`.
+// Coordinates are signed; rows outside the tensor arrive as zeros.
+__device__ __forceinline__ void tma_load_2d_e(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint32_t el) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "r"(el) : "memory");
+}
 // a value every lane of the (converged) warp holds identically, in a form ptxas can keep in a uniform register
 __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

@@ -8,6 +8,7 @@
 // utterance, zero padding at utterance edges).  Phase 1 (vits_prepare) runs the text side and
 // ends with the only host sync of the path: the per-utterance frame counts.  Phase 2
 // (vits_decode) runs the frame side in chunks bounded by a frame budget.
+#include <cuda.h>
 #include "../../include/vits_b200.h"
 #include "../../include/vits_b200_test.h"
 #include "common.cuh"
@@ -430,12 +431,45 @@ struct TileBuilder {
     }
 };
 
+// cuTensorMapEncodeTiled, fetched from the driver at run time (the library links cudart only)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<tmap_encode_fn>(p);
+    }();
+    return fn;
+}
+
+// 2-D tensor map over bf16 operand rows [rows, C] (row-major) with boxes of [box_rows rows x 8 channels]: one box == one 8-channel
+// plane segment of the K-major no-swizzle operand tile (mrf3_tc.cuh).  Rows outside [0, rows) read as zeros.
+bool make_rows_tmap(CUtensorMap* tm, const void* base, long rows, int C, int box_rows) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc || rows < 1 || (reinterpret_cast<uintptr_t>(base) & 15) || (C * 2) % 16) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {8u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the fused MRF kernel with CUDA events around the kernel proper (the tile-descriptor helper launch stays outside)
 cudaError_t mrf3_launch_timed(vits_handle* h, const Mrf3Args& m, const Mrf3Cfg& c, int stage) {
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (c.tma) {
+        const bool modeU = m.up_u != 0;
+        if (!make_rows_tmap(&tm, modeU ? (const void*)m.hb : (const void*)m.xb, m.in_rows, modeU ? m.up_cin : m.C, c.box_rows))
+            return cudaErrorInvalidValue;
+    }
     cudaError_t e = mrf3_tiles_launch(m, c, h->stream);
     if (e != cudaSuccess) return e;
     const size_t slot = sub_begin(h, stage);
-    e = mrf3_kernel_launch(m, c, h->num_sms, h->stream);
+    e = mrf3_kernel_launch(m, c, tm, h->num_sms, h->stream);
     sub_end(h, slot);
     return e;
 }
@@ -998,6 +1032,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         // fused MRF stage kernel (mrf3_tc.cuh) where the stage qualifies: bf16 mode, ResBlock2, 32 / 64 channels.  The last stage also
         // absorbs its ConvTranspose1d and lrelu -> conv_post -> tanh.  Stages that do not qualify run conv by conv on bf16 operand rows
         // (below) -- which is also the reference the fused kernel is tested against (option no_fused_mrf).
+        // input tiles of the fused kernels by TMA (cp.async.bulk.tensor) unless option mrf_tma = 0 or the driver has no encoder
+        const bool use_tma = (h->opts.count("mrf_tma") ? h->opts["mrf_tma"] != 0 : true) && tmap_encoder() != nullptr;
         std::vector<Mrf3Args> mrf3_args(A.n_ups + 1);
         std::vector<Mrf3Cfg> mrf3_cfg(A.n_ups + 1);
         std::vector<int> mrf_on(A.n_ups + 1, 0);      // 0: conv by conv, 3: fused (bf16 inter-stage rows, optional fused ConvTranspose)
@@ -1028,7 +1064,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             for (int tryu = can_up ? 1 : 0; tryu >= 0 && !done; tryu--) {
                 m3.up_u = tryu ? U.rate : 0; m3.up_cin = tryu ? U.A.cin : 0;
                 for (int tryp = want_post ? 1 : 0; tryp >= 0 && !done; tryp--)
-                    if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0)) {
+                    if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0, use_tma)) {
                         mrf_on[i + 1] = 3; up_fused[i + 1] = tryu; if (tryp) post_fused = true; done = true;
                     }
             }
@@ -1184,7 +1220,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
                 if (up_fused[i + 1]) {
                     m.hb = cur_b; m.up_w[0] = U.A.wtc; m.up_w[1] = U.B.wtc; m.up_b = U.A.b;     // bias tiled per phase: first C entries
-                } else m.xb = Xb;
+                    m.in_rows = (long)Fr * rates[i];
+                } else { m.xb = Xb; m.in_rows = (long)Fr * rates[i + 1]; }
                 m.out = nullptr; m.outb = nullptr; m.post_w = nullptr; m.audio = nullptr;
                 if (post_fused && i == A.n_ups - 1) { m.post_w = h->post_w; m.post_slope = 0.01f; m.audio = audio + (int64_t)f_lo * hop; }
                 else if (i + 1 < A.n_ups && up_fused[i + 2]) { m.outb = reinterpret_cast<__nv_bfloat16*>(XS); m.outb_slope = 0.1f; }

@@ -25,6 +25,11 @@
 //     before the first epilogue result is needed, so E1(r) overlaps C1(r+1..) and C2(r-1); the previous tile's conv_post goes in
 //     behind this tile's first conv1 instead of idling the tensor pipe at the tile's end.
 //
+//   * (round 2) the input tile arrives by TMA: the K-major no-swizzle operand plane of 8 channels IS a [rows x 16 bytes] box of the
+//     2-D tensor [rows, C] of bf16 operand rows, so C/8 x ceil(rows/256) cp.async.bulk.tensor (UTMALDG) issued by one lane replace
+//     ~2.2k LDGSTS of the 32-lane cp.async loader; rows outside the ARRAY come back as zeros from the TMA unit, rows inside the array
+//     but outside the tile's utterance (first / last tile of an utterance only) are zeroed by the loader warp afterwards.  The
+//     cp.async loader stays as option `mrf_tma` = 0 (A/B, and the reference for the parity test of the two loaders).
 //   * two MMA-issuing warps, each owning half of the M blocks (distinct accumulators, so the result does not depend on
 //     how their instructions interleave): one thread's descriptor set-up (R2UR moves, uniform adds) does not overlap
 //     the execution of its own MMAs -- measured 60-75 cycles per N=32 MMA issued against 40 executed -- but it does
@@ -33,6 +38,7 @@
 // Warp roles (640 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
 // elected lane = weight producer (+ TMEM allocation), warps 17 and 19 elected lane = MMA issuers, warp 18 = input-row loader.
 #pragma once
+#include <cuda.h>          // CUtensorMap (the type only: the encoder is fetched at run time, engine.cu)
 #include "mrf_tiles.cuh"
 
 #define MRF3_THREADS 640
@@ -42,6 +48,7 @@
 #define MRF3_MAX_STAGES 32
 #define MRF3_POST_K 7
 #define MRF3_NBAR 16
+#define MRF3_TMA_BOX 256          // rows per TMA box (hardware limit of a box dimension)
 #define MRF3_DBG_TILES 24
 
 struct Mrf3Args {
@@ -53,6 +60,7 @@ struct Mrf3Args {
     int nrb;  int k[MRF3_MAX_RB];  int d1[MRF3_MAX_RB];  int d2[MRF3_MAX_RB];
     const __nv_bfloat16* w[MRF3_MAX_RB][2];  const float* b[MRF3_MAX_RB][2];
     const int* cu;  const int* tile_cu;  int B;  int rate;  int ntiles;
+    long in_rows;                                                // host side: rows of the input array (xb, or hb in mode U), for its tensor map
     const int4* tdesc;                                           // per tile {first row of the utterance, its rows, o0, -}
     float out_div;  float slope;  int interleave;                // issue order of the convs (mrf3_step)
     float* out;                                                  // fp32 [rows, C]                       (or null)
@@ -71,6 +79,7 @@ struct Mrf3Cfg {
     int nub, u_rows, u_bytes, upw_bytes;   // mode U: M blocks of the ups pass, rows / bytes of its input tile, bytes of both weight halves
     int bias_off, postw_off, sp_off;   // sp: per-row per-tap partial sums of conv_post, [span + 8][MRF3_SP_PITCH] floats
     int smem_bytes;
+    int tma, nboxes, box_rows;   // input tile by TMA: per 8-channel plane `nboxes` boxes of [box_rows rows x 16 bytes] (rows == nboxes * box_rows)
 };
 
 namespace tc {
@@ -103,7 +112,7 @@ __device__ __forceinline__ void mrf3_step(int step, int nrb, int interleave, int
 #define MRF3_STAMP(it_, slot_) do { if (dbg_on && (it_) < MRF3_DBG_TILES) a.dbg[(it_) * 48 + (slot_)] = (unsigned long long)clock64(); } while (0)
 
 template <int C>
-__global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, const Mrf3Cfg c) {
+__global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, const Mrf3Cfg c, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sX = smem;                                       // lrelu(x)  bf16 K-major chunks [C/8][rx][8]
     uint8_t* sX1 = sX + c.x_bytes;                            // lrelu(x1) bf16 K-major chunks [C/8][rx1][8]; then the conv_post operand
@@ -126,6 +135,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
     const uint32_t bar_post_done = bar_fix + 88u;             // conv_post accumulators ready       (commit / tile)
     const uint32_t bar_post_free = bar_fix + 96u;             // conv_post accumulators drained     (512 / tile)
     const uint32_t bar_upw = bar_fix + 104u;                  // ups weights landed                 (once)
+    const uint32_t bar_tma = bar_fix + 112u;                  // input tile landed in shared memory (TMA bytes / tile; the loader warp waits)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + MRF3_NBAR);
     float* sB = reinterpret_cast<float*>(smem + c.bias_off);  // bias1 of every resblock, then sum_r bias2_r, then the ups bias
     uint8_t* sWp = smem + c.postw_off;
@@ -150,6 +160,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         tc::mbar_init(bar_post_done, nmw);
         tc::mbar_init(bar_post_free, MRF3_EPI_THREADS);
         tc::mbar_init(bar_upw, 1);
+        tc::mbar_init(bar_tma, 1);
         tc::fence_mbar_init();
     }
     for (int i = tid; i < C; i += MRF3_THREADS) {
@@ -587,6 +598,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
         // ===================== input-row loader (warp 18): cp.async, 16 B per lane, zero fill outside the utterance =====================
         uint32_t n_free = 0;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        const uint32_t el = tc::elect_flag();
         int it = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
             long row0; int len, o0;
@@ -595,6 +607,37 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             MRF3_STAMP(it, 44);
             if (tile != (int)blockIdx.x) { tc::mbar_wait(bar_in_free, n_free & 1); n_free++; }
             MRF3_STAMP(it, 45);
+            if (c.tma) {
+                // tile row j of plane kc <- tensor row g0 + j, channels [8 kc, 8 kc + 8); rows [vlo, vhi) belong to this tile's utterance
+                int g0, rows, planes, vlo, vhi;
+                uint32_t dst0;
+                if (modeU) {
+                    const int qb = q_base(tbase);
+                    g0 = (int)(row0 >> 2) + qb - 1; rows = c.u_rows; planes = KCU; dst0 = tc::smem_u32(sU);
+                    vlo = 1 - qb; vhi = (len >> 2) - qb + 1;
+                } else {
+                    g0 = (int)row0 + tbase; rows = c.rx; planes = KC; dst0 = tc::smem_u32(sX);
+                    vlo = -tbase; vhi = len - tbase;
+                }
+                vlo = min(max(vlo, 0), rows); vhi = min(max(vhi, vlo), rows);
+                tc::fence_proxy_async();                          // the previous tile's generic-proxy reads of this buffer are behind us
+                tc::mbar_expect_tx_e(bar_tma, (uint32_t)(planes * rows) * 16u, el);
+                for (int kc = 0; kc < planes; kc++)
+                    for (int bx = 0; bx < c.nboxes; bx++)
+                        tc::tma_load_2d_e(dst0 + (uint32_t)(kc * rows + bx * c.box_rows) * 16u, &tmap, kc * 8, g0 + bx * c.box_rows, bar_tma, el);
+                tc::mbar_wait(bar_tma, (uint32_t)it & 1u);
+                // rows of OTHER utterances (inside the array, so the TMA unit delivered them): zero, as the convolutions' padding
+                const int nz = vlo + (rows - vhi);
+                for (int i = lane; i < nz * planes; i += 32) {
+                    const int kc = i / nz, j = i - kc * nz;
+                    const int r = j < vlo ? j : vhi + (j - vlo);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst0 + (uint32_t)(kc * rows + r) * 16u), "r"(0u) : "memory");
+                }
+                tc::fence_proxy_async();
+                tc::mbar_arrive(bar_in);
+                MRF3_STAMP(it, 46);
+                continue;
+            }
             if (modeU) {
                 const int qb = q_base(tbase);
                 const long rin0 = row0 >> 2;                      // first input row of the utterance (rate / u rows per frame)
@@ -632,7 +675,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post) {
+static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post, bool use_tma = true) {
     memset(&c, 0, sizeof c);
     if (a.C != 32 && a.C != 64) return false;
     if (a.nrb < 1 || a.nrb > MRF3_MAX_RB) return false;
@@ -659,7 +702,15 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
         if (fuse_post && nb * 16 > nb * a.C) continue;
         c.nb = nb; c.nmw = (nb % 2 == 0) ? 2 : 1; c.span = 128 * nb; c.t_out = c.span - 2 * hmax; c.t_step = c.t_out - 2 * c.post_halo;
         if (c.t_step < 32) continue;
-        c.rx = ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
+        // rows of a TMA-fed tile: a whole number of equal boxes of a multiple of 8 rows (planes stay 128-byte aligned); otherwise odd
+        // (the cp.async loader's 16-byte writes of one row's chunks then land in different banks)
+        auto tma_rows = [&](int need) {
+            const int r8 = (need + 7) / 8 * 8, nbx = (r8 + MRF3_TMA_BOX - 1) / MRF3_TMA_BOX;
+            c.nboxes = nbx; c.box_rows = ((r8 + nbx - 1) / nbx + 7) / 8 * 8;
+            return c.nboxes * c.box_rows;
+        };
+        c.tma = use_tma ? 1 : 0;
+        c.rx = (use_tma && !modeU) ? tma_rows(c.span + 2 * h1max) : ((c.span + 2 * h1max + 7) / 8) * 8 + 1;
         c.rx1 = ((c.span + 2 * hmax + 7) / 8) * 8 + 1;
         c.x_bytes = ((a.C / 8) * c.rx * 16 + 127) / 128 * 128;
         c.x1_bytes = ((a.C / 8) * c.rx1 * 16 + 127) / 128 * 128;
@@ -670,7 +721,7 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
             // ups accumulators live in conv1 buffers 0 .. n_r - 2: those are drained when the next tile's ups pass is issued (before
             // the last conv2), and the last buffer doubles as the conv_post accumulator
             if (a.nrb < 2 || c.nub * a.up_u * a.C > (a.nrb - 1) * nb * a.C) continue;
-            c.u_rows = ((c.nub * 128 + 2 + 7) / 8) * 8 + 1;
+            c.u_rows = use_tma ? tma_rows(c.nub * 128 + 2) : ((c.nub * 128 + 2 + 7) / 8) * 8 + 1;
             c.u_bytes = ((a.up_cin / 8) * c.u_rows * 16 + 127) / 128 * 128;
             c.upw_bytes = 2 * 2 * a.up_cin * (a.up_u / 2) * a.C * 2;
         }
@@ -701,7 +752,7 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
 }
 
 template <int C>
-static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
+static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, const CUtensorMap& tmap, int num_sms, cudaStream_t st) {
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -715,7 +766,7 @@ static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, int
     int gx = num_sms;                       // one persistent CTA per SM (TMEM: 512 columns each)
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) return cudaSuccess;
-    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c);
+    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c, tmap);
     return cudaGetLastError();
 }
 
@@ -727,14 +778,10 @@ static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c,
     return cudaGetLastError();
 }
 
-static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
-    if (a.C == 32) return mrf3_launch_t<32>(a, c, num_sms, st);
-    if (a.C == 64) return mrf3_launch_t<64>(a, c, num_sms, st);
+// tmap: the tensor map of the kernel's input rows (mode A: xb [rows, C]; mode U: hb [rows / u, up_cin]) with box {8, c.box_rows};
+// ignored (may be zero-filled) when c.tma == 0
+static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, const CUtensorMap& tmap, int num_sms, cudaStream_t st) {
+    if (a.C == 32) return mrf3_launch_t<32>(a, c, tmap, num_sms, st);
+    if (a.C == 64) return mrf3_launch_t<64>(a, c, tmap, num_sms, st);
     return cudaErrorInvalidConfiguration;
-}
-
-static inline cudaError_t mrf3_launch(const Mrf3Args& a, const Mrf3Cfg& c, int num_sms, cudaStream_t st) {
-    cudaError_t e = mrf3_tiles_launch(a, c, st);
-    if (e != cudaSuccess) return e;
-    return mrf3_kernel_launch(a, c, num_sms, st);
 }

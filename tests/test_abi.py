@@ -71,6 +71,7 @@ def test_blackwell_instructions_present(built_lib):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([exe, "-sass", built_lib], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+    assert "UTMALDG" in sass                      # cp.async.bulk.tensor: the fused stage kernels' input tiles
     assert "sm_100a" in subprocess.run([exe, "-lelf", built_lib], capture_output=True, text=True).stdout
 
 

@@ -515,6 +515,35 @@ def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
     assert np.isfinite(outs[1][0]).all() and np.array_equal(outs[0][0], outs[1][0])
 
 
+@pytest.mark.parametrize("preset", ["medium", "x_low"])
+def test_tma_fed_input_tiles_are_bit_identical(lib, tmp_path_factory, preset):
+    """The fused stage kernels take their input tiles by TMA (cp.async.bulk.tensor boxes, default) or through the cp.async loader warp
+    (`mrf_tma` = 0).  Same operand bytes in shared memory -> bit-identical audio.  The lengths put utterance starts and ends inside
+    tiles (rows of the neighbouring utterance must be zeroed after the TMA delivered them), the first utterance at the start of the
+    array and the last at its end (rows outside the array: zeros from the TMA unit), and a one-id utterance shorter than any halo."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, preset, 1)
+    rs = np.random.RandomState(12)
+    lens = np.array([1, 97, 3, 160, 41, 2, 77, 130, 5], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
+    outs = []
+    for opt in (0, 1):
+        for chunk in (None, 900):                      # one chunk, and several (the tensor map follows the chunk's row count)
+            sess = B200Session(p, precision="bf16")
+            sess.engine.set_option("mrf_tma", opt)
+            if chunk:
+                sess.engine.set_option("max_chunk_frames", chunk)
+            a, alen = sess.synthesize_packed(feed)
+            outs.append((a.copy(), alen.copy()))
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][1], o[1])
+        assert np.isfinite(o[0]).all() and np.array_equal(outs[0][0], o[0])
+
+
 def test_resblock1_stages_on_bf16_rows_match_fp32_rows(lib, tmp_path_factory):
     """ResBlock1 (`high`, modules.py:301-314) conv by conv: bf16 operand rows between the convs (default) vs fp32 rows with a
     conversion pass per launch (`no_stage_bf16`): same MMAs, the residual stream rounds to bf16 once per conv pair."""
