@@ -47,7 +47,8 @@ struct ConvArgs {
     // total); all zero = every slice uses toff[0 .. ntaps).  Lets ONE launch sum convolutions with different kernels / dilations.
     int ntaps_ks[CONV_MAX_SLICES];  int tap0_ks[CONV_MAX_SLICES];
     const __nv_bfloat16* xb;  int ldxb;       // tcgen05 path: the input as bf16 MMA-operand rows [rows, ldxb] (already activated) instead of fp32 `x`;
-                                            // cp.async'd straight into the operand tile (xcol applies)
+                                            // TMA'd (or cp.async'd) straight into the operand tile (xcol applies)
+    long xb_rows;                           // host side: rows of the xb array (> 0 enables the TMA loader: its tensor map needs the extent)
     int nresb;  int resb_stride;            // > 1: the residual is the SUM of nresb such row groups, resb_stride columns apart (<= 3)
     const __nv_bfloat16* resb;  int ldresb;  float resb_slope;   // residual given as bf16 lrelu_{slope} rows: res = min(v, v / slope) (rescol applies)
     __nv_bfloat16* outb;  float outb_slope;   // EPI_STORE / EPI_GATE on the tcgen05 path: write bf16(lrelu_{slope}(v)) here instead of fp32 `out`

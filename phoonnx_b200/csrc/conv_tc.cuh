@@ -19,6 +19,7 @@
 // What bounds it: the SM's 128 B/clk shared-memory port, shared by the MMA operand reads, the loader and the
 // epilogue transpose.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type + enums; the encoder is fetched from the driver at run time)
 #include <type_traits>
 #include "common.cuh"
 #include "kernels_f32.cuh"
@@ -33,6 +34,7 @@
 #define TC_M 128
 #define TC_LOAD_BATCH 8          // fp32 loader: (row, chunk) items whose 2 x LDG.128 are in flight per thread before any conversion
 #define TC_EPI_WARPS 8
+#define TC_NFIXBAR 10               // fixed mbarriers behind the weight ring's (a_full, a_empty, acc_full, acc_empty, a_tma: two each)
 #define TC_LOAD_WARPS 6
 #define TC_THREADS ((TC_EPI_WARPS + TC_LOAD_WARPS + 2) * 32)
 #define TC_LOAD_THREADS (TC_LOAD_WARPS * 32)
@@ -61,6 +63,7 @@ struct TcCfg {
     int nepi;         // epilogue warps: 8, or 12 when the loader is the cp.async one (bf16 operand rows: 2 loader warps suffice)
     int nload;        // loader warps = 14 - nepi
     int gw;           // accumulator columns per epilogue work item (32, or 16 when that spreads the items better over the warps)
+    int tma, nboxes, box_rows;   // activation tile by TMA (bf16 operand rows): per 8-channel plane `nboxes` boxes of [box_rows x 16 bytes]
     int cluster;      // 2: CTA pairs (cluster 2x1x1) share every weight piece -- each CTA fetches every other piece and multicasts it to both
                       //    (the ring-mode launches are bound by L2 -> SM weight traffic: a 128-row tile re-streams all taps); 1: off
 };
@@ -570,19 +573,20 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
 // that fits the instruction cache (as ONE kernel with a run-time dispatch this was 18k SASS instructions, spilling for the
 // heaviest variant's sake and stalling on instruction fetch -- r01d ncu `no_inst`)
 template <int EPI, int RESK, int ACC>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sW = smem + (size_t)c.nabuf * c.a_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)c.nstages * c.slot_bytes);
-    // bars: w_full[nstages], w_empty[nstages], a_full[2], a_empty[2], acc_full[2], acc_empty[2]; then tmem ptr
+    // bars: w_full[nstages], w_empty[nstages], a_full[2], a_empty[2], acc_full[2], acc_empty[2], a_tma[2]; then tmem ptr
     const uint32_t bar_full0 = tc::smem_u32(bars);
     const uint32_t bar_empty0 = bar_full0 + 8u * c.nstages;
     const uint32_t bar_afull0 = bar_empty0 + 8u * c.nstages;
     const uint32_t bar_aempty0 = bar_afull0 + 16u;
     const uint32_t bar_accfull0 = bar_aempty0 + 16u;
     const uint32_t bar_accempty0 = bar_accfull0 + 16u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + 8);
+    const uint32_t bar_tma0 = bar_accempty0 + 16u;               // a_tma[2]: activation tile landed (TMA bytes; the loader warp waits)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * c.nstages + TC_NFIXBAR);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform in a form ptxas can see (role branches stay converged)
@@ -595,7 +599,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
     if (tid == 0) {
         for (int s = 0; s < c.nstages; s++) { tc::mbar_init(bar_full0 + 8u * s, 1); tc::mbar_init(bar_empty0 + 8u * s, (uint32_t)c.cluster); }
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(bar_afull0 + 8u * i, (uint32_t)c.nload * 32u);
+            tc::mbar_init(bar_afull0 + 8u * i, c.tma ? 32u : (uint32_t)c.nload * 32u);
+            tc::mbar_init(bar_tma0 + 8u * i, 1);
             tc::mbar_init(bar_aempty0 + 8u * i, 1);
             tc::mbar_init(bar_accfull0 + 8u * i, 1);
             tc::mbar_init(bar_accempty0 + 8u * i, (uint32_t)c.nepi * 32u);
@@ -631,6 +636,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
         else tc_epilogue<EPI, RESK, ACC>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
     } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= activation loaders (the warps between the epilogue warps and warp 14) =================
+        if (c.tma) {
+            // ---- TMA loader (bf16 operand rows): the first loader warp alone.  An 8-channel plane of the K-major no-swizzle tile is a
+            // [rows_a x 16 bytes] box of the 2-D tensor [rows, ldxb]: cin/8 x nboxes cp.async.bulk.tensor per (tile, K slice), issued by
+            // one lane, replace rows_a * cin/8 LDGSTS spread over the loader warps -- whose stream the r01g timeline showed pacing the
+            // epilogue's own loads through the LSU queue.  Rows outside the array arrive as zeros; rows of neighbouring utterances
+            // (first / last tile of an utterance) are zeroed here afterwards.
+            if (warp == c.nepi) {
+                const uint32_t el = tc::elect_flag();
+                uint32_t it = 0;
+                for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
+                    TC_STAMP(it, 4);
+                    const int4 dsc = __ldg(a.tdesc + tile);
+                    const int t0 = dsc.z, len = dsc.y;
+                    const int g0 = dsc.x + t0 + c.min_off;                              // tensor row of tile row 0
+                    const int tlo = min(max(-(t0 + c.min_off), 0), c.rows_a), thi = min(max(len - (t0 + c.min_off), tlo), c.rows_a);
+                    for (int ks = 0; ks < a.nks; ks++) {
+                        const uint32_t lit = it * (uint32_t)a.nks + (uint32_t)ks;
+                        const uint32_t abuf = lit % (uint32_t)c.nabuf, ause = lit / (uint32_t)c.nabuf;
+                        tc::mbar_wait(bar_aempty0 + 8u * abuf, (ause & 1u) ^ 1u);     // MMAs that read this buffer have retired
+                        TC_STAMP(it, 5);
+                        const uint32_t dA = tc::smem_u32(sA + (size_t)abuf * c.a_bytes), bt = bar_tma0 + 8u * abuf;
+                        const int col0 = a.xcol + ks * a.cin;
+                        tc::mbar_expect_tx_e(bt, (uint32_t)(kc_total * c.rows_a) * 16u, el);
+                        for (int kc = 0; kc < kc_total; kc++)
+                            for (int bx = 0; bx < c.nboxes; bx++)
+                                tc::tma_load_2d_e(dA + (uint32_t)(kc * c.rows_a + bx * c.box_rows) * 16u, &tmap, col0 + kc * 8, g0 + bx * c.box_rows, bt, el);
+                        tc::mbar_wait(bt, ause & 1u);
+                        const int nz = tlo + (c.rows_a - thi);
+                        for (int i = lane; i < nz * kc_total; i += 32) {
+                            const int kc = i / nz, j = i - kc * nz;
+                            const int r = j < tlo ? j : thi + (j - tlo);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dA + (uint32_t)(kc * c.rows_a + r) * 16u), "r"(0u) : "memory");
+                        }
+                        tc::fence_proxy_async();
+                        tc::mbar_arrive(bar_afull0 + 8u * abuf);
+                        TC_STAMP(it, 6);
+                    }
+                }
+            }
+        } else {
         const int lt = tid - c.nepi * 32;
         const int nlt = c.nload * 32;                   // loader threads
         uint32_t it = 0;
@@ -717,6 +762,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             tc::mbar_arrive(bar_afull0 + 8u * abuf);
             TC_STAMP(it, 6);
             }
+        }
         }
     } else if (warp == TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= weight producer (cp.async.bulk ring; warp-uniform loop, copies predicated on the elected lane) =================
@@ -858,6 +904,33 @@ static inline bool conv_tc_supported(const ConvArgs& a) {
     return true;
 }
 
+// cuTensorMapEncodeTiled, fetched from the driver at run time (the library links cudart only)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<tmap_encode_fn>(p);
+    }();
+    return fn;
+}
+// 2-D tensor map over bf16 operand rows [rows, ld] (row-major) with boxes of [box_rows rows x 8 channels]: one box == one 8-channel
+// plane segment of the K-major no-swizzle operand tile.  Rows outside [0, rows) read as zeros.
+static inline bool make_rows_tmap(CUtensorMap* tm, const void* base, long rows, int ld, int box_rows) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc || rows < 1 || box_rows < 1 || box_rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {8u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static int g_tc_tma = 1;             // engine option "conv_tma" (process-wide): bf16 operand rows reach the activation tile by TMA
+static int g_tc_tma_max_cin = 128;   // engine option "conv_tma_max_cin"
+
 // Epilogue warps when the loader is the cp.async one.  12 (two loader warps) was measured NEUTRAL to slightly worse against 8
 // (profiles/r02m_ab_conv_nepi.log: medium decoder 181-185 vs 184-186 ms, flow 53.5 vs 56 ms, `high` 203.5 vs 206.3 ms): the
 // epilogue is not short of warps -- the small-channel launches move ~1.3 GB per conv and sit at 50-67 % of HBM bandwidth.
@@ -867,7 +940,19 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     for (int i = 1; i < a.ntaps; i++) { mn = a.toff[i] < mn ? a.toff[i] : mn; mx = a.toff[i] > mx ? a.toff[i] : mx; }
     c.min_off = mn;
     int rows = TC_M + (mx - mn);
-    rows = ((rows + 7) / 8) * 8 + 1;           // odd row count: (kc + r) mod 8 spreads 16 B chunks over all banks
+    // TMA for activation tiles of up to g_tc_tma_max_cin channels per K slice: a box is 16 bytes wide (one 8-channel plane of the
+    // no-swizzle layout), so the TMA unit fetches a 32-byte sector per row and plane and uses half of it; measured (profiles/r02y):
+    // the 32-128-channel decoder launches gain 1.5 % (their loader warps' LDGSTS stream no longer paces the epilogue's loads through
+    // the LSU queue), the 192-channel coupling-flow convs lose 8 % (52 KB tiles: the doubled sector traffic shows).
+    c.tma = (a.xb && !a.split3 && a.xb_rows > 0 && g_tc_tma && a.cin <= g_tc_tma_max_cin && tmap_encoder() != nullptr) ? 1 : 0;
+    c.nboxes = 1; c.box_rows = 0;
+    if (c.tma) {
+        // a whole number of equal boxes of a multiple of 8 rows each (<= 256, the TMA box limit): planes stay 128-byte aligned
+        const int r8 = (rows + 7) / 8 * 8;
+        c.nboxes = (r8 + 255) / 256; c.box_rows = ((r8 + c.nboxes - 1) / c.nboxes + 7) / 8 * 8;
+        rows = c.nboxes * c.box_rows;
+    } else
+        rows = ((rows + 7) / 8) * 8 + 1;       // odd row count: (kc + r) mod 8 spreads the loaders' 16 B chunks over all banks
     c.rows_a = rows;
     const int planes = a.split3 ? 2 : 1, nseg = a.split3 ? 2 : 1;     // weight segments streamed per tap (split3: wh, wl)
     c.a_bytes = (planes * (a.cin / 8) * rows * 16 + 127) / 128 * 128;
@@ -898,7 +983,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
         c.slot_bytes = c.piece_ch * nt * 2;
         const long res_bytes = (long)c.npieces * c.slot_bytes;
         auto total = [&](int nabuf, int nstages) {
-            return (nabuf * c.a_bytes + nstages * c.slot_bytes + (2 * nstages + 8) * 8 + 16 + 127) / 128 * 128 + epi_bytes;
+            return (nabuf * c.a_bytes + nstages * c.slot_bytes + (2 * nstages + TC_NFIXBAR) * 8 + 16 + 127) / 128 * 128 + epi_bytes;
         };
         bool ok = false;
         if (c.npieces <= TC_MAX_STAGES && total(2, c.npieces) <= limit) {     // (res_bytes up to ~120 KB: weights read once per CTA, not per tile)
@@ -913,7 +998,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
                     if (total(nabuf, ns) <= limit) { c.nabuf = nabuf; c.nstages = ns; ok = true; }
         }
         if (ok) {
-            c.epi_off = (c.nabuf * c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + 8) * 8 + 16 + 127) / 128 * 128;
+            c.epi_off = (c.nabuf * c.a_bytes + c.nstages * c.slot_bytes + (2 * c.nstages + TC_NFIXBAR) * 8 + 16 + 127) / 128 * 128;
             c.smem_bytes = c.epi_off + epi_bytes;
             break;
         }
@@ -941,7 +1026,10 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
     TcCfg c;
     if (!conv_tc_plan(a, c, num_sms)) return cudaErrorInvalidConfiguration;
     // epilogue variant (compile-time in the kernel)
-    typedef void (*KFn)(const ConvArgs, const TcCfg);
+    typedef void (*KFn)(const ConvArgs, const TcCfg, const CUtensorMap);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (c.tma && !make_rows_tmap(&tm, a.xb, a.xb_rows, a.ldxb, c.box_rows)) return cudaErrorInvalidValue;
     const bool anyacc = a.accumulate || (a.epi == EPI_SPLIT && a.accumulate2);
     KFn fn; int vid;
     if (!c.vec) { fn = k_conv_tc<-1, 0, 0>; vid = 0; }
@@ -988,8 +1076,8 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, fn, a, c);
+        return cudaLaunchKernelEx(&cfg, fn, a, c, tm);
     }
-    fn<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c);
+    fn<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c, tm);
     return cudaGetLastError();
 }

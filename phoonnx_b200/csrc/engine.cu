@@ -259,7 +259,7 @@ int mkdds(vits_handle* h, std::vector<DdsP>& v, const std::string& name, int C) 
 // launches
 // ------------------------------------------------------------------------------------------
 struct Tiles { const int* cu; const int* t64; const int* t128; const int* t256; const int* tx; int n64, n128, n256, nx, tmx; int B; int rate;
-               const int4* d128; };   // d128: per-128-row-tile descriptors for the tcgen05 conv kernel (make_d128)
+               const int4* d128; long rows; };   // rows: all rows of the arrays these tiles cover (sum of the utterances' lengths x rate)   // d128: per-128-row-tile descriptors for the tcgen05 conv kernel (make_d128)
 
 ConvArgs base_args(const ConvP& c, const float* x, int ldx, int xcol, float* out, int ldo, int ocol) {
     ConvArgs a;
@@ -279,6 +279,7 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     if (a.nks <= 1) { a.nks = 1; a.wtc_ks[0] = a.wtc; }
     if (allow_tc && h->precision == 1 && conv_tc_supported(a)) {
         a.tile_cu = T.t128; a.ntiles = T.n128; a.tdesc = T.d128;
+        a.xb_rows = a.xb ? T.rows : 0;          // the TMA loader's tensor map covers exactly the rows these tiles address
         if (T.n128 == 0) return 0;
         if (!T.d128) return fail(h, VITS_E_STATE, "conv_tc: tile descriptors missing for rate %d", T.rate);
         a.dbg = nullptr;
@@ -425,37 +426,11 @@ struct TileBuilder {
         for (auto& e : ents) if (e.rate == rate) {
             Tiles t; t.cu = dev + cu_off; t.t64 = dev + e.o64; t.t128 = dev + e.o128; t.t256 = dev + e.o256;
             t.n64 = e.n64; t.n128 = e.n128; t.n256 = e.n256; t.B = B; t.rate = rate;
-            t.tx = dev + e.ox; t.nx = e.nx; t.tmx = e.tmx; t.d128 = nullptr; return t;
+            t.tx = dev + e.ox; t.nx = e.nx; t.tmx = e.tmx; t.d128 = nullptr; t.rows = (long)host[cu_off + B] * rate; return t;
         }
         Tiles t; memset(&t, 0, sizeof t); return t;
     }
 };
-
-// cuTensorMapEncodeTiled, fetched from the driver at run time (the library links cudart only)
-typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-tmap_encode_fn tmap_encoder() {
-    static tmap_encode_fn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        return reinterpret_cast<tmap_encode_fn>(p);
-    }();
-    return fn;
-}
-
-// 2-D tensor map over bf16 operand rows [rows, C] (row-major) with boxes of [box_rows rows x 8 channels]: one box == one 8-channel
-// plane segment of the K-major no-swizzle operand tile (mrf3_tc.cuh).  Rows outside [0, rows) read as zeros.
-bool make_rows_tmap(CUtensorMap* tm, const void* base, long rows, int C, int box_rows) {
-    tmap_encode_fn enc = tmap_encoder();
-    if (!enc || rows < 1 || (reinterpret_cast<uintptr_t>(base) & 15) || (C * 2) % 16) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    const cuuint32_t box[2] = {8u, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1u, 1u};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 // the fused MRF kernel with CUDA events around the kernel proper (the tile-descriptor helper launch stays outside)
 cudaError_t mrf3_launch_timed(vits_handle* h, const Mrf3Args& m, const Mrf3Cfg& c, int stage) {
@@ -608,6 +583,10 @@ int vits_set_option(vits_handle* h, const char* key, double value) {
     } else if (k == "num_sms") {
         if (value < 1) return fail(h, VITS_E_INVALID, "num_sms must be >= 1");
         h->num_sms = (int)value;                 // test hook: persistent grids use this many CTAs
+    } else if (k == "conv_tma") {
+        g_tc_tma = value != 0;                   // experiment switch of conv_tc.cuh (process-wide): TMA or cp.async activation loader
+    } else if (k == "conv_tma_max_cin") {
+        g_tc_tma_max_cin = (int)value;
     } else if (k == "conv_nepi") {
         if (value != 8 && value != 12) return fail(h, VITS_E_INVALID, "conv_nepi must be 8 or 12");
         g_tc_nepi_xb = (int)value;               // experiment switch of conv_tc.cuh (process-wide)

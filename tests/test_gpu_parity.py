@@ -515,10 +515,11 @@ def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
     assert np.isfinite(outs[1][0]).all() and np.array_equal(outs[0][0], outs[1][0])
 
 
-@pytest.mark.parametrize("preset", ["medium", "x_low"])
-def test_tma_fed_input_tiles_are_bit_identical(lib, tmp_path_factory, preset):
-    """The fused stage kernels take their input tiles by TMA (cp.async.bulk.tensor boxes, default) or through the cp.async loader warp
-    (`mrf_tma` = 0).  Same operand bytes in shared memory -> bit-identical audio.  The lengths put utterance starts and ends inside
+@pytest.mark.parametrize("preset,option", [("medium", "mrf_tma"), ("x_low", "mrf_tma"), ("medium", "conv_tma"), ("high", "conv_tma")])
+def test_tma_fed_input_tiles_are_bit_identical(lib, tmp_path_factory, preset, option):
+    """The fused stage kernels (`mrf_tma`) and every conv_tc launch on bf16 operand rows (`conv_tma`: coupling flow, ConvTranspose,
+    unfused stages) take their activation tiles by TMA (cp.async.bulk.tensor boxes, default) or through cp.async loader warps
+    (option = 0).  Same operand bytes in shared memory -> bit-identical audio.  The lengths put utterance starts and ends inside
     tiles (rows of the neighbouring utterance must be zeroed after the TMA delivered them), the first utterance at the start of the
     array and the last at its end (rows outside the array: zeros from the TMA unit), and a one-id utterance shorter than any halo."""
     from phoonnx_b200.session import B200Session
@@ -534,11 +535,15 @@ def test_tma_fed_input_tiles_are_bit_identical(lib, tmp_path_factory, preset):
     for opt in (0, 1):
         for chunk in (None, 900):                      # one chunk, and several (the tensor map follows the chunk's row count)
             sess = B200Session(p, precision="bf16")
-            sess.engine.set_option("mrf_tma", opt)
+            sess.engine.set_option(option, opt)
+            if option == "conv_tma":
+                sess.engine.set_option("conv_tma_max_cin", 4096)     # every launch on bf16 rows, the coupling flow's 192 channels too
             if chunk:
                 sess.engine.set_option("max_chunk_frames", chunk)
             a, alen = sess.synthesize_packed(feed)
             outs.append((a.copy(), alen.copy()))
+    sess.engine.set_option(option, 1)                 # conv_tma* are process-wide: leave the defaults behind
+    sess.engine.set_option("conv_tma_max_cin", 128)
     for o in outs[1:]:
         assert np.array_equal(outs[0][1], o[1])
         assert np.isfinite(o[0]).all() and np.array_equal(outs[0][0], o[0])
