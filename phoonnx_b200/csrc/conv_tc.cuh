@@ -340,6 +340,11 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcCfg& c, u
     // gate outputs straight to bf16 operand rows (lrelu slope 1 = identity; 16-byte aligned rows)
     const bool gate_direct = (EPI == EPI_GATE) && a.outb != nullptr && a.outb_slope == 1.f && (a.ldo % 8 == 0) && (a.ocol % 8 == 0);
     const float* sBias = reinterpret_cast<const float*>(smem + c.epi_off) + c.nepi * (32 * TC_EPI_PITCH);   // this N tile's bias
+    // (round 2, measured and removed: storing bf16 operand rows straight from registers -- thread = row, 16 contiguous bytes per 8
+    // channels, residual rows read the same way, no shared-memory transpose -- is bit-identical and SLOWER: medium decoder 182.5 vs
+    // 179.2 ms per step, `high` 161.1 vs 159.5 (profiles/r02z_ab_conv_direct_epilogue*.log).  A warp-wide 16-byte access that touches
+    // 32 different 128-byte lines costs the LSU 32 wavefronts; the transpose's coalesced 8-byte stores cost 2-4.  The gate epilogue
+    // keeps its direct stores: there the alternative was a second phase, not a cheaper one.)
     uint32_t it = 0;
     int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, it++) {
