@@ -949,7 +949,11 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     // no-swizzle layout), so the TMA unit fetches a 32-byte sector per row and plane and uses half of it; measured (profiles/r02y):
     // the 32-128-channel decoder launches gain 1.5 % (their loader warps' LDGSTS stream no longer paces the epilogue's loads through
     // the LSU queue), the 192-channel coupling-flow convs lose 8 % (52 KB tiles: the doubled sector traffic shows).
-    c.tma = (a.xb && !a.split3 && a.xb_rows > 0 && g_tc_tma && a.cin <= g_tc_tma_max_cin && tmap_encoder() != nullptr) ? 1 : 0;
+    // Not in latency mode (a launch of a few tiles, e.g. TTSVoice's one utterance per call): every launch carries its own tensor map, and
+    // the TMA unit's first fetch of that descriptor is a ~1 us round trip per launch that the cp.async loader does not pay (C1: 1.82 ->
+    // 1.87 ms per call with TMA everywhere).
+    c.tma = (a.xb && !a.split3 && a.xb_rows > 0 && g_tc_tma && a.cin <= g_tc_tma_max_cin && tmap_encoder() != nullptr &&
+             (num_sms <= 0 || (long)a.ntiles * 2 > (long)num_sms)) ? 1 : 0;
     c.nboxes = 1; c.box_rows = 0;
     if (c.tma) {
         // a whole number of equal boxes of a multiple of 8 rows each (<= 256, the TMA box limit): planes stay 128-byte aligned

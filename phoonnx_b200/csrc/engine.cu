@@ -1036,6 +1036,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             }
             if (!ok) continue;
             const bool want_post = (i == A.n_ups - 1) && h->opts["no_fused_post"] == 0 && co <= 64;
+            // TMA input tiles only when the launch has more tiles than half the SMs (latency mode keeps the cp.async loader: conv_tc.cuh)
+            const bool many_tiles = (long)Fr * rates[i + 1] / 512 * 2 > (long)h->num_sms;
             const int nbp = (int)(h->opts.count("mrf_nb") ? h->opts["mrf_nb"] : (co == 32 ? 4 : 2));
             const auto& U = h->ups[i];
             const bool can_up = i >= 1 && mrf_on[i] == 3 && U.rate == 4 && U.A.wtc && U.B.wtc && h->opts["no_fused_ups"] == 0;
@@ -1043,7 +1045,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             for (int tryu = can_up ? 1 : 0; tryu >= 0 && !done; tryu--) {
                 m3.up_u = tryu ? U.rate : 0; m3.up_cin = tryu ? U.A.cin : 0;
                 for (int tryp = want_post ? 1 : 0; tryp >= 0 && !done; tryp--)
-                    if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0, use_tma)) {
+                    if (mrf3_plan(m3, mrf3_cfg[i + 1], nbp, tryp != 0, use_tma && many_tiles)) {
                         mrf_on[i + 1] = 3; up_fused[i + 1] = tryu; if (tryp) post_fused = true; done = true;
                     }
             }
