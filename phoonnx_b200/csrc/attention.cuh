@@ -32,6 +32,7 @@ template <int NC>   // dk == 16 * NC
 __global__ void __launch_bounds__(AT_THREADS) k_rel_attention_tiled(
     const float* __restrict__ qkv, const float* __restrict__ Ek, const float* __restrict__ Ev,
     float* __restrict__ out, const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int H, int window) {
+    pdl_enter();
     constexpr int DK = 16 * NC;
     extern __shared__ __align__(16) float sm_att[];
     float* Qt = sm_att;                       // [DK][AT_LD]  q^T / sqrt(dk)
@@ -212,7 +213,7 @@ static inline bool attention_tiled_launch(const float* qkv, const float* Ek, con
             if (*err != cudaSuccess) return true;                                                                     \
             attr_done[dev] = true;                                                                                    \
         }                                                                                                             \
-        k_rel_attention_tiled<NC><<<grid, AT_THREADS, smem, st>>>(qkv, Ek, Ev, out, cu, tile_cu64, B, H, window);     \
+        launch_k(k_rel_attention_tiled<NC>, grid, AT_THREADS, smem, st, qkv, Ek, Ev, out, cu, tile_cu64, B, H, window);     \
         break;                                                                                                        \
     }
     switch (dk / 16) {
@@ -324,6 +325,7 @@ template <int DK>
 __global__ void __launch_bounds__(AT2_THREADS, 2) k_rel_attention_mma(
     const float* __restrict__ qkv, const float* __restrict__ Ek, const float* __restrict__ Ev,
     float* __restrict__ out, const int4* __restrict__ tdesc64, int H, int window) {
+    pdl_enter();
     constexpr int P = DK + 8;                 // bf16 elements per staged row: 16-byte segments of 8 consecutive rows hit 8 distinct bank groups
     constexpr int NTO = DK / 8;               // output n-tiles (8 channels each)
     extern __shared__ __align__(16) uint8_t sm_at2[];
@@ -545,7 +547,7 @@ static inline bool attention_mma_launch(const float* qkv, const float* Ek, const
             if (*err != cudaSuccess) return true;                                                                     \
             attr_done[dev] = true;                                                                                    \
         }                                                                                                             \
-        k_rel_attention_mma<DKV><<<grid, AT2_THREADS, smem, st>>>(qkv, Ek, Ev, out, tdesc64, H, window);              \
+        launch_k(k_rel_attention_mma<DKV>, grid, AT2_THREADS, smem, st, qkv, Ek, Ev, out, tdesc64, H, window);              \
         break;                                                                                                        \
     }
     switch (dk) {

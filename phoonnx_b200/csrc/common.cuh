@@ -16,6 +16,16 @@ enum OutAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 // Rows of utterance b are [cu[b]*rate, cu[b+1]*rate); samples outside the utterance read 0
 // (the zero padding of every Conv1d on the path; the decoder is unmasked, models.py:720,
 // so B=1 semantics == zero padding at utterance edges).
+// ---- programmatic dependent launch (PDL).  Every kernel of the engine starts with pdl_enter(): wait for the preceding grid of the
+// stream to complete and flush (griddepcontrol.wait -- a no-op when the launch carries no programmatic dependency), then allow the
+// NEXT grid to be launched (griddepcontrol.launch_dependents): its CTAs are scheduled while this grid runs and sit in their own
+// pdl_enter() until this grid is done.  What overlaps is the launch latency only -- no kernel touches its inputs early -- which is what a
+// one-utterance call consists of: ~150 dependent launches of a few CTAs each (bench C1).  Host side: launch_k() below.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct ConvArgs {
     const float* x;  int ldx;  int xcol;  int cin;
     int ntaps;  int toff[CONV_MAX_TAPS];
@@ -76,4 +86,18 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- host: every launch of the engine goes through here (PDL attribute; engine option "pdl" = 0 launches plainly)
+static int g_pdl = 1;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }

@@ -302,6 +302,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // per role per tile (r01d ncu: 18 % of all stall samples sat on that search and the geometry loads behind it)
 __global__ void k_tile_desc(const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int rate, int ntiles, int tm,
                             int4* __restrict__ out) {
+    pdl_enter();
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= ntiles) return;
     const int b = find_segment(tile_cu, B, tile);
@@ -311,6 +312,7 @@ __global__ void k_tile_desc(const int* __restrict__ cu, const int* __restrict__ 
 
 // [rows][n16][8] -> [n16 / wt][rows][wt][8]  (rows = tap x 8-channel chunk): the N-tiled weight copy, built once at load time
 __global__ void k_retile_weights(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int n16, int wt) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte (8-element) unit per thread
     if (i >= rows * n16) return;
     const long r = i / n16; const int n = (int)(i - r * n16);
@@ -579,6 +581,7 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
 // heaviest variant's sake and stalling on instruction fetch -- r01d ncu `no_inst`)
 template <int EPI, int RESK, int ACC>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c, const __grid_constant__ CUtensorMap tmap) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sW = smem + (size_t)c.nabuf * c.a_bytes;
@@ -1087,6 +1090,6 @@ static inline cudaError_t conv_tc_launch(const ConvArgs& a, int num_sms, cudaStr
         cfg.attrs = at; cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, fn, a, c, tm);
     }
-    fn<<<grid, TC_THREADS, c.smem_bytes, st>>>(a, c, tm);
+    launch_k(fn, grid, TC_THREADS, c.smem_bytes, st, a, c, tm);
     return cudaGetLastError();
 }

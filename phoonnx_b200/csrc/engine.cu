@@ -209,7 +209,7 @@ int mkconv(vits_handle* h, ConvP& c, const std::string& name, int cin, int n, co
             CK(h, cudaMalloc(&d, (size_t)rows * c.npad16 * 16));
             h->owned.push_back(d);
             const long units = rows * c.npad16;
-            k_retile_weights<<<(unsigned)((units + 255) / 256), 256, 0, h->stream>>>(src, d, rows, c.npad16, wt);
+            launch_k(k_retile_weights, (unsigned)((units + 255) / 256), 256, 0, h->stream, src, d, rows, c.npad16, wt);
             CK(h, cudaGetLastError());
             *dst = d;
             return 0;
@@ -298,7 +298,7 @@ int launch_conv(vits_handle* h, ConvArgs& a, const Tiles& T, bool allow_tc) {
     a.tile_cu = T.t64; a.ntiles = T.n64;
     if (T.n64 == 0) return 0;
     dim3 grid(T.n64, (a.n + CF_TN - 1) / CF_TN);
-    k_conv_f32<<<grid, 256, 0, h->stream>>>(a);
+    launch_k(k_conv_f32, grid, 256, 0, h->stream, a);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -337,7 +337,7 @@ int launch_ln(vits_handle* h, const float* in, float* out, const LnP& ln, int ro
     if (rows == 0) return 0;
     if (C % 64 == 0 && C <= 256 && (mode != 1 || h->A.dp_kernel == 3) && h->opts["ln_scalar"] == 0) {
         // 64-bit accesses (kernels_f32.cuh k_layernorm_v2); every exported voice's widths (192, 256) qualify, x_low's 96 does not
-#define LN2_LAUNCH(N_) k_layernorm_v2<N_><<<(rows + 3) / 4, 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, mode, dw ? dw->dw_w : nullptr, \
+#define LN2_LAUNCH(N_) launch_k(k_layernorm_v2<N_>, (rows + 3) / 4, 128, 0, h->stream, in, out, ln.g, ln.b, rows, mode, dw ? dw->dw_w : nullptr, \
                            dw ? dw->dw_b : nullptr, dw ? dw->dil : 1, ptr<int2>(h->rowpos))
         switch (C / 64) { case 1: LN2_LAUNCH(1); break; case 2: LN2_LAUNCH(2); break; case 3: LN2_LAUNCH(3); break; default: LN2_LAUNCH(4); break; }
 #undef LN2_LAUNCH
@@ -346,7 +346,7 @@ int launch_ln(vits_handle* h, const float* in, float* out, const LnP& ln, int ro
         return 0;
     }
     const int rpw = h->opts.count("ln_rpw") ? (int)h->opts["ln_rpw"] : 1;
-#define LN_LAUNCH(R_) k_layernorm<R_><<<(rows + 4 * R_ - 1) / (4 * R_), 128, 0, h->stream>>>(in, out, ln.g, ln.b, rows, C, mode, \
+#define LN_LAUNCH(R_) launch_k(k_layernorm<R_>, (rows + 4 * R_ - 1) / (4 * R_), 128, 0, h->stream, in, out, ln.g, ln.b, rows, C, mode, \
                           dw ? dw->dw_w : nullptr, dw ? dw->dw_b : nullptr, h->A.dp_kernel, dw ? dw->dil : 1, ptr<int2>(h->rowpos))
     if (rpw >= 4) LN_LAUNCH(4); else if (rpw == 2) LN_LAUNCH(2); else LN_LAUNCH(1);
 #undef LN_LAUNCH
@@ -453,7 +453,7 @@ cudaError_t mrf3_launch_timed(vits_handle* h, const Mrf3Args& m, const Mrf3Cfg& 
 int make_d128(vits_handle* h, Tiles& T, int4* dst) {
     T.d128 = dst;
     if (T.n128 <= 0) return 0;
-    k_tile_desc<<<(T.n128 + 255) / 256, 256, 0, h->stream>>>(T.cu, T.t128, T.B, T.rate, T.n128, TC_M, dst);
+    launch_k(k_tile_desc, (T.n128 + 255) / 256, 256, 0, h->stream, T.cu, T.t128, T.B, T.rate, T.n128, TC_M, dst);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -583,6 +583,8 @@ int vits_set_option(vits_handle* h, const char* key, double value) {
     } else if (k == "num_sms") {
         if (value < 1) return fail(h, VITS_E_INVALID, "num_sms must be >= 1");
         h->num_sms = (int)value;                 // test hook: persistent grids use this many CTAs
+    } else if (k == "pdl") {
+        g_pdl = value != 0;                      // programmatic dependent launch of every kernel (common.cuh launch_k; process-wide)
     } else if (k == "conv_tma") {
         g_tc_tma = value != 0;                   // experiment switch of conv_tc.cuh (process-wide): TMA or cp.async activation loader
     } else if (k == "conv_tma_max_cin") {
@@ -808,11 +810,11 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
     Tiles T = tb.get(ptr<int>(h->tile_t), 1);
     if ((rc = ensure(h, h->tdesc_t, (size_t)std::max(T.n128 + T.n64, 1) * sizeof(int4))) || (rc = make_d128(h, T, ptr<int4>(h->tdesc_t)))) return rc;
     if (T.n64 > 0) {     // 64-row tile descriptors (attention q tiles) behind the 128-row ones
-        k_tile_desc<<<(T.n64 + 255) / 256, 256, 0, st>>>(T.cu, T.t64, T.B, 1, T.n64, 64, ptr<int4>(h->tdesc_t) + T.n128);
+        launch_k(k_tile_desc, (T.n64 + 255) / 256, 256, 0, st, T.cu, T.t64, T.B, 1, T.n64, 64, ptr<int4>(h->tdesc_t) + T.n128);
         h->launches++;
     }
     if ((rc = ensure(h, h->rowpos, (size_t)R * sizeof(int2)))) return rc;
-    k_row_pos<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(T.cu, B, (int)R, ptr<int2>(h->rowpos));
+    launch_k(k_row_pos, (unsigned)((R + 255) / 256), 256, 0, st, T.cu, B, (int)R, ptr<int2>(h->rowpos));
     h->launches++;
     const int* d_sid = ptr<int>(h->sid);
     float *x = ptr<float>(h->x), *y = ptr<float>(h->y), *qkv = ptr<float>(h->qkv), *att = ptr<float>(h->att),
@@ -821,7 +823,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
     // ---- text encoder (models.py:198-209, attentions.py:60-74)
     {
         long n4 = R * (H / 4);
-        k_embed<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ptr<int>(h->ids), h->emb, x, (int)R, H, sqrtf((float)H));
+        launch_k(k_embed, (unsigned)((n4 + 255) / 256), 256, 0, st, ptr<int>(h->ids), h->emb, x, (int)R, H, sqrtf((float)H));
         h->launches++;
         const int dk = H / A.n_heads, nrel = 2 * A.window + 1;
         for (int i = 0; i < A.n_layers; i++) {
@@ -837,7 +839,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
                 attention_tiled_launch(qkv, L.rel_k, L.rel_v, att, T.cu, T.t64, T.n64, B, H, A.n_heads, dk, A.window, st, &ae)) {
                 if (ae != cudaSuccess) return fail(h, VITS_E_CUDA, "attention launch: %s", cudaGetErrorString(ae));
             } else {
-                k_rel_attention<<<dim3((R + 3) / 4, A.n_heads), 128, 4 * (dk + nrel) * sizeof(float), st>>>(
+                launch_k(k_rel_attention, dim3((R + 3) / 4, A.n_heads), 128, 4 * (dk + nrel) * sizeof(float), st, 
                     qkv, L.rel_k, L.rel_v, att, T.cu, B, (int)R, H, A.n_heads, dk, A.window);
             }
             h->launches++;
@@ -866,7 +868,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         if ((rc = run_dds(h, h->dp_dds, d0, d1, y, (int)R, Fd, T))) return rc;
         a = base_args(h->dp_proj, d0, Fd, 0, gdp, Fd, 0);
         if ((rc = launch_conv_text(h, h->dp_proj, a, T))) return rc;
-        k_noise_dp<<<(R + 255) / 256, 256, 0, st>>>(z0, z1, d_inj, dp_stride, T.cu, B, (int)R, h->scales[2], seed, h->utt_base);
+        launch_k(k_noise_dp, (R + 255) / 256, 256, 0, st, z0, z1, d_inj, dp_stride, T.cu, B, (int)R, h->scales[2], seed, h->utt_base);
         h->launches++;
         if (h->opts.count("debug_keep_noise_dp") && h->opts["debug_keep_noise_dp"] != 0) {
             // test hook: the duration predictor's noise (models.py:111) as drawn, [z0 | z1], before the flows overwrite it
@@ -878,16 +880,16 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
             std::swap(z0, z1);                                   // Flip (modules.py:386)
             auto& cf = h->cflows[k];
             long n = R * Fd;
-            k_cf_pre<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z0, cf.pre_w, cf.pre_b, gdp, d0, (int)R, Fd);
+            launch_k(k_cf_pre, (unsigned)((n + 255) / 256), 256, 0, st, z0, cf.pre_w, cf.pre_b, gdp, d0, (int)R, Fd);
             h->launches++;
             if ((rc = run_dds(h, cf.dds, d0, d1, y, (int)R, Fd, T))) return rc;
             a = base_args(cf.proj, d0, Fd, 0, hp, 32, 0);
             if ((rc = launch_conv(h, a, T, false))) return rc;
-            k_spline_inverse<<<(R + 127) / 128, 128, 0, st>>>(hp, 32, z1, (int)R, 1.f / sqrtf((float)Fd));
+            launch_k(k_spline_inverse, (R + 127) / 128, 128, 0, st, hp, 32, z1, (int)R, 1.f / sqrtf((float)Fd));
             h->launches++;
         }
         std::swap(z0, z1);                                       // final Flip, then EA on channel 0
-        k_ea_logw<<<(R + 255) / 256, 256, 0, st>>>(z0, h->ea_m, expf(-h->ea_logs), logw, (int)R);
+        launch_k(k_ea_logw, (R + 255) / 256, 256, 0, st, z0, h->ea_m, expf(-h->ea_logs), logw, (int)R);
         h->launches++;
     } else {
         float *d0 = ptr<float>(h->d0), *d1 = ptr<float>(h->d1);
@@ -895,7 +897,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         if (A.n_speakers > 1) {
             CK(h, cudaMemcpyAsync(y, x, R * H * 4, cudaMemcpyDeviceToDevice, st));
             long n = R * H;
-            k_add_rowbias<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, h->dp_cond_tab, d_sid, T.cu, B, (int)R, H);
+            launch_k(k_add_rowbias, (unsigned)((n + 255) / 256), 256, 0, st, y, h->dp_cond_tab, d_sid, T.cu, B, (int)R, H);
             h->launches++;
             xin = y;
         }
@@ -909,7 +911,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
         if ((rc = launch_conv(h, a, T, false))) return rc;
     }
     // ---- length regulation (integer path)
-    k_durations<<<B, 256, 0, st>>>(logw, h->scales[1], T.cu, ptr<int>(h->dur), ptr<int>(h->cum), ptr<int>(h->ylen));
+    launch_k(k_durations, B, 256, 0, st, logw, h->scales[1], T.cu, ptr<int>(h->dur), ptr<int>(h->cum), ptr<int>(h->ylen));
     h->launches++;
     CK(h, cudaGetLastError());
     stage_end(h);
@@ -1103,13 +1105,13 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         float *P = ptr<float>(h->P), *fh = ptr<float>(h->fh), *facts = ptr<float>(h->facts), *fskip = ptr<float>(h->fskip);
         // ---- prior expansion + sampling (models.py:705-718)
         stage_begin(h, 1);
-        k_frame_index<<<(Fr + 255) / 256, 256, 0, st>>>(ptr<int>(h->cum), ptr<int>(h->tile_t), T1.cu, b_lo, nB, Fr, ptr<int>(h->fidx), ptr<int2>(h->fpos));
+        launch_k(k_frame_index, (Fr + 255) / 256, 256, 0, st, ptr<int>(h->cum), ptr<int>(h->tile_t), T1.cu, b_lo, nB, Fr, ptr<int>(h->fidx), ptr<int2>(h->fpos));
         h->launches++;
         {
             long n = (long)Fr * (C / 4);
             // test hook "debug_eps": m_p = logs_p = 0, so z_p IS the noise draw (times noise_scale) -- the statistical test of the device RNG
             const float* stats_in = (h->opts.count("debug_eps") && h->opts["debug_eps"] != 0) ? nullptr : ptr<float>(h->stats);
-            k_expand_sample<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_in, ptr<int>(h->fidx), ptr<int2>(h->fpos),
+            launch_k(k_expand_sample, (unsigned)((n + 255) / 256), 256, 0, st, stats_in, ptr<int>(h->fidx), ptr<int2>(h->fpos),
                                                                          d_injz, z_stride, h->scales[0], h->seed, h->utt_base, P, Fr, C);
             h->launches++;
         }
@@ -1316,7 +1318,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
             const Tiles Tl = TR[A.n_ups];
             if (Tl.n256 > 0 && !post_fused) {
                 size_t smem = (size_t)(CP_TILE + 6) * (h->post_c + 1) * sizeof(float);
-                k_conv_post<<<Tl.n256, 256, smem, st>>>(cur, h->post_c, h->post_w, Tl.cu, Tl.t256, nB, Tl.rate, 0.01f,
+                launch_k(k_conv_post, Tl.n256, 256, smem, st, cur, h->post_c, h->post_w, Tl.cu, Tl.t256, nB, Tl.rate, 0.01f,
                                                         audio + (int64_t)f_lo * hop);
                 h->launches++;
             }
@@ -1326,8 +1328,8 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         if (out_kind == 2) {
             // caller-side post-processing on device (voice.py:271-282, 88-91) for this chunk's utterances
             dim3 g(32, (unsigned)std::min(nB, 65535));
-            k_absmax<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo);
-            k_to_int16<<<g, 256, 0, st>>>(audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo, normalize, volume, audio16);
+            launch_k(k_absmax, g, 256, 0, st, audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo);
+            launch_k(k_to_int16, g, 256, 0, st, audio, ptr<int>(h->cu_y_dev) + b_lo, nB, hop, ptr<unsigned int>(h->peaks) + b_lo, normalize, volume, audio16);
             h->launches += 2;
             CK(h, cudaGetLastError());
         }

@@ -39,6 +39,7 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvArgs& a, int b, lo
 }
 
 __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
+    pdl_enter();
     __shared__ __align__(16) float As[CF_KC][CF_TM + 4];
     __shared__ __align__(16) float Bs[CF_KC][CF_TN];
     const int tid = threadIdx.x;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
 // ------------------------------------------------------------------------------------------
 __global__ void k_embed(const int* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
                         int rows, int H, float scale) {
+    pdl_enter();
     const int q = H >> 2;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * q) return;
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(128) k_rel_attention(const float* __restrict__
                                                        const float* __restrict__ Ev, float* __restrict__ out,
                                                        const int* __restrict__ cu, int B, int rows, int H,
                                                        int n_heads, int dk, int window) {
+    pdl_enter();
     extern __shared__ float sm[];   // per warp: q[dk] + qe[2w+1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nrel = 2 * window + 1;
@@ -237,6 +240,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // per row of the packed batch: {position inside its utterance, utterance length}; built once per vits_prepare so that the
 // per-row kernels below need no binary search over the utterance table (10 dependent L2 loads per warp, r01e profile)
 __global__ void k_row_pos(const int* __restrict__ cu, int B, int rows, int2* __restrict__ out) {
+    pdl_enter();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const int b = find_segment(cu, B, row);
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(128, 10) k_layernorm(const float* __restrict__
                                                    int rows, int C, int mode,
                                                    const float* __restrict__ dw_w, const float* __restrict__ dw_b,
                                                    int dw_k, int dw_dil, const int2* __restrict__ rowpos) {
+    pdl_enter();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * 4 + warp) * LN_RPW;
     if (row0 >= rows) return;
@@ -366,6 +371,7 @@ __global__ void __launch_bounds__(128, 8) k_layernorm_v2(const float* __restrict
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, int mode, const float* __restrict__ dw_w,
                                                         const float* __restrict__ dw_b, int dw_dil, const int2* __restrict__ rowpos) {
+    pdl_enter();
     constexpr int C = 64 * NV2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + warp;
@@ -423,6 +429,7 @@ __global__ void __launch_bounds__(128, 8) k_layernorm_v2(const float* __restrict
 // x[t, c] += tab[idx[b]][c]   (DurationPredictor speaker conditioning, models.py:153-155)
 __global__ void k_add_rowbias(float* __restrict__ x, const float* __restrict__ tab, const int* __restrict__ idx,
                               const int* __restrict__ cu, int B, int rows, int C) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * C) return;
     const int r = (int)(i / C), c = (int)(i % C);
@@ -463,6 +470,7 @@ __device__ __forceinline__ float normal_at(uint64_t seed, uint32_t domain, uint6
 __global__ void k_noise_dp(float* __restrict__ z0, float* __restrict__ z1, const float* __restrict__ inj,
                            long stride, const int* __restrict__ cu, int B, int rows, float noise_w,
                            uint64_t seed, uint64_t utt_base) {
+    pdl_enter();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const int b = find_segment(cu, B, r);
@@ -483,6 +491,7 @@ __global__ void k_noise_dp(float* __restrict__ z0, float* __restrict__ z1, const
 // h[t, c] = w[c] * x0[t] + b[c] + g[t, c]
 __global__ void k_cf_pre(const float* __restrict__ x0, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ g, float* __restrict__ h, int rows, int C) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * C) return;
     const int r = (int)(i / C), c = (int)(i % C);
@@ -496,6 +505,7 @@ __global__ void k_cf_pre(const float* __restrict__ x0, const float* __restrict__
 #define SPL_K 10
 __global__ void k_spline_inverse(const float* __restrict__ hp, int ldh, float* __restrict__ x1, int rows,
                                  float inv_sqrt_fc) {
+    pdl_enter();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const float y = x1[r];
@@ -555,6 +565,7 @@ __global__ void k_spline_inverse(const float* __restrict__ hp, int ldh, float* _
 
 // ElementwiseAffine reverse on the logw channel (modules.py:408): logw = (z - m) * exp(-logs)
 __global__ void k_ea_logw(const float* __restrict__ z, float m, float neg_logs_exp, float* __restrict__ logw, int rows) {
+    pdl_enter();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows) logw[r] = (z[r] - m) * neg_logs_exp;
 }
@@ -568,6 +579,7 @@ __global__ void k_ea_logw(const float* __restrict__ z, float m, float neg_logs_e
 __global__ void __launch_bounds__(256) k_durations(const float* __restrict__ logw, float length_scale,
                                                    const int* __restrict__ cu, int* __restrict__ dur,
                                                    int* __restrict__ cum, int* __restrict__ y_len) {
+    pdl_enter();
     __shared__ int wsum[8];
     __shared__ long long carry_s;      // 64-bit: 2^20 ids x 10^6 frames would wrap an int; cum / y_len saturate at INT_MAX and the host rejects
     const int b = blockIdx.x;
@@ -606,6 +618,7 @@ __global__ void __launch_bounds__(256) k_durations(const float* __restrict__ log
 // frame j of utterance b -> phoneme index: first t with cum[t] > j (searchsorted right), -1 if none
 __global__ void k_frame_index(const int* __restrict__ cum, const int* __restrict__ cu_t, const int* __restrict__ cu_y,
                               int b_lo, int nB, int frames, int* __restrict__ fidx, int2* __restrict__ fpos) {
+    pdl_enter();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= frames) return;
     const int lb = find_segment(cu_y, nB, f);
@@ -629,6 +642,7 @@ __global__ void k_frame_index(const int* __restrict__ cum, const int* __restrict
 __global__ void k_expand_sample(const float* __restrict__ stats, const int* __restrict__ fidx, const int2* __restrict__ fpos,
                                 const float* __restrict__ inj, long stride, float noise_scale, uint64_t seed,
                                 uint64_t utt_base, float* __restrict__ zp, int frames, int C) {
+    pdl_enter();
     const int c4n = C >> 2;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)frames * c4n) return;
@@ -666,6 +680,7 @@ __global__ void k_expand_sample(const float* __restrict__ stats, const int* __re
 __global__ void __launch_bounds__(256) k_conv_post(const float* __restrict__ x, int C, const float* __restrict__ w /*[7][C]*/,
                                                    const int* __restrict__ cu, const int* __restrict__ tile_cu, int B,
                                                    int rate, float slope, float* __restrict__ audio) {
+    pdl_enter();
     extern __shared__ float sx[];      // [(CP_TILE + 6)][C + 1]
     __shared__ float sw[7 * 64];
     const int tile = blockIdx.x;
@@ -703,6 +718,7 @@ __global__ void __launch_bounds__(256) k_conv_post(const float* __restrict__ x, 
 // ------------------------------------------------------------------------------------------
 __global__ void k_absmax(const float* __restrict__ audio, const int* __restrict__ cu, int B, int rate,
                          unsigned int* __restrict__ peak_bits) {
+    pdl_enter();
     // grid: (chunks, min(B, 65535)); utterances beyond the grid's y extent are covered by the loop
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
@@ -716,6 +732,7 @@ __global__ void k_absmax(const float* __restrict__ audio, const int* __restrict_
 __global__ void k_to_int16(const float* __restrict__ audio, const int* __restrict__ cu, int B, int rate,
                            const unsigned int* __restrict__ peak_bits, int normalize, float volume,
                            int16_t* __restrict__ out) {
+    pdl_enter();
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const long s0 = (long)cu[b] * rate, n = (long)(cu[b + 1] - cu[b]) * rate;
         const float peak = __uint_as_float(peak_bits[b]);

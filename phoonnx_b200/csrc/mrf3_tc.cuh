@@ -113,6 +113,7 @@ __device__ __forceinline__ void mrf3_step(int step, int nrb, int interleave, int
 
 template <int C>
 __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, const Mrf3Cfg c, const __grid_constant__ CUtensorMap tmap) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sX = smem;                                       // lrelu(x)  bf16 K-major chunks [C/8][rx][8]
     uint8_t* sX1 = sX + c.x_bytes;                            // lrelu(x1) bf16 K-major chunks [C/8][rx1][8]; then the conv_post operand
@@ -766,14 +767,14 @@ static inline cudaError_t mrf3_launch_t(const Mrf3Args& a, const Mrf3Cfg& c, con
     int gx = num_sms;                       // one persistent CTA per SM (TMEM: 512 columns each)
     if (gx > a.ntiles) gx = a.ntiles;
     if (gx < 1) return cudaSuccess;
-    k_mrf3_tc<C><<<gx, MRF3_THREADS, c.smem_bytes, st>>>(a, c, tmap);
+    launch_k(k_mrf3_tc<C>, gx, MRF3_THREADS, c.smem_bytes, st, a, c, tmap);
     return cudaGetLastError();
 }
 
 // the per-tile descriptors the kernel reads (launched separately so that the kernel proper can be timed alone)
 static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c, cudaStream_t st) {
     if (a.ntiles < 1) return cudaSuccess;
-    k_mrf_tiles<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
+    launch_k(k_mrf_tiles, (a.ntiles + 255) / 256, 256, 0, st, a.cu, a.tile_cu, a.B, a.rate, a.ntiles, c.t_step, c.post_halo,
                                                          const_cast<int4*>(a.tdesc));
     return cudaGetLastError();
 }

@@ -8,6 +8,7 @@
 // {first row of the utterance, its rows, first stage-output row of the tile (o0), utterance}
 __global__ void k_mrf_tiles(const int* __restrict__ cu, const int* __restrict__ tile_cu, int B, int rate, int ntiles,
                             int t_step, int post_halo, int4* __restrict__ out) {
+    pdl_enter();
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= ntiles) return;
     const int b = find_segment(tile_cu, B, tile);

@@ -515,11 +515,12 @@ def test_cluster_weight_multicast_is_bit_identical(lib, tmp_path_factory):
     assert np.isfinite(outs[1][0]).all() and np.array_equal(outs[0][0], outs[1][0])
 
 
-@pytest.mark.parametrize("preset,option", [("medium", "mrf_tma"), ("x_low", "mrf_tma"), ("medium", "conv_tma"), ("high", "conv_tma")])
+@pytest.mark.parametrize("preset,option", [("medium", "mrf_tma"), ("x_low", "mrf_tma"), ("medium", "conv_tma"), ("high", "conv_tma"), ("medium", "pdl")])
 def test_tma_fed_input_tiles_are_bit_identical(lib, tmp_path_factory, preset, option):
     """The fused stage kernels (`mrf_tma`) and every conv_tc launch on bf16 operand rows (`conv_tma`: coupling flow, ConvTranspose,
     unfused stages) take their activation tiles by TMA (cp.async.bulk.tensor boxes, default) or through cp.async loader warps
-    (option = 0).  Same operand bytes in shared memory -> bit-identical audio.  The lengths put utterance starts and ends inside
+    (option = 0).  Same operand bytes in shared memory -> bit-identical audio.  `pdl`: every kernel launched with the programmatic-
+    dependent-launch attribute (default) or plainly (0): only launch latency may overlap, never data.  The lengths put utterance starts and ends inside
     tiles (rows of the neighbouring utterance must be zeroed after the TMA delivered them), the first utterance at the start of the
     array and the last at its end (rows outside the array: zeros from the TMA unit), and a one-id utterance shorter than any halo."""
     from phoonnx_b200.session import B200Session
