@@ -21,6 +21,10 @@ enum OutAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 // NEXT grid to be launched (griddepcontrol.launch_dependents): its CTAs are scheduled while this grid runs and sit in their own
 // pdl_enter() until this grid is done.  What overlaps is the launch latency only -- no kernel touches its inputs early -- which is what a
 // one-utterance call consists of: ~150 dependent launches of a few CTAs each (bench C1).  Host side: launch_k() below.
+// The two halves, for kernels with a prologue worth overlapping (conv_tc.cuh): trigger first, run everything that touches only
+// constants (barriers, tensor memory, bias, the weight ring), and wait only in the warps that read or write activations.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -581,7 +581,10 @@ __device__ __forceinline__ void tc_epilogue_scalar(const ConvArgs& a, const TcCf
 // heaviest variant's sake and stalling on instruction fetch -- r01d ncu `no_inst`)
 template <int EPI, int RESK, int ACC>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, const TcCfg c, const __grid_constant__ CUtensorMap tmap) {
-    pdl_enter();
+    // PDL: the prologue below (barriers, bias, tensor-memory allocation) and the whole weight ring read constants only, so they run
+    // while the preceding grid is still finishing; the epilogue and loader warps -- the ones that touch activations, tile descriptors
+    // or outputs -- call pdl_wait() first.  The MMA warp only follows their barriers.
+    pdl_trigger();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sW = smem + (size_t)c.nabuf * c.a_bytes;
@@ -640,10 +643,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
 
     if (warp < c.nepi) {
         // ================= epilogue (8 warps; 12 when the loader is the cp.async one) =================
+        pdl_wait();
         if constexpr (EPI < 0) tc_epilogue_scalar(a, c, tmem_base, bar_accfull0, bar_accempty0, warp, lane);
         else tc_epilogue<EPI, RESK, ACC>(a, c, smem, tmem_base, bar_accfull0, bar_accempty0, warp, lane, dbg_on);
     } else if (warp < TC_EPI_WARPS + TC_LOAD_WARPS) {
         // ================= activation loaders (the warps between the epilogue warps and warp 14) =================
+        pdl_wait();
         if (c.tma) {
             // ---- TMA loader (bf16 operand rows): the first loader warp alone.  An 8-channel plane of the K-major no-swizzle tile is a
             // [rows_a x 16 bytes] box of the 2-D tensor [rows, ldxb]: cin/8 x nboxes cp.async.bulk.tensor per (tile, K slice), issued by

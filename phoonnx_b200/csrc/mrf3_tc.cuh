@@ -113,7 +113,10 @@ __device__ __forceinline__ void mrf3_step(int step, int nrb, int interleave, int
 
 template <int C>
 __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, const Mrf3Cfg c, const __grid_constant__ CUtensorMap tmap) {
-    pdl_enter();
+    // PDL as in k_conv_tc: barriers, biases, conv_post weights, tensor memory and the weight producer only read constants and run
+    // under the preceding grid's tail; the epilogue warps and the input loader call pdl_wait() before they touch the tile
+    // descriptors (written by k_mrf_tiles just before), activations or outputs.
+    pdl_trigger();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sX = smem;                                       // lrelu(x)  bf16 K-major chunks [C/8][rx][8]
     uint8_t* sX1 = sX + c.x_bytes;                            // lrelu(x1) bf16 K-major chunks [C/8][rx1][8]; then the conv_post operand
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 
     if (warp < MRF3_EPI_WARPS) {
         // ===================== epilogues (512 threads) =====================
+        pdl_wait();
         // work item of this warp: rows 128*bb + 32*q + lane, channels [32*cg, 32*cg + 32)
         const int q = warp & 3, item = warp >> 2;
         const int bb = item / NG, cg = item - bb * NG;
@@ -596,7 +600,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
             if (post && it > 0) issue_post(it - 1);          // the last tile's conv_post
         }
     } else {
-        // ===================== input-row loader (warp 18): cp.async, 16 B per lane, zero fill outside the utterance =====================
+        // ===================== input-row loader (warp 18): TMA boxes, or cp.async 16 B per lane with zero fill outside the utterance =====================
+        pdl_wait();
         uint32_t n_free = 0;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
         const uint32_t el = tc::elect_flag();
