@@ -32,7 +32,9 @@
 #define TC_EXPERIMENT_SKIP_RESB 0      // timing experiment only (wrong results): skip the bf16 residual prefetch
 #endif
 #define TC_M 128
-#define TC_LOAD_BATCH 8          // fp32 loader: (row, chunk) items whose 2 x LDG.128 are in flight per thread before any conversion
+#define TC_LOAD_BATCH 9          // fp32 loader: (row, chunk) items whose 2 x LDG.128 are in flight per thread before any conversion.  9 x 192
+                                 // threads cover the 130 x 12 items of a k = 3, 96-channel K slice in ONE memory round trip (8 left 24 items
+                                 // to a second one; the 128 x 12 items of a 1x1 slice need exactly 8 once the unused pad row is skipped)
 #define TC_EPI_WARPS 8
 #define TC_NFIXBAR 10               // fixed mbarriers behind the weight ring's (a_full, a_empty, acc_full, acc_empty, a_tma: two each)
 #define TC_LOAD_WARPS 6
@@ -47,6 +49,7 @@ struct TcCfg {
     int ntile;        // N columns per CTA (multiple of 16, <= 256)
     int tmem_cols;    // power of two >= 32
     int rows_a;       // activation rows held in smem (odd: conflict-free 16 B chunk scatter)
+    int rows_need;    // rows the MMAs actually read: 128 + (max tap offset - min tap offset); the rest of rows_a is padding, never loaded
     int min_off;      // smallest tap offset
     int piece_ch;     // channels per weight piece (<= 64)
     int cpt;          // pieces per tap
@@ -692,7 +695,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
         const int lt = tid - c.nepi * 32;
         const int nlt = c.nload * 32;                   // loader threads
         uint32_t it = 0;
-        const int items = c.rows_a * kc_total;
+        const int items = c.rows_need * kc_total;      // pad rows are never read by an MMA: not loaded (for a 1x1 conv the pad row alone
+                                                       // cost every K slice a second memory round trip: 129 x 12 items for 8 x 192 slots)
         const int dr = nlt / kc_total, dk = nlt - dr * kc_total;   // advance of (r, kc) per nlt items
         int4 dnext = ((int)blockIdx.x < a.ntiles) ? __ldg(a.tdesc + blockIdx.x) : make_int4(0, 0, 0, 0);
         const int lr0 = lt / kc_total, lk0 = lt - lr0 * kc_total;          // this thread's first (row, chunk) item
@@ -734,23 +738,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
             int r = lr0, kc = lk0;
             for (int base = lt; base < items; base += TC_LOAD_BATCH * nlt) {
                 float4 v0[TC_LOAD_BATCH], v1[TC_LOAD_BATCH];
-                int rr[TC_LOAD_BATCH], kk[TC_LOAD_BATCH];
-                bool ok[TC_LOAD_BATCH];
+                const int r_s = r, kc_s = kc;
 #pragma unroll
                 for (int u = 0; u < TC_LOAD_BATCH; u++) {
-                    rr[u] = r; kk[u] = kc;
-                    ok[u] = (base + u * nlt < items);
                     v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
-                    if (ok[u] && r >= tlo && r < thi) {
+                    if (base + u * nlt < items && r >= tlo && r < thi) {
                         const float4* src = reinterpret_cast<const float4*>(xbase + (long)r * a.ldx + kc * 8);
                         v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
                     }
                     r += dr; kc += dk;
                     if (kc >= kc_total) { kc -= kc_total; r++; }
                 }
+                int r2 = r_s, kc2 = kc_s;              // the same walk again (cheaper than keeping every item's row / chunk in registers)
 #pragma unroll
                 for (int u = 0; u < TC_LOAD_BATCH; u++) {
-                    if (!ok[u]) continue;
+                    const int ru = r2, ku = kc2;
+                    r2 += dr; kc2 += dk;
+                    if (kc2 >= kc_total) { kc2 -= kc_total; r2++; }
+                    if (base + u * nlt >= items) continue;
                     float4 a0 = v0[u], a1 = v1[u];
                     if (a.in_act) {
                         a0.x = leaky(a0.x, a.in_slope); a0.y = leaky(a0.y, a.in_slope); a0.z = leaky(a0.z, a.in_slope); a0.w = leaky(a0.w, a.in_slope);
@@ -759,7 +764,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                     uint4 pk;
                     pk.x = tc::pack_bf16(a0.x, a0.y); pk.y = tc::pack_bf16(a0.z, a0.w);
                     pk.z = tc::pack_bf16(a1.x, a1.y); pk.w = tc::pack_bf16(a1.z, a1.w);
-                    *reinterpret_cast<uint4*>(dstA + ((size_t)kk[u] * c.rows_a + rr[u]) * 16) = pk;
+                    *reinterpret_cast<uint4*>(dstA + ((size_t)ku * c.rows_a + ru) * 16) = pk;
                     if (a.split3) {
                         // lo plane: bf16(x - bf16(x)), exact subtraction in fp32
                         uint4 lo;
@@ -767,7 +772,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const ConvArgs a, con
                         lo.y = tc::pack_bf16(a0.z - tc::bf16_lo_f(pk.y), a0.w - tc::bf16_hi_f(pk.y));
                         lo.z = tc::pack_bf16(a1.x - tc::bf16_lo_f(pk.z), a1.y - tc::bf16_hi_f(pk.z));
                         lo.w = tc::pack_bf16(a1.z - tc::bf16_lo_f(pk.w), a1.w - tc::bf16_hi_f(pk.w));
-                        *reinterpret_cast<uint4*>(dstA + ((size_t)(kk[u] + kc_total) * c.rows_a + rr[u]) * 16) = lo;
+                        *reinterpret_cast<uint4*>(dstA + ((size_t)(ku + kc_total) * c.rows_a + ru) * 16) = lo;
                     }
                 }
             }
@@ -953,6 +958,7 @@ static inline bool conv_tc_plan(const ConvArgs& a, TcCfg& c, int num_sms = 0) {
     for (int i = 1; i < a.ntaps; i++) { mn = a.toff[i] < mn ? a.toff[i] : mn; mx = a.toff[i] > mx ? a.toff[i] : mx; }
     c.min_off = mn;
     int rows = TC_M + (mx - mn);
+    c.rows_need = rows;
     // TMA for activation tiles of up to g_tc_tma_max_cin channels per K slice: a box is 16 bytes wide (one 8-channel plane of the
     // no-swizzle layout), so the TMA unit fetches a 32-byte sector per row and plane and uses half of it; measured (profiles/r02y):
     // the 32-128-channel decoder launches gain 1.5 % (their loader warps' LDGSTS stream no longer paces the epilogue's loads through
