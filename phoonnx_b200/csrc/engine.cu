@@ -646,7 +646,7 @@ int vits_finalize(vits_handle* h) {
             if ((rc = need_f32(h, p + ".pre_w", &cf.pre_w, Fd))) return rc;
             if ((rc = need_f32(h, p + ".pre_b", &cf.pre_b, Fd))) return rc;
             if ((rc = mkdds(h, cf.dds, p + ".convs", Fd))) return rc;
-            if ((rc = mkconv(h, cf.proj, p + ".proj", Fd, 3 * A.num_bins - 1, {0}, true))) return rc;
+            if ((rc = mkconv(h, cf.proj, p + ".proj", Fd, rup(3 * A.num_bins - 1, 16), {0}, true))) return rc;   // packed with zero padding channels
         }
         if (!h->opts.count("dp.ea_m") || !h->opts.count("dp.ea_logs"))
             return fail(h, VITS_E_STATE, "missing options dp.ea_m / dp.ea_logs (ElementwiseAffine of the duration flow)");
@@ -884,7 +884,7 @@ int vits_prepare(vits_handle* h, const int64_t* ids, const int64_t* lengths, int
             h->launches++;
             if ((rc = run_dds(h, cf.dds, d0, d1, y, (int)R, Fd, T))) return rc;
             a = base_args(cf.proj, d0, Fd, 0, hp, 32, 0);
-            if ((rc = launch_conv(h, a, T, false))) return rc;
+            if ((rc = launch_conv_text(h, cf.proj, a, T))) return rc;
             launch_k(k_spline_inverse, (R + 127) / 128, 128, 0, st, hp, 32, z1, (int)R, 1.f / sqrtf((float)Fd));
             h->launches++;
         }

@@ -397,8 +397,16 @@ inline bool pack_model(const Canon& W, const vits_arch& a, std::map<std::string,
         if (!std_conv("dp.pre", "dp.pre", false, true) || !std_conv("dp.proj", "dp.proj", false, true) || !pack_dds("dp.convs", "dp.convs")) return false;
         for (int q = 0; q < a.n_cflows; q++) {
             const std::string f = "dp.flows." + std::to_string(a.cflows[q]);
-            if (!copy(f + ".pre_w", f + ".pre.weight") || !copy(f + ".pre_b", f + ".pre.bias") || !pack_dds(f + ".convs", f + ".convs") ||
-                !std_conv(f + ".proj", f + ".proj", false, false)) return false;
+            if (!copy(f + ".pre_w", f + ".pre.weight") || !copy(f + ".pre_b", f + ".pre.bias") || !pack_dds(f + ".convs", f + ".convs")) return false;
+            // 3 * num_bins - 1 spline parameters padded with zero output channels to a multiple of 16: the projection then runs on the
+            // tensor cores (bf16x3) like the rest of the text side (packing.py)
+            Conv3 pc;
+            if (!conv_std(W, f + ".proj", pc, err)) return false;
+            Conv3 pp; pp.taps = pc.taps; pp.cin = pc.cin; pp.n = rup(pc.n, 16); pp.has_b = true;
+            pp.w.assign((size_t)pp.taps * pp.cin * pp.n, 0.f); pp.b.assign(pp.n, 0.f);
+            for (int t = 0; t < pc.taps; t++) for (int ci = 0; ci < pc.cin; ci++) for (int n = 0; n < pc.n; n++) pp.at(t, ci, n) = pc.at(t, ci, n);
+            if (pc.has_b) for (int n = 0; n < pc.n; n++) pp.b[n] = pc.b[n];
+            pack_conv(o, f + ".proj", pp, false, true);
         }
         const Tensor *m0 = T("dp.flows.0.m"), *l0 = T("dp.flows.0.logs");
         if (!m0 || !l0) return false;

@@ -145,7 +145,13 @@ def pack_model(W: Dict[str, np.ndarray], a: VitsArch, tc: bool = True):
             o[f"dp.flows.{fi}.pre_w"] = np.ascontiguousarray(W[f"dp.flows.{fi}.pre.weight"][:, 0, 0], np.float32)
             o[f"dp.flows.{fi}.pre_b"] = W[f"dp.flows.{fi}.pre.bias"]
             pack_dds(f"dp.flows.{fi}.convs", f"dp.flows.{fi}.convs")
-            pack_conv(o, f"dp.flows.{fi}.proj", *_conv_std(W, f"dp.flows.{fi}.proj"))
+            # 3 * num_bins - 1 = 29 spline parameters: padded with zero output channels to a multiple of 16 so that the projection
+            # runs on the tensor cores like the rest of the text side (bf16x3); k_spline_inverse never reads the padding
+            pw, pb = _conv_std(W, f"dp.flows.{fi}.proj")
+            n16 = _rup(pw.shape[2], 16)
+            pwp = np.zeros(pw.shape[:2] + (n16,), np.float32); pwp[:, :, :pw.shape[2]] = pw
+            pbp = np.zeros((n16,), np.float32); pbp[:pw.shape[2]] = pb
+            pack_conv(o, f"dp.flows.{fi}.proj", pwp, pbp, tc3=tc)
         # the final Flip puts logical channel 0 on logw; ElementwiseAffine indexes logical channels (modules.py:408)
         opts["dp.ea_m"] = float(W["dp.flows.0.m"][0, 0])
         opts["dp.ea_logs"] = float(W["dp.flows.0.logs"][0, 0])
