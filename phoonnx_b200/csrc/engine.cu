@@ -1068,6 +1068,39 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 }
             rb_bf16[i + 1] = ok;
         }
+        // ResBlock1 stages of 32 / 64 channels (`high`): every (conv_{k,d} -> conv_{k,1}) pair of modules.py:301-314 as ONE fused launch
+        // (mrf3_tc.cuh with n_r = 1, rb1): the intermediate never leaves shared memory -- conv by conv these stages move ~1.3 GB per
+        // launch and sit at 50-67 % of HBM bandwidth (profiles/r02l_launch_list_C4.txt).  All pairs of a stage share one tile table
+        // (the halo of the widest second conv).
+        std::vector<int> rb1_fused(A.n_ups + 2, 0);
+        std::vector<std::vector<Mrf3Args>> rb1_args(A.n_ups + 2);
+        std::vector<std::vector<Mrf3Cfg>> rb1_cfg(A.n_ups + 2);
+        for (int i = 0; i < A.n_ups; i++) {
+            const int co = chans[i + 1];
+            if (A.resblock_type != 1 || !rb_bf16[i + 1] || (co != 32 && co != 64) || h->opts["no_fused_rb1"] != 0) continue;
+            int hmax = 0;
+            bool shape_ok = true;
+            for (int j = 0; j < A.n_rbk; j++) { hmax = std::max(hmax, (A.rb_kernels[j] - 1) / 2); if (A.rb_kernels[j] % 2 == 0) shape_ok = false; }
+            if (!shape_ok) continue;
+            const bool many_tiles = (long)Fr * rates[i + 1] / 512 * 2 > (long)h->num_sms;
+            for (int nbp = (co == 32 ? 4 : 2); nbp >= 1 && !rb1_fused[i + 1]; nbp--) {
+                std::vector<Mrf3Args> as; std::vector<Mrf3Cfg> cs;
+                bool all = true;
+                for (int j = 0; j < A.n_rbk && all; j++)
+                    for (int c2 = 0; c2 < A.rb_ndil[j] && all; c2++) {
+                        const ConvP &c1v = h->rb_c1[i * A.n_rbk + j][c2], &c2v = h->rb_c2[i * A.n_rbk + j][c2];
+                        Mrf3Args m; memset(&m, 0, sizeof m);
+                        m.C = co; m.nrb = 1; m.rb1 = 1; m.out_div = 1.f; m.slope = 0.1f;
+                        m.k[0] = A.rb_kernels[j]; m.d1[0] = A.rb_dilations[j][c2]; m.d2[0] = 1;
+                        m.w[0][0] = c1v.wtc; m.w[0][1] = c2v.wtc; m.b[0][0] = c1v.b; m.b[0][1] = c2v.b;
+                        Mrf3Cfg cf;
+                        if (!c1v.wtc || !c2v.wtc || !c1v.b || !c2v.b || c1v.ntaps != m.k[0] || c2v.ntaps != m.k[0] ||
+                            !mrf3_plan(m, cf, nbp, false, use_tma && many_tiles, hmax) || cf.nb != nbp) { all = false; break; }
+                        as.push_back(m); cs.push_back(cf);
+                    }
+                if (all && !as.empty()) { rb1_fused[i + 1] = 1; rb1_args[i + 1] = as; rb1_cfg[i + 1] = cs; }
+            }
+        }
         // ... of which: stages whose second convs run as one summed launch (needs a consumer that takes bf16 rows or fp32)
         std::vector<int> stage_sum2(A.n_ups + 2, 0);
         for (int i = 0; i < A.n_ups; i++) {
@@ -1078,7 +1111,7 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         }
         TileBuilder tb; tb.begin(cu_local.data(), nB);
         for (int i = 0; i <= A.n_ups; i++)
-            tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : 0);
+            tb.add(rates[i], mrf_on[i] == 3 ? mrf3_cfg[i].t_step : (rb1_fused[i] ? rb1_cfg[i][0].t_step : 0));
         if ((rc = ensure(h, h->chunk_meta, tb.host.size() * 4)) || (rc = ensure(h, h->P, (size_t)Fr * C * 4)) ||
             (rc = ensure(h, h->fh, (size_t)Fr * H * 4)) || (rc = ensure(h, h->facts, (size_t)Fr * H * 4)) ||
             (rc = ensure(h, h->fskip, (size_t)Fr * H * 4)) || (rc = ensure(h, h->fidx, (size_t)Fr * 4)) || (rc = ensure(h, h->fpos, (size_t)Fr * 8)) ||
@@ -1255,6 +1288,35 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 a.xb = X1; a.ldxb = nr * co; a.resb = X1; a.ldresb = nr * co; a.resb_slope = 0.1f; a.nresb = nr; a.resb_stride = co;
                 if (i + 1 < A.n_ups) { a.outb = reinterpret_cast<__nv_bfloat16*>(XS); a.outb_slope = 0.1f; out_is_b = true; }
                 if ((rc = launch_conv(h, a, Tout, true))) return rc;
+            } else if (rb1_fused[i + 1]) {
+                // one fused launch per (conv_{k,d} -> conv_{k,1}) pair; x travels between pairs as bf16 lrelu rows, the last pair of
+                // each resblock adds its result into the fp32 stage output (divided by n_r by the last one): the same dataflow as the
+                // conv-by-conv path below, minus the intermediate's round trip and one launch per pair
+                if (Tout.nx > 0) {
+                    if ((rc = ensure(h, h->tdesc, (size_t)Tout.nx * sizeof(int4)))) return rc;
+                    size_t q = 0;
+                    for (int j = 0; j < A.n_rbk; j++) {
+                        const bool first = (j == 0), last = (j == A.n_rbk - 1);
+                        const int nd = A.rb_ndil[j];
+                        for (int c2 = 0; c2 < nd; c2++, q++) {
+                            const bool fin = (c2 == nd - 1);
+                            Mrf3Args m = rb1_args[i + 1][q];
+                            const Mrf3Cfg& cf = rb1_cfg[i + 1][q];
+                            m.cu = Tout.cu; m.tile_cu = Tout.tx; m.B = Tout.B; m.rate = Tout.rate; m.ntiles = Tout.nx;
+                            m.tdesc = ptr<int4>(h->tdesc);
+                            m.xb = (c2 == 0) ? Xb : reinterpret_cast<const __nv_bfloat16*>((c2 & 1) ? Ya : Yb);
+                            m.in_rows = (long)Fr * rates[i + 1];
+                            if (fin) { m.out = XS; m.accumulate = !first; m.out_div = last ? (float)A.n_rbk : 1.f; }
+                            else { m.outb = reinterpret_cast<__nv_bfloat16*>((c2 & 1) ? Yb : Ya); m.outb_slope = 0.1f; }
+                            CUtensorMap tm; memset(&tm, 0, sizeof tm);
+                            if (cf.tma && !make_rows_tmap(&tm, m.xb, m.in_rows, co, cf.box_rows)) return fail(h, VITS_E_CUDA, "rb1 pair: tensor map");
+                            cudaError_t e = (q == 0) ? mrf3_tiles_launch(m, cf, st) : cudaSuccess;      // one tile table for the whole stage
+                            if (e == cudaSuccess) e = mrf3_kernel_launch(m, cf, tm, h->num_sms, st);
+                            if (e != cudaSuccess) return fail(h, VITS_E_CUDA, "rb1 pair launch: %s", cudaGetErrorString(e));
+                            h->launches += (q == 0) ? 2 : 1;
+                        }
+                    }
+                }
             } else
             for (int j = 0; j < A.n_rbk; j++) {
                 const int n = i * A.n_rbk + j;

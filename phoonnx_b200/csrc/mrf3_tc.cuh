@@ -4,7 +4,9 @@
 //     out = ( sum_r  rb_r(x) ) / n_r ,   rb_r(x) = x1 + conv_{k_r, d_r2}(lrelu(x1)) ,  x1 = x + conv_{k_r, d_r1}(lrelu(x))
 //     [last stage only]  audio = tanh( conv_post( lrelu_{0.01}(out) ) )             (models.py:356-366 + modules.py:355-364)
 //
-// in ONE kernel per stage.  Tile geometry as in mrf2_tc.cuh (a CTA owns a window of 128*NB rows, all convs of all
+// in ONE kernel per stage.  The same kernel with n_r = 1 and `rb1` set is one (conv_{k,d} -> conv_{k,1}) PAIR of a ResBlock1
+// (modules.py:301-314: xt = c1(lrelu x); xt = c2(lrelu xt); x = xt + x): the only differences are that the first convolution carries no
+// residual and the second adds x instead of x1 -- the `high` preset's 64- and 32-channel stages, round 2.  Tile geometry as in mrf2_tc.cuh (a CTA owns a window of 128*NB rows, all convs of all
 // resblocks run on the same M=128 blocks, only the central rows are stored).  What v3 changes, after the r01 phase
 // timeline of v2 (profiles/r01b_mma_probe_and_mrf2_timeline.log: tensor pipe busy 11.8k of a 22.4k-cycle tile, the
 // rest a serial C1(r) -> E1(r) -> C2(r) chain; and a separate polyphase ConvTranspose kernel that wrote and re-read
@@ -63,6 +65,8 @@ struct Mrf3Args {
     long in_rows;                                                // host side: rows of the input array (xb, or hb in mode U), for its tensor map
     const int4* tdesc;                                           // per tile {first row of the utterance, its rows, o0, -}
     float out_div;  float slope;  int interleave;                // issue order of the convs (mrf3_step)
+    int rb1;                                                     // ResBlock1 pair (modules.py:301-314): t = conv1(lrelu x), out = x + conv2(lrelu t)  [n_r must be 1]
+    int accumulate;                                              // fp32 `out` only: out = (out + result) / out_div (per-resblock results summed in place)
     float* out;                                                  // fp32 [rows, C]                       (or null)
     __nv_bfloat16* outb;  float outb_slope;                      // bf16 lrelu_{outb_slope}(out) [rows, C] (or null)
     const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
@@ -341,8 +345,10 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                                 const float2 li = __fmul2_rn(l, inv_slope2);
                                 const float2 xv = make_float2(fminf(l.x, li.x), fminf(l.y, li.y));
                                 const float2 vb = __fadd2_rn(make_float2(v[8 * h8 + 2 * p2], v[8 * h8 + 2 * p2 + 1]), *reinterpret_cast<const float2*>(b1 + ch));
-                                const float2 x1p = __fadd2_rn(vb, xv);
-                                xacc[ch >> 1] = __fadd2_rn(xacc[ch >> 1], x1p);
+                                // ResBlock2: x1 = x + conv1(..) is both the next operand and the residual; ResBlock1 pair: the operand is
+                                // conv1(..) alone and the residual of the pair is x itself
+                                const float2 x1p = a.rb1 ? vb : __fadd2_rn(vb, xv);
+                                xacc[ch >> 1] = __fadd2_rn(xacc[ch >> 1], a.rb1 ? xv : x1p);
                                 const float2 xs = __fmul2_rn(x1p, slope2);
                                 // conv2 zero-pads x1 beyond the utterance
                                 pk[ch >> 1] = inr ? tc::pack_bf16(fmaxf(x1p.x, xs.x), fmaxf(x1p.y, xs.y)) : 0u;
@@ -418,11 +424,12 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                         if (st) {
 #pragma unroll
                             for (int qd = 0; qd < 4; qd++) {
-                                float4 ov;
-                                ov.x = (v[4 * qd + 0] + xacc[(n0 + 4 * qd) >> 1].x) * inv_div;
-                                ov.y = (v[4 * qd + 1] + xacc[(n0 + 4 * qd) >> 1].y) * inv_div;
-                                ov.z = (v[4 * qd + 2] + xacc[(n0 + 4 * qd + 2) >> 1].x) * inv_div;
-                                ov.w = (v[4 * qd + 3] + xacc[(n0 + 4 * qd + 2) >> 1].y) * inv_div;
+                                float4 ov, old = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (a.accumulate) old = *(reinterpret_cast<const float4*>(orow + n0) + qd);
+                                ov.x = (v[4 * qd + 0] + xacc[(n0 + 4 * qd) >> 1].x + old.x) * inv_div;
+                                ov.y = (v[4 * qd + 1] + xacc[(n0 + 4 * qd) >> 1].y + old.y) * inv_div;
+                                ov.z = (v[4 * qd + 2] + xacc[(n0 + 4 * qd + 2) >> 1].x + old.z) * inv_div;
+                                ov.w = (v[4 * qd + 3] + xacc[(n0 + 4 * qd + 2) >> 1].y + old.w) * inv_div;
                                 *(reinterpret_cast<float4*>(orow + n0) + qd) = ov;
                             }
                         }
@@ -681,7 +688,8 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post, bool use_tma = true) {
+// min_hmax: plan with at least this second-conv halo, so that kernels of one stage with different kernel sizes share one tile table
+static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post, bool use_tma = true, int min_hmax = 0) {
     memset(&c, 0, sizeof c);
     if (a.C != 32 && a.C != 64) return false;
     if (a.nrb < 1 || a.nrb > MRF3_MAX_RB) return false;
@@ -694,6 +702,8 @@ static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fu
         hmax = h2 > hmax ? h2 : hmax; h1max = h1 > h1max ? h1 : h1max;
         npieces += 2 * a.k[r];
     }
+    if (hmax < min_hmax) hmax = min_hmax;
+    if (a.rb1 && a.nrb != 1) return false;
     c.hmax = hmax; c.h1max = h1max; c.npieces = npieces;
     c.slot_bytes = a.C * a.C * 2;
     c.post_halo = fuse_post ? (MRF3_POST_K - 1) / 2 : 0;

@@ -572,3 +572,32 @@ def test_resblock1_stages_on_bf16_rows_match_fp32_rows(lib, tmp_path_factory):
     # measured 44.9 dB between the two variants on these (short, ragged) utterances; against the fp32 oracle the bf16-row path reads
     # 61.6 dB on the `high` preset (profiles/r02_snr_report.txt) and is gated at 40 dB per utterance by test_gpu_baseline_configs C4
     assert snr_db(outs[1][0], outs[0][0]) > 40.0, snr_db(outs[1][0], outs[0][0])
+
+
+def test_fused_resblock1_pairs_equal_conv_by_conv(lib, tmp_path_factory):
+    """`high` preset, 64- and 32-channel stages: each (conv_{k,d} -> conv_{k,1}) pair of ResBlock1 (modules.py:301-314) as ONE fused
+    launch (default) vs two conv launches with the intermediate as bf16 rows in HBM (`no_fused_rb1`).  Same operands, same bf16
+    rounding points (the intermediate and the pair's output are bf16 lrelu rows either way); the accumulation order inside a
+    convolution differs (per tap vs per K slice), so the comparison is an SNR, far above the gate."""
+    from phoonnx_b200.session import B200Session
+    p, arch, _ = _voice(tmp_path_factory, "high", 1)
+    rs = np.random.RandomState(13)
+    lens = np.array([97, 3, 160, 41, 1, 2, 130], np.int64)
+    B, T = len(lens), int(lens.max())
+    ids = rs.randint(0, arch.n_vocab, (B, T)).astype(np.int64)
+    nd = rs.randn(B, 2, T).astype(np.float32)
+    nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
+    feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
+    outs = []
+    for opt, chunk in ((1, None), (0, None), (0, 700)):
+        sess = B200Session(p, precision="bf16")
+        sess.engine.set_option("no_fused_rb1", opt)
+        if chunk:
+            sess.engine.set_option("max_chunk_frames", chunk)
+        a, alen = sess.synthesize_packed(feed)
+        outs.append((np.array(a), np.array(alen)))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], outs[2][1])
+    assert np.isfinite(outs[1][0]).all()
+    assert snr_db(outs[1][0], outs[0][0]) > 55.0, snr_db(outs[1][0], outs[0][0])
+    assert np.array_equal(outs[1][0], outs[2][0])              # chunking is invisible to the fused path too
+
