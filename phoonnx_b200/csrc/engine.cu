@@ -1077,13 +1077,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
         std::vector<std::vector<Mrf3Cfg>> rb1_cfg(A.n_ups + 2);
         for (int i = 0; i < A.n_ups; i++) {
             const int co = chans[i + 1];
-            if (A.resblock_type != 1 || !rb_bf16[i + 1] || (co != 32 && co != 64) || h->opts["no_fused_rb1"] != 0) continue;
+            if (A.resblock_type != 1 || !rb_bf16[i + 1] || (co != 32 && co != 64 && co != 128) || h->opts["no_fused_rb1"] != 0) continue;
+            if (co == 128 && h->opts["no_fused_rb1_128"] != 0) continue;
             int hmax = 0;
             bool shape_ok = true;
             for (int j = 0; j < A.n_rbk; j++) { hmax = std::max(hmax, (A.rb_kernels[j] - 1) / 2); if (A.rb_kernels[j] % 2 == 0) shape_ok = false; }
             if (!shape_ok) continue;
             const bool many_tiles = (long)Fr * rates[i + 1] / 512 * 2 > (long)h->num_sms;
-            for (int nbp = (co == 32 ? 4 : 2); nbp >= 1 && !rb1_fused[i + 1]; nbp--) {
+            for (int nbp = (co == 32 ? 4 : (co == 64 ? 2 : 1)); nbp >= 1 && !rb1_fused[i + 1]; nbp--) {
                 std::vector<Mrf3Args> as; std::vector<Mrf3Cfg> cs;
                 bool all = true;
                 for (int j = 0; j < A.n_rbk && all; j++)

@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
 // min_hmax: plan with at least this second-conv halo, so that kernels of one stage with different kernel sizes share one tile table
 static inline bool mrf3_plan(const Mrf3Args& a, Mrf3Cfg& c, int nb_pref, bool fuse_post, bool use_tma = true, int min_hmax = 0) {
     memset(&c, 0, sizeof c);
-    if (a.C != 32 && a.C != 64) return false;
+    if (a.C != 32 && a.C != 64 && !(a.C == 128 && a.rb1)) return false;      // 128 channels: ResBlock1 pairs only (one M block per tile)
     if (a.nrb < 1 || a.nrb > MRF3_MAX_RB) return false;
     const bool modeU = a.up_u != 0;
     if (modeU && (a.up_u != 4 || a.up_cin % 16 || a.up_cin < 16 || a.up_cin > 128 || (a.up_u / 2) * a.C > 256)) return false;
@@ -799,5 +799,6 @@ static inline cudaError_t mrf3_tiles_launch(const Mrf3Args& a, const Mrf3Cfg& c,
 static inline cudaError_t mrf3_kernel_launch(const Mrf3Args& a, const Mrf3Cfg& c, const CUtensorMap& tmap, int num_sms, cudaStream_t st) {
     if (a.C == 32) return mrf3_launch_t<32>(a, c, tmap, num_sms, st);
     if (a.C == 64) return mrf3_launch_t<64>(a, c, tmap, num_sms, st);
+    if (a.C == 128) return mrf3_launch_t<128>(a, c, tmap, num_sms, st);
     return cudaErrorInvalidConfiguration;
 }
