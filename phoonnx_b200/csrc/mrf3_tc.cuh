@@ -37,6 +37,7 @@
 //     the execution of its own MMAs -- measured 60-75 cycles per N=32 MMA issued against 40 executed -- but it does
 //     overlap the other warp's.
 //
+// C = 128 (ResBlock1 pairs only): one M block per tile, 16 epilogue warps = 4 lane quadrants x 4 column groups, weights through the ring.
 // Warp roles (640 threads): warps 0-15 epilogues (TMEM lane quadrant = warp % 4, work item = warp / 4), warp 16
 // elected lane = weight producer (+ TMEM allocation), warps 17 and 19 elected lane = MMA issuers, warp 18 = input-row loader.
 #pragma once
