@@ -1293,6 +1293,14 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                 // one fused launch per (conv_{k,d} -> conv_{k,1}) pair; x travels between pairs as bf16 lrelu rows, the last pair of
                 // each resblock adds its result into the fp32 stage output (divided by n_r by the last one): the same dataflow as the
                 // conv-by-conv path below, minus the intermediate's round trip and one launch per pair
+                // stages followed by another ConvTranspose hand over bf16 rows (below); the last stage feeds conv_post in fp32
+                const bool rows_out = (i + 1 < A.n_ups) && A.n_rbk >= 2 && A.n_rbk <= 3 && h->opts["no_rb1_rows_out"] == 0;
+                __nv_bfloat16 *R0 = reinterpret_cast<__nv_bfloat16*>(T1b), *R1 = nullptr;
+                if (rows_out) {
+                    if ((rc = ensure(h, h->sX1b, (size_t)Fr * rates[i + 1] * co * 2))) return rc;
+                    R1 = ptr<__nv_bfloat16>(h->sX1b);
+                    out_is_b = true;
+                }
                 if (Tout.nx > 0) {
                     if ((rc = ensure(h, h->tdesc, (size_t)Tout.nx * sizeof(int4)))) return rc;
                     size_t q = 0;
@@ -1307,7 +1315,15 @@ int vits_decode(vits_handle* h, const float* noise_z, int64_t z_stride, int32_t 
                             m.tdesc = ptr<int4>(h->tdesc);
                             m.xb = (c2 == 0) ? Xb : reinterpret_cast<const __nv_bfloat16*>((c2 & 1) ? Ya : Yb);
                             m.in_rows = (long)Fr * rates[i + 1];
-                            if (fin) { m.out = XS; m.accumulate = !first; m.out_div = last ? (float)A.n_rbk : 1.f; }
+                            if (fin && rows_out) {
+                                // the per-resblock results leave as plain bf16 rows; the last resblock's last pair adds them, divides by n_r
+                                // and writes the next ConvTranspose's bf16 lrelu operand rows -- 10 bytes per value of stage output instead
+                                // of 24 (three fp32 read-modify-writes + the fp32 read of the consumer; r02zj launch list: ~0.45 ms of
+                                // every accumulating launch)
+                                if (!last) { m.outb = (j == 0) ? R0 : R1; m.outb_slope = 1.f; }
+                                else { m.addb[0] = R0; m.addb[1] = R1; m.naddb = A.n_rbk - 1; m.out_div = (float)A.n_rbk;
+                                       m.outb = reinterpret_cast<__nv_bfloat16*>(XS); m.outb_slope = 0.1f; }
+                            } else if (fin) { m.out = XS; m.accumulate = !first; m.out_div = last ? (float)A.n_rbk : 1.f; }
                             else { m.outb = reinterpret_cast<__nv_bfloat16*>((c2 & 1) ? Yb : Ya); m.outb_slope = 0.1f; }
                             CUtensorMap tm; memset(&tm, 0, sizeof tm);
                             if (cf.tma && !make_rows_tmap(&tm, m.xb, m.in_rows, co, cf.box_rows)) return fail(h, VITS_E_CUDA, "rb1 pair: tensor map");

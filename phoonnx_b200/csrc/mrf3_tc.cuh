@@ -68,6 +68,8 @@ struct Mrf3Args {
     float out_div;  float slope;  int interleave;                // issue order of the convs (mrf3_step)
     int rb1;                                                     // ResBlock1 pair (modules.py:301-314): t = conv1(lrelu x), out = x + conv2(lrelu t)  [n_r must be 1]
     int accumulate;                                              // fp32 `out` only: out = (out + result) / out_div (per-resblock results summed in place)
+    const __nv_bfloat16* addb[2];  int naddb;                    // up to two more row arrays [rows, C] (plain bf16 values) added to the result before out_div:
+                                                                 // the other resblocks' results when the LAST resblock's last pair finishes a ResBlock1 stage
     float* out;                                                  // fp32 [rows, C]                       (or null)
     __nv_bfloat16* outb;  float outb_slope;                      // bf16 lrelu_{outb_slope}(out) [rows, C] (or null)
     const float* post_w;  float post_slope;  float* audio;      // fused conv_post (last stage) or null
@@ -381,6 +383,22 @@ __global__ void __launch_bounds__(MRF3_THREADS, 1) k_mrf3_tc(const Mrf3Args a, c
                 e0_stage(tile + gridDim.x, it + 1);
             }
             // ---- final epilogue: out = (acc2 + sum_r(x1_r + b2_r)) / n_r on the central rows
+            if (a.naddb && active && inr && (wr >= c.hmax) && (wr < c.hmax + c.t_out)) {
+                // the other resblocks' results of this row (bf16, written by their last pairs): fetched while conv2 is still running
+                for (int j = 0; j < a.naddb; j++) {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.addb[j] + (row0 + tm) * C + 32 * cg);
+                    uint4 w4[4];
+#pragma unroll
+                    for (int n8 = 0; n8 < 4; n8++) w4[n8] = __ldg(src + n8);
+#pragma unroll
+                    for (int n8 = 0; n8 < 4; n8++) {
+                        const uint32_t ww[4] = {w4[n8].x, w4[n8].y, w4[n8].z, w4[n8].w};
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; p2++)
+                            xacc[4 * n8 + p2] = __fadd2_rn(xacc[4 * n8 + p2], make_float2(tc::bf16_lo_f(ww[p2]), tc::bf16_hi_f(ww[p2])));
+                    }
+                }
+            }
             tc::mbar_wait(bar_c2, n_c2 & 1); n_c2++;
             MRF3_STAMP(it, 16);
             tc::tc_fence_after();

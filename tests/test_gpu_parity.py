@@ -575,10 +575,12 @@ def test_resblock1_stages_on_bf16_rows_match_fp32_rows(lib, tmp_path_factory):
 
 
 def test_fused_resblock1_pairs_equal_conv_by_conv(lib, tmp_path_factory):
-    """`high` preset, 64- and 32-channel stages: each (conv_{k,d} -> conv_{k,1}) pair of ResBlock1 (modules.py:301-314) as ONE fused
-    launch (default) vs two conv launches with the intermediate as bf16 rows in HBM (`no_fused_rb1`).  Same operands, same bf16
-    rounding points (the intermediate and the pair's output are bf16 lrelu rows either way); the accumulation order inside a
-    convolution differs (per tap vs per K slice), so the comparison is an SNR, far above the gate."""
+    """`high` preset, 128- / 64- / 32-channel stages: each (conv_{k,d} -> conv_{k,1}) pair of ResBlock1 (modules.py:301-314) as ONE fused
+    launch (default) vs two conv launches with the intermediate as bf16 rows in HBM (`no_fused_rb1`).  With `no_rb1_rows_out` the fused
+    path has the same rounding points as the conv-by-conv one (intermediate and pair output are bf16 lrelu rows, per-resblock results
+    accumulate in fp32) and only the accumulation order inside a convolution differs; by default the per-resblock results of a stage
+    that feeds another ConvTranspose also travel as bf16 rows and are combined by the last pair -- one more bf16 rounding per
+    resblock, measured against the fp32 oracle at 61.7 dB either way (profiles/r02_snr_report.txt, tools/snr_report.py)."""
     from phoonnx_b200.session import B200Session
     p, arch, _ = _voice(tmp_path_factory, "high", 1)
     rs = np.random.RandomState(13)
@@ -588,16 +590,17 @@ def test_fused_resblock1_pairs_equal_conv_by_conv(lib, tmp_path_factory):
     nd = rs.randn(B, 2, T).astype(np.float32)
     nz = rs.randn(B, arch.inter, 2600).astype(np.float32)
     feed = {"input": ids, "input_lengths": lens, "scales": SCALES, "noise_dp": nd, "noise_z": nz}
-    outs = []
-    for opt, chunk in ((1, None), (0, None), (0, 700)):
+    outs = {}
+    for name, opts in (("conv_by_conv", {"no_fused_rb1": 1}), ("fused_fp32_sum", {"no_rb1_rows_out": 1}), ("fused", {}),
+                       ("fused_chunked", {"max_chunk_frames": 700})):
         sess = B200Session(p, precision="bf16")
-        sess.engine.set_option("no_fused_rb1", opt)
-        if chunk:
-            sess.engine.set_option("max_chunk_frames", chunk)
+        for k, v in opts.items():
+            sess.engine.set_option(k, v)
         a, alen = sess.synthesize_packed(feed)
-        outs.append((np.array(a), np.array(alen)))
-    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], outs[2][1])
-    assert np.isfinite(outs[1][0]).all()
-    assert snr_db(outs[1][0], outs[0][0]) > 55.0, snr_db(outs[1][0], outs[0][0])
-    assert np.array_equal(outs[1][0], outs[2][0])              # chunking is invisible to the fused path too
-
+        outs[name] = (np.array(a), np.array(alen))
+    for name in outs:
+        assert np.array_equal(outs[name][1], outs["conv_by_conv"][1]) and np.isfinite(outs[name][0]).all(), name
+    ref = outs["conv_by_conv"][0]
+    assert snr_db(outs["fused_fp32_sum"][0], ref) > 55.0, snr_db(outs["fused_fp32_sum"][0], ref)
+    assert snr_db(outs["fused"][0], ref) > 45.0, snr_db(outs["fused"][0], ref)
+    assert np.array_equal(outs["fused"][0], outs["fused_chunked"][0])      # chunking is invisible to the fused path too
