@@ -50,6 +50,14 @@ def test_mas_header_symbols_are_exported(built_lib):
         assert hasattr(lib, n), n
 
 
+def test_mas_flag_values_match_the_header():
+    from phoonnx_b200 import monotonic_align as ma
+    hdr = open(os.path.join(ROOT, "include", "mas_b200.h")).read()
+    flags = dict(re.findall(r"#define\s+(MAS_[A-Z_0-9]+)\s+(0x[0-9a-fA-F]+)", hdr))
+    assert int(flags["MAS_DEVICE_PTRS"], 16) == ma.MAS_DEVICE_PTRS and int(flags["MAS_PATH_F32"], 16) == ma.MAS_PATH_F32
+    assert int(flags["MAS_TIMED"], 16) == ma.MAS_TIMED and int(flags["MAS_ROW_KERNEL"], 16) == ma.MAS_ROW_KERNEL
+
+
 def test_mas_refuses_cpu_tensors(built_lib):
     import torch
     from phoonnx_b200 import monotonic_align
