@@ -36,6 +36,19 @@ int vits_test_mma_probe_mode(vits_handle* h, int mode, int n, int iters, int nd,
 int vits_test_file_arch(const char* path, vits_arch* arch, char* err, size_t err_cap);
 int64_t vits_test_file_blob(const char* path, const char* name, void* out, int64_t cap, int* dtype);
 
+/* Host-side launch plans of the two tensor-core kernels, without a GPU (the planners are plain host code): the CPU tests check their
+ * invariants (shared-memory budget, TMA box geometry, tile steps shared by the kernels of one stage).
+ * vits_test_mrf3_plan: one fused stage / ResBlock1 pair of `C` channels with `nrb` resblocks of kernel sizes k[], first / second
+ * dilations d1[], d2[]; up_cin > 0: with the fused ConvTranspose (u = 4) from up_cin channels.  out[16] receives
+ * {nb, span, hmax, h1max, t_out, t_step, rx, rx1, smem_bytes, tmem_cols, nstages, resident, tma, nboxes, box_rows, u_rows}; returns 1 when
+ * the shape can be planned, 0 when not.
+ * vits_test_conv_plan: k_conv_tc for cin -> n channels with `ntaps` taps at offsets toff[], input as bf16 operand rows (xb != 0, xb_rows
+ * rows) or fp32, split3 = the bf16x3 text-side form, over `ntiles` 128-row tiles on `num_sms` SMs.  out[16] receives
+ * {ntile, rows_a, rows_need, a_bytes, slot_bytes, nstages, resident, nabuf, smem_bytes, tmem_cols, tma, nboxes, box_rows, nepi, nload, naccbuf}. */
+int vits_test_mrf3_plan(int C, int nrb, const int* k, const int* d1, const int* d2, int rb1, int up_cin, int nb_pref, int fuse_post,
+                        int use_tma, int min_hmax, int* out);
+int vits_test_conv_plan(int cin, int n, int ntaps, const int* toff, int xb, long xb_rows, int split3, int ntiles, int num_sms, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -512,6 +512,37 @@ int vits_open(const char* path, int device_id, int precision, vits_handle** out,
     return VITS_OK;
 }
 
+int vits_test_mrf3_plan(int C, int nrb, const int* k, const int* d1, const int* d2, int rb1, int up_cin, int nb_pref, int fuse_post,
+                        int use_tma, int min_hmax, int* out) {
+    if (!k || !d1 || !d2 || !out || nrb < 1 || nrb > MRF3_MAX_RB) return 0;
+    Mrf3Args m; memset(&m, 0, sizeof m);
+    m.C = C; m.nrb = nrb; m.rb1 = rb1; m.out_div = (float)nrb; m.slope = 0.1f;
+    for (int j = 0; j < nrb; j++) { m.k[j] = k[j]; m.d1[j] = d1[j]; m.d2[j] = d2[j]; }
+    if (up_cin > 0) { m.up_u = 4; m.up_cin = up_cin; }
+    Mrf3Cfg c;
+    if (!mrf3_plan(m, c, nb_pref, fuse_post != 0, use_tma != 0, min_hmax)) return 0;
+    const int v[16] = {c.nb, c.span, c.hmax, c.h1max, c.t_out, c.t_step, c.rx, c.rx1, c.smem_bytes, c.tmem_cols, c.nstages, c.resident,
+                       c.tma, c.nboxes, c.box_rows, c.u_rows};
+    memcpy(out, v, sizeof v);
+    return 1;
+}
+
+int vits_test_conv_plan(int cin, int n, int ntaps, const int* toff, int xb, long xb_rows, int split3, int ntiles, int num_sms, int* out) {
+    if (!toff || !out || ntaps < 1 || ntaps > CONV_MAX_TAPS) return 0;
+    ConvArgs a; memset(&a, 0, sizeof a);
+    a.cin = cin; a.n = n; a.npad = rup(n, 4); a.npad16 = rup(n, 16); a.ntaps = ntaps;
+    for (int i = 0; i < ntaps; i++) a.toff[i] = toff[i];
+    a.nks = 1; a.split3 = split3; a.ntiles = ntiles; a.ldo = a.npad16; a.ldx = cin; a.ldxb = cin;
+    static const __nv_bfloat16 dummy[8] = {};
+    if (xb) { a.xb = dummy; a.xb_rows = xb_rows; }
+    TcCfg c; memset(&c, 0, sizeof c);
+    if (!conv_tc_plan(a, c, num_sms)) return 0;
+    const int v[16] = {c.ntile, c.rows_a, c.rows_need, c.a_bytes, c.slot_bytes, c.nstages, c.resident, c.nabuf, c.smem_bytes, c.tmem_cols,
+                       c.tma, c.nboxes, c.box_rows, c.nepi, c.nload, c.naccbuf};
+    memcpy(out, v, sizeof v);
+    return 1;
+}
+
 int vits_test_file_arch(const char* path, vits_arch* arch, char* err, size_t err_cap) {
     if (!path || !arch) return VITS_E_INVALID;
     vf::Voice v;

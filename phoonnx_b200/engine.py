@@ -145,7 +145,8 @@ EXPORTED_SYMBOLS = (
     "vits_set_output_offsets", "vits_host_register", "vits_host_unregister",
 )
 # include/vits_b200_test.h: test-only hooks, not part of the drop-in boundary
-TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe", "vits_test_mma_probe_mode", "vits_test_file_arch", "vits_test_file_blob")
+TEST_SYMBOLS = ("vits_test_conv", "vits_test_mma_probe", "vits_test_mma_probe_mode", "vits_test_file_arch", "vits_test_file_blob",
+                "vits_test_mrf3_plan", "vits_test_conv_plan")
 VITS_OUT_ASYNC = 0x100
 
 _DT = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.int32): 2}
