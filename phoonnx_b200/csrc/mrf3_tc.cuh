@@ -6,8 +6,9 @@
 //
 // in ONE kernel per stage.  The same kernel with n_r = 1 and `rb1` set is one (conv_{k,d} -> conv_{k,1}) PAIR of a ResBlock1
 // (modules.py:301-314: xt = c1(lrelu x); xt = c2(lrelu xt); x = xt + x): the only differences are that the first convolution carries no
-// residual and the second adds x instead of x1 -- the `high` preset's 64- and 32-channel stages, round 2.  Tile geometry as in mrf2_tc.cuh (a CTA owns a window of 128*NB rows, all convs of all
-// resblocks run on the same M=128 blocks, only the central rows are stored).  What v3 changes, after the r01 phase
+// residual and the second adds x instead of x1 -- the `high` preset's 128-, 64- and 32-channel stages, round 2.
+// Tile geometry: a CTA owns a window of 128*NB rows, all convs of all resblocks run on the same M=128 blocks, only the central rows
+// are stored.  What v3 changes, after the r01 phase
 // timeline of v2 (profiles/r01b_mma_probe_and_mrf2_timeline.log: tensor pipe busy 11.8k of a 22.4k-cycle tile, the
 // rest a serial C1(r) -> E1(r) -> C2(r) chain; and a separate polyphase ConvTranspose kernel that wrote and re-read
 // 64 KB of fp32 per frame at 2.6 TB/s):
